@@ -1,0 +1,205 @@
+/*
+ * srj_b200.h -- C ABI of libsrj_b200.so: the B200-native (sm_100a) replacement for the
+ * row<->columnar + Spark row-hash hot path of NVIDIA/spark-rapids-jni.
+ *
+ * This is the drop-in boundary.  Every entry point below is what the reference's
+ * JNI layer for this path would bind; each cites the reference interface it replaces.  Paths are
+ * relative to the reference tree; RC = src/main/cpp/src/row_conversion.cu.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All data pointers are DEVICE pointers owned by the
+ *     caller (the JNI shim allocates them with rmm exactly where the reference does); functions
+ *     whose name ends in _host take HOST pointers and stage through the device themselves.
+ *   - Every function returns SRJ_OK (0) or a negative srj_status; nothing throws across the
+ *     boundary.  srj_last_error() returns a thread-local message for the last failure.
+ *     The JNI shim maps codes to the reference's exception classes:
+ *       SRJ_EINVAL/SRJ_EUNSUPPORTED -> ai.rapids.cudf.CudfException (cudf::logic_error, error.hpp:233-239)
+ *       SRJ_EOVERFLOW -> CudfColumnSizeOverflowException, SRJ_ENOMEM -> OutOfMemoryError,
+ *       SRJ_ECUDA -> CudaException / CudaFatalException.
+ *   - Work is enqueued on the caller's `stream` (the reference uses the per-thread default
+ *     stream, CMakeLists.txt:322-326); functions are re-entrant and keep no global mutable state.
+ *     Functions documented "synchronizes" block until `stream` is idle because they return
+ *     host-visible sizes (the reference synchronises at the same points: RC:1534-1544, 2389).
+ *   - Bitmasks are cudf bitmasks: uint32 words, bit (i % 32) of word (i / 32), 1 = valid
+ *     (thirdparty/cudf/cpp/include/cudf/utilities/bit.hpp:48-106).  NULL mask = all valid.
+ *   - Row counts are int64 at this ABI; the JNI shim passes cudf::size_type (int32) values.
+ */
+#ifndef SRJ_B200_H
+#define SRJ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SRJ_API __attribute__((visibility("default")))
+#else
+#define SRJ_API
+#endif
+
+/* ---- status codes --------------------------------------------------------------------------- */
+typedef enum srj_status {
+  SRJ_OK           = 0,
+  SRJ_EINVAL       = -1, /* bad argument / layout precondition (CUDF_EXPECTS -> cudf::logic_error)  */
+  SRJ_EUNSUPPORTED = -2, /* type not supported on this path (RowConversion.java:131, hive_hash.cu:63) */
+  SRJ_EOVERFLOW    = -3, /* a column would exceed the int32 size_type limit (std::overflow_error)    */
+  SRJ_ECUDA        = -4, /* CUDA runtime error (cudf::cuda_error)                                    */
+  SRJ_ENOMEM       = -5  /* device allocation failed (rmm::out_of_memory)                            */
+} srj_status;
+
+/* ---- cudf type ids: thirdparty/cudf/cpp/include/cudf/types.hpp:191-224 ----------------------- */
+typedef enum srj_type_id {
+  SRJ_EMPTY = 0, SRJ_INT8, SRJ_INT16, SRJ_INT32, SRJ_INT64, SRJ_UINT8, SRJ_UINT16, SRJ_UINT32, SRJ_UINT64,
+  SRJ_FLOAT32, SRJ_FLOAT64, SRJ_BOOL8, SRJ_TIMESTAMP_DAYS, SRJ_TIMESTAMP_SECONDS,
+  SRJ_TIMESTAMP_MILLISECONDS, SRJ_TIMESTAMP_MICROSECONDS, SRJ_TIMESTAMP_NANOSECONDS,
+  SRJ_DURATION_DAYS, SRJ_DURATION_SECONDS, SRJ_DURATION_MILLISECONDS, SRJ_DURATION_MICROSECONDS,
+  SRJ_DURATION_NANOSECONDS, SRJ_DICTIONARY32, SRJ_STRING, SRJ_LIST, SRJ_DECIMAL32, SRJ_DECIMAL64,
+  SRJ_DECIMAL128, SRJ_STRUCT, SRJ_NUM_TYPE_IDS
+} srj_type_id;
+
+/*
+ * srj_column: the cudf::column_view fields this path reads/writes
+ * (thirdparty/cudf/cpp/include/cudf/column/column_view.hpp:237-244).  One struct serves inputs and
+ * outputs; for outputs the caller allocates every buffer and the library fills it.
+ *   fixed-width column : data = size * size_of(type) bytes
+ *   STRING column      : data = chars, offsets = int32[size + 1]   (RC:1919-1923, 2421-2428)
+ * Sliced views (offset != 0) are not supported, as in the reference (RC:1809-1811).
+ */
+typedef struct srj_column {
+  int32_t type_id;     /* srj_type_id                                        */
+  int32_t scale;       /* decimals only; carried, never interpreted           */
+  int64_t size;        /* rows                                                */
+  void* data;          /* device                                              */
+  uint32_t* null_mask; /* device, ceil(size/32) words, or NULL (= all valid)  */
+  int32_t* offsets;    /* device, STRING only                                 */
+} srj_column;
+
+/* One output batch of convert_to_rows = one LIST<INT8> column of <= INT32_MAX bytes (RC:174-190). */
+typedef struct srj_row_batch {
+  int64_t row_start; /* first table row in this batch                     */
+  int64_t row_count; /* rows in this batch (multiple of 32 except the last, RC:1515-1517) */
+  int64_t num_bytes; /* size of the INT8 child                            */
+} srj_row_batch;
+
+/* ---- library --------------------------------------------------------------------------------- */
+SRJ_API const char* srj_version(void);
+SRJ_API const char* srj_last_error(void);
+SRJ_API const char* srj_status_string(int status);
+
+/* ---- layout: compute_column_information, RC:1332-1371 ---------------------------------------- */
+typedef struct srj_layout {
+  int32_t num_columns;
+  int32_t num_string_columns;
+  int32_t validity_offset;    /* byte offset of the validity bytes in a row                 */
+  int32_t size_per_row;       /* validity_offset + ceil(ncols/8): UNPADDED fixed+validity   */
+  int32_t fixed_row_size;     /* round_up(size_per_row, 8): the row stride of a fixed-width-only table */
+  int32_t reserved;
+} srj_layout;
+
+/* col_starts/col_sizes (each num_columns entries) may be NULL. */
+SRJ_API int srj_compute_layout(const int32_t* type_ids, int32_t num_columns, srj_layout* out,
+                               int32_t* col_starts, int32_t* col_sizes);
+
+/*
+ * A plan caches the per-schema device metadata (column starts/sizes, width-class schedule) so the
+ * hot calls do no host->device metadata traffic.  Create once per schema per device (the JNI shim
+ * keeps a small schema-keyed cache); destroy when done.  Plans are immutable => thread-safe.
+ */
+typedef struct srj_plan srj_plan;
+SRJ_API int srj_plan_create(const int32_t* type_ids, const int32_t* scales /* may be NULL */,
+                            int32_t num_columns, srj_plan** out);
+SRJ_API void srj_plan_destroy(srj_plan* plan);
+SRJ_API int srj_plan_layout(const srj_plan* plan, srj_layout* out);
+
+/* ---- convert_to_rows: RowConversion.convertToRows / RC:1994-2055 ------------------------------ */
+/*
+ * Step 1 (synchronizes when the table has STRING columns): per-row sizes (RC:201-257) and the
+ * <= 2 GiB / 32-row batch cut (build_batches, RC:1466-1557).  `workspace` must hold
+ * srj_to_rows_workspace_bytes(plan, num_rows) bytes (0 for fixed-width-only tables) and must be
+ * passed unchanged to step 2.  Writes up to max_batches entries; *num_batches gets the count
+ * (0 for an empty table: the caller then returns one empty LIST column).
+ */
+SRJ_API int64_t srj_to_rows_workspace_bytes(const srj_plan* plan, int64_t num_rows);
+SRJ_API int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64_t num_rows,
+                                     void* workspace, srj_row_batch* batches, int32_t max_batches,
+                                     int32_t* num_batches, void* stream);
+/*
+ * Step 2 (async): fill each batch's LIST offsets child (int32[row_count + 1]) and INT8 data child
+ * (num_bytes).  Fuses copy_to_rows + copy_validity_to_rows + copy_strings_to_rows
+ * (RC:574-688, 706-798, 816-861).  Padding bytes are written as zeros (undefined in the reference).
+ */
+SRJ_API int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t num_rows,
+                                const void* workspace, const srj_row_batch* batches,
+                                int32_t num_batches, int32_t* const* batch_offsets,
+                                uint8_t* const* batch_data, void* stream);
+
+/* ---- convert_from_rows: RowConversion.convertFromRows / RC:2149-2441 -------------------------- */
+/*
+ * Phase 1 (async): fixed-width columns, every column's validity mask, exact null counts
+ * (replaces fixup_null_counts, RC:2130-2136) and, for STRING columns, the offsets child
+ * (lengths + exclusive scan, RC:2375-2388).  Fuses copy_from_rows + copy_validity_from_rows
+ * (RC:879-969, 987-1094).
+ *   rows        : the LIST's INT8 child
+ *   row_offsets : the LIST's offsets child (int32[num_rows + 1]) or NULL for a fixed-width-only
+ *                 schema, where rows are read at stride fixed_row_size exactly as the reference
+ *                 does (RC:2317; it ignores the offsets there too)
+ *   rows_bytes  : size of `rows`; checked against size_per_row * num_rows (RC:2197)
+ *   cols        : num_columns outputs; data (fixed-width), null_mask and (STRING) offsets must be
+ *                 allocated; STRING data (chars) may be NULL in this phase
+ *   d_null_counts : device int64[num_columns] or NULL
+ *   d_char_totals : device int64[num_columns] (0 for non-STRING) or NULL; the caller reads it back
+ *                 (that read is the one sync the reference also has, RC:2389) to size the chars.
+ * If hash_kind != SRJ_HASH_NONE the row hash of the listed key columns is computed from the same
+ * shared-memory tile and written to hash_out (int64 for xxhash64, int32 otherwise): the fused
+ * from_rows + partition-hash of BASELINE config 4.  Keys must be fixed-width columns.
+ */
+typedef enum srj_hash_kind { SRJ_HASH_NONE = 0, SRJ_HASH_XXHASH64 = 1, SRJ_HASH_MURMUR3_32 = 2, SRJ_HASH_HIVE = 3 } srj_hash_kind;
+
+typedef struct srj_fused_hash {
+  int32_t kind;            /* srj_hash_kind */
+  int32_t num_keys;        /* <= 16 */
+  int32_t key_columns[16]; /* indices into the schema, hashed in this order */
+  int64_t seed;            /* xxhash64: int64 seed; murmur: low 32 bits; hive: ignored */
+  void* out;               /* device, num_rows elements */
+} srj_fused_hash;
+
+SRJ_API int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows,
+                                        const int32_t* row_offsets, int64_t rows_bytes,
+                                        int64_t num_rows, const srj_column* cols,
+                                        int64_t* d_null_counts, int64_t* d_char_totals,
+                                        const srj_fused_hash* hash /* may be NULL */, void* stream);
+/* Phase 2 (async): gather the chars of every STRING column (copy_strings_from_rows, RC:1110-1150). */
+SRJ_API int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows,
+                                          const int32_t* row_offsets, int64_t num_rows,
+                                          const srj_column* cols, void* stream);
+
+/* ---- row hashes: Hash.xxhash64 / murmurHash32 / hiveHash, hash/hash.hpp:40-74 ------------------ */
+#define SRJ_DEFAULT_XXHASH64_SEED 42 /* hash/hash.hpp:27 */
+#define SRJ_MAX_STACK_DEPTH 8        /* hash/hash.hpp:28 (nested types; not on this path yet) */
+SRJ_API int srj_get_max_stack_depth(void); /* Hash.getMaxStackDepth, HashJni.cpp:26-30 */
+/* out has no null mask (xxhash64.cu:556-562).  num_columns == 0 or num_rows == 0 is a no-op. */
+SRJ_API int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed,
+                         int64_t* out, void* stream);
+SRJ_API int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num_rows,
+                                uint32_t seed, int32_t* out, void* stream);
+SRJ_API int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* out,
+                          void* stream);
+
+/* ---- host-buffer convenience (end-to-end path: H2D + convert + D2H, pipelined in chunks) ------- */
+/*
+ * Fixed-width-only schemas.  `h_rows` is num_rows * fixed_row_size bytes of HOST memory (pinned for
+ * full PCIe speed); h_cols[i].data / null_mask are HOST buffers to fill.  Rows are streamed through
+ * the device in chunks of `chunk_rows` (0 = library default) on internal streams so that the H2D
+ * copy, the conversion kernel and the D2H copies of consecutive chunks overlap.  Synchronizes.
+ */
+SRJ_API int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int64_t num_rows,
+                                       const srj_column* h_cols, int64_t* h_null_counts,
+                                       int64_t chunk_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRJ_B200_H */

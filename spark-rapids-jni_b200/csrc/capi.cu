@@ -1,0 +1,587 @@
+// capi.cu -- the extern "C" boundary declared in include/srj_b200.h: argument checking, plans,
+// per-call pointer tables, launch sequencing.  No kernels here.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "hash_device.cuh"
+#include "kernels.hpp"
+#include "plan.hpp"
+
+namespace srj {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return e == cudaErrorMemoryAllocation ? SRJ_ENOMEM : SRJ_ECUDA;
+}
+
+static int size_of_type(int32_t t)
+{
+  switch (t) {
+    case SRJ_INT8: case SRJ_UINT8: case SRJ_BOOL8: return 1;
+    case SRJ_INT16: case SRJ_UINT16: return 2;
+    case SRJ_INT32: case SRJ_UINT32: case SRJ_FLOAT32: case SRJ_TIMESTAMP_DAYS: case SRJ_DURATION_DAYS:
+    case SRJ_DECIMAL32: return 4;
+    case SRJ_INT64: case SRJ_UINT64: case SRJ_FLOAT64: case SRJ_TIMESTAMP_SECONDS: case SRJ_TIMESTAMP_MILLISECONDS:
+    case SRJ_TIMESTAMP_MICROSECONDS: case SRJ_TIMESTAMP_NANOSECONDS: case SRJ_DURATION_SECONDS:
+    case SRJ_DURATION_MILLISECONDS: case SRJ_DURATION_MICROSECONDS: case SRJ_DURATION_NANOSECONDS:
+    case SRJ_DECIMAL64: return 8;
+    case SRJ_DECIMAL128: return 16;
+    default: return 0;
+  }
+}
+
+// compute_column_information, RC:1332-1371
+static int compute_layout(const int32_t* types, int32_t n, srj_layout* out, std::vector<int32_t>* starts,
+                          std::vector<int32_t>* sizes)
+{
+  if (n < 0 || (n > 0 && !types)) { set_error("layout: bad schema"); return SRJ_EINVAL; }
+  int64_t off = 0;
+  int nstr    = 0;
+  if (starts) starts->clear();
+  if (sizes) sizes->clear();
+  for (int32_t i = 0; i < n; ++i) {
+    const bool compound = types[i] == SRJ_STRING;
+    const int sz        = compound ? 8 : size_of_type(types[i]);
+    if (sz == 0) {
+      set_error("column %d: type id %d is not supported by the row format (only fixed-width and STRING, RowConversion.java:131)", i, types[i]);
+      return SRJ_EUNSUPPORTED;
+    }
+    const int al = compound ? 4 : sz;
+    off          = (off + al - 1) / al * al;
+    if (starts) starts->push_back(static_cast<int32_t>(off));
+    if (sizes) sizes->push_back(sz);
+    off += sz;
+    nstr += compound;
+    if (off > INT32_MAX - 8) { set_error("layout: row too large"); return SRJ_EOVERFLOW; }
+  }
+  out->num_columns        = n;
+  out->num_string_columns = nstr;
+  out->validity_offset    = static_cast<int32_t>(off);
+  off += (n + 7) / 8;
+  out->size_per_row   = static_cast<int32_t>(off);
+  out->fixed_row_size = static_cast<int32_t>((off + 7) / 8 * 8);
+  out->reserved       = 0;
+  return SRJ_OK;
+}
+
+struct Scratch {  // stream-ordered per-call device scratch
+  void* ptr = nullptr;
+  cudaStream_t stream;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  int alloc(size_t bytes)
+  {
+    SRJ_CUDA_TRY(cudaMallocAsync(&ptr, bytes ? bytes : 16, stream));
+    return SRJ_OK;
+  }
+  ~Scratch()
+  {
+    if (ptr) cudaFreeAsync(ptr, stream);
+  }
+};
+
+static int check_cols(const srj_plan* plan, const srj_column* cols, int64_t num_rows, const char* who)
+{
+  if (!plan || (plan->num_columns > 0 && !cols)) { set_error("%s: null argument", who); return SRJ_EINVAL; }
+  if (num_rows < 0) { set_error("%s: negative row count", who); return SRJ_EINVAL; }
+  for (int c = 0; c < plan->num_columns; ++c) {
+    if (cols[c].type_id != plan->type_ids[c]) { set_error("%s: column %d type %d does not match the plan (%d)", who, c, cols[c].type_id, plan->type_ids[c]); return SRJ_EINVAL; }
+    if (cols[c].size != num_rows) { set_error("%s: column %d has %lld rows, expected %lld", who, c, (long long)cols[c].size, (long long)num_rows); return SRJ_EINVAL; }
+  }
+  return SRJ_OK;
+}
+
+}  // namespace srj
+
+using namespace srj;
+
+extern "C" {
+
+const char* srj_version(void) { return "srj_b200 0.1.0 (sm_100a)"; }
+const char* srj_last_error(void) { return g_err; }
+const char* srj_status_string(int s)
+{
+  switch (s) {
+    case SRJ_OK: return "SRJ_OK";
+    case SRJ_EINVAL: return "SRJ_EINVAL";
+    case SRJ_EUNSUPPORTED: return "SRJ_EUNSUPPORTED";
+    case SRJ_EOVERFLOW: return "SRJ_EOVERFLOW";
+    case SRJ_ECUDA: return "SRJ_ECUDA";
+    case SRJ_ENOMEM: return "SRJ_ENOMEM";
+    default: return "SRJ_E?";
+  }
+}
+
+int srj_compute_layout(const int32_t* type_ids, int32_t num_columns, srj_layout* out, int32_t* col_starts,
+                       int32_t* col_sizes)
+{
+  if (!out) { set_error("layout: out is null"); return SRJ_EINVAL; }
+  std::vector<int32_t> st, sz;
+  const int rc = compute_layout(type_ids, num_columns, out, &st, &sz);
+  if (rc != SRJ_OK) return rc;
+  if (col_starts) std::copy(st.begin(), st.end(), col_starts);
+  if (col_sizes) std::copy(sz.begin(), sz.end(), col_sizes);
+  return SRJ_OK;
+}
+
+int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_columns, srj_plan** out)
+{
+  if (!out) { set_error("plan_create: out is null"); return SRJ_EINVAL; }
+  *out = nullptr;
+  srj_layout lay{};
+  std::vector<int32_t> st, sz;
+  int rc = compute_layout(type_ids, num_columns, &lay, &st, &sz);
+  if (rc != SRJ_OK) return rc;
+  auto* p               = new srj_plan();
+  p->num_columns        = num_columns;
+  p->num_string_columns = lay.num_string_columns;
+  p->validity_offset    = lay.validity_offset;
+  p->size_per_row       = lay.size_per_row;
+  p->fixed_row_size     = lay.fixed_row_size;
+  p->type_ids.assign(type_ids, type_ids + num_columns);
+  p->scales.assign(num_columns, 0);
+  if (scales) p->scales.assign(scales, scales + num_columns);
+  p->col_start = st;
+  p->col_size  = sz;
+  std::vector<int32_t> string_start;
+  for (int c = 0; c < num_columns; ++c)
+    if (type_ids[c] == SRJ_STRING) {
+      p->string_columns.push_back(c);
+      string_start.push_back(st[c]);
+    }
+  // schedules: entries grouped by width class
+  for (int k = 0; k < kNumClasses; ++k) {
+    p->fr_class_begin[k] = static_cast<int32_t>(p->fr_entries.size());
+    p->tr_class_begin[k] = static_cast<int32_t>(p->tr_entries.size());
+    for (int c = 0; c < num_columns; ++c) {
+      if (type_ids[c] == SRJ_STRING) {
+        if (k == 2) p->fr_entries.push_back(Entry{st[c] + 4, c});  // the length word, RC:2163-2172
+      } else if (class_of_size(sz[c]) == k) {
+        p->fr_entries.push_back(Entry{st[c], c});
+        p->tr_entries.push_back(Entry{st[c], c});
+      }
+    }
+  }
+  p->fr_class_begin[kNumClasses] = static_cast<int32_t>(p->fr_entries.size());
+  p->tr_class_begin[kNumClasses] = static_cast<int32_t>(p->tr_entries.size());
+
+  // from_rows tiling (shared memory budget 227 KB/CTA on sm_100)
+  Tiling& tl = p->tiling;
+  const int S = p->fixed_row_size;
+  if (S <= 2048) { tl.num_stages = 3; tl.stage_bytes = 64 * 1024; }
+  else           { tl.num_stages = 2; tl.stage_bytes = 100 * 1024; }
+  int fitrows = tl.stage_bytes / S;
+  int R       = fitrows / 32 * 32;
+  if (R > 512) R = 512;
+  if (R < 32) R = fitrows >= 16 ? 16 : 8;
+  tl.tile_rows     = R;
+  tl.rows_per_item = R >= 32 ? 32 : R;
+
+  // device mirror
+  SRJ_CUDA_TRY(cudaGetDevice(&p->device));
+  const size_t b_fr = p->fr_entries.size() * sizeof(Entry);
+  const size_t b_tr = p->tr_entries.size() * sizeof(Entry);
+  const size_t b_cs = static_cast<size_t>(num_columns) * 4;
+  const size_t b_sc = p->string_columns.size() * 4;
+  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + 64;
+  std::vector<uint8_t> blob(tot, 0);
+  size_t o = 0;
+  auto put = [&](const void* src, size_t n) { size_t at = o; if (n) memcpy(blob.data() + o, src, n); o += (n + 7) & ~size_t{7}; return at; };
+  const size_t o_fr = put(p->fr_entries.data(), b_fr);
+  const size_t o_tr = put(p->tr_entries.data(), b_tr);
+  const size_t o_cs = put(st.data(), b_cs);
+  const size_t o_sc = put(p->string_columns.data(), b_sc);
+  const size_t o_ss = put(string_start.data(), b_sc);
+  cudaError_t e = cudaMalloc(&p->d_blob, tot);
+  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
+  e = cudaMemcpy(p->d_blob, blob.data(), tot, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(p->d_blob); delete p; return cuda_fail(e, "cudaMemcpy(plan)"); }
+  auto* base        = static_cast<uint8_t*>(p->d_blob);
+  p->d_fr_entries   = reinterpret_cast<const Entry*>(base + o_fr);
+  p->d_tr_entries   = reinterpret_cast<const Entry*>(base + o_tr);
+  p->d_col_start    = reinterpret_cast<const int32_t*>(base + o_cs);
+  p->d_string_cols  = reinterpret_cast<const int32_t*>(base + o_sc);
+  p->d_string_start = reinterpret_cast<const int32_t*>(base + o_ss);
+  *out              = p;
+  return SRJ_OK;
+}
+
+void srj_plan_destroy(srj_plan* plan)
+{
+  if (!plan) return;
+  if (plan->d_blob) cudaFree(plan->d_blob);
+  delete plan;
+}
+
+int srj_plan_layout(const srj_plan* plan, srj_layout* out)
+{
+  if (!plan || !out) { set_error("plan_layout: null argument"); return SRJ_EINVAL; }
+  out->num_columns        = plan->num_columns;
+  out->num_string_columns = plan->num_string_columns;
+  out->validity_offset    = plan->validity_offset;
+  out->size_per_row       = plan->size_per_row;
+  out->fixed_row_size     = plan->fixed_row_size;
+  out->reserved           = 0;
+  return SRJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// convert_to_rows
+// ---------------------------------------------------------------------------------------------------
+static const int kRsChunkHost = 4096;  // must match kRsChunk in to_rows.cu
+
+int64_t srj_to_rows_workspace_bytes(const srj_plan* plan, int64_t num_rows)
+{
+  if (!plan || plan->num_string_columns == 0 || num_rows <= 0) return 0;
+  const int64_t nchunks = (num_rows + kRsChunkHost - 1) / kRsChunkHost;
+  return (num_rows + nchunks) * 8;
+}
+
+static int read_u64(const uint64_t* d, int64_t i, uint64_t* out, cudaStream_t s)
+{
+  SRJ_CUDA_TRY(cudaMemcpyAsync(out, d + i, 8, cudaMemcpyDeviceToHost, s));
+  SRJ_CUDA_TRY(cudaStreamSynchronize(s));
+  return SRJ_OK;
+}
+
+int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64_t num_rows, void* workspace,
+                             srj_row_batch* batches, int32_t max_batches, int32_t* num_batches, void* stream_)
+{
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc              = check_cols(plan, cols, num_rows, "to_rows_plan_batches");
+  if (rc != SRJ_OK) return rc;
+  if (!batches || !num_batches || max_batches < 1) { set_error("to_rows_plan_batches: bad batch array"); return SRJ_EINVAL; }
+  *num_batches = 0;
+  if (num_rows == 0) return SRJ_OK;
+  const uint64_t MAXB = INT32_MAX;  // MAX_BATCH_SIZE, RC:65
+  if (plan->num_string_columns == 0) {
+    // constant row size: build_batches (RC:1466-1557) in closed form.
+    const uint64_t S = plan->fixed_row_size;
+    int64_t last     = 0;
+    while (last < num_rows) {
+      // lower_bound over (i - last) * S >= MAXB  (cum[i] - cum[last] with cum inclusive)
+      const int64_t k      = static_cast<int64_t>((MAXB + S - 1) / S);  // first i - last reaching MAXB
+      const bool to_end    = last + k >= num_rows;
+      int64_t rows         = to_end ? num_rows - last : k / 32 * 32;
+      while (static_cast<uint64_t>(rows) * S > MAXB) rows -= (rows % 32) ? (rows % 32) : 32;  // overflow guard
+      if (rows <= 0) { set_error("to_rows: a single row exceeds 2 GiB"); return SRJ_EOVERFLOW; }
+      if (*num_batches >= max_batches) { set_error("to_rows: more than %d batches", max_batches); return SRJ_EINVAL; }
+      batches[*num_batches] = srj_row_batch{last, rows, static_cast<int64_t>(static_cast<uint64_t>(rows) * S)};
+      ++*num_batches;
+      last += rows;
+    }
+    return SRJ_OK;
+  }
+  if (!workspace) { set_error("to_rows_plan_batches: workspace is null"); return SRJ_EINVAL; }
+  // device: per-row sizes + inclusive scan
+  const int nstr = plan->num_string_columns;
+  std::vector<const int32_t*> h_off(nstr);
+  for (int s = 0; s < nstr; ++s) {
+    h_off[s] = cols[plan->string_columns[s]].offsets;
+    if (!h_off[s]) { set_error("to_rows: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
+  }
+  Scratch sc(stream);
+  rc = sc.alloc(sizeof(void*) * nstr);
+  if (rc != SRJ_OK) return rc;
+  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, h_off.data(), sizeof(void*) * nstr, cudaMemcpyHostToDevice, stream));
+  uint64_t* cum = static_cast<uint64_t*>(workspace);
+  rc            = launch_row_sizes(plan, static_cast<const int32_t* const*>(sc.ptr), num_rows, cum, stream);
+  if (rc != SRJ_OK) return rc;
+  uint64_t total = 0;
+  rc             = read_u64(cum, num_rows - 1, &total, stream);
+  if (rc != SRJ_OK) return rc;
+  int64_t last      = 0;
+  uint64_t cum_last = 0;  // cum[last - 1]
+  while (last < num_rows) {
+    int64_t row_end;
+    if (total - cum_last < MAXB) {
+      // common case: everything left fits one batch.  (The reference's lower_bound compares
+      // cum[i] - cum[last], i.e. it ignores the first row of the batch; the guard below covers the
+      // overshoot that can cause.)
+      row_end = num_rows;
+    } else {
+      uint64_t cl = 0;
+      rc          = read_u64(cum, last, &cl, stream);
+      if (rc != SRJ_OK) return rc;
+      int64_t lo = last, hi = num_rows;  // first i with cum[i] - cum[last] >= MAXB
+      while (lo < hi) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        uint64_t v        = 0;
+        rc                = read_u64(cum, mid, &v, stream);
+        if (rc != SRJ_OK) return rc;
+        if (v - cl < MAXB) lo = mid + 1; else hi = mid;
+      }
+      const int64_t bs = lo - last;
+      row_end          = (lo == num_rows) ? last + bs : last + bs / 32 * 32;
+    }
+    uint64_t cend = 0;
+    for (;;) {
+      if (row_end <= last) { set_error("to_rows: a single row exceeds 2 GiB"); return SRJ_EOVERFLOW; }
+      rc = read_u64(cum, row_end - 1, &cend, stream);
+      if (rc != SRJ_OK) return rc;
+      if (cend - cum_last <= MAXB) break;
+      const int64_t n = row_end - last;
+      row_end -= (n % 32) ? (n % 32) : 32;
+    }
+    if (*num_batches >= max_batches) { set_error("to_rows: more than %d batches", max_batches); return SRJ_EINVAL; }
+    batches[*num_batches] = srj_row_batch{last, row_end - last, static_cast<int64_t>(cend - cum_last)};
+    ++*num_batches;
+    last     = row_end;
+    cum_last = cend;
+  }
+  return SRJ_OK;
+}
+
+int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t num_rows, const void* workspace,
+                        const srj_row_batch* batches, int32_t num_batches, int32_t* const* batch_offsets,
+                        uint8_t* const* batch_data, void* stream_)
+{
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc              = check_cols(plan, cols, num_rows, "convert_to_rows");
+  if (rc != SRJ_OK) return rc;
+  if (num_batches == 0 || num_rows == 0) return SRJ_OK;
+  if (!batches || !batch_offsets || !batch_data) { set_error("convert_to_rows: null batch arrays"); return SRJ_EINVAL; }
+  const int nc = plan->num_columns, nstr = plan->num_string_columns;
+  if (nstr > 0 && !workspace) { set_error("convert_to_rows: workspace is null"); return SRJ_EINVAL; }
+  // pointer tables: [col_data nc][masks nc][str_offsets nstr][str_chars nstr]
+  std::vector<const void*> tab(2 * static_cast<size_t>(nc) + 2 * static_cast<size_t>(nstr));
+  for (int c = 0; c < nc; ++c) {
+    if (plan->type_ids[c] != SRJ_STRING && !cols[c].data) { set_error("convert_to_rows: column %d has no data", c); return SRJ_EINVAL; }
+    tab[c]      = cols[c].data;
+    tab[nc + c] = cols[c].null_mask;
+  }
+  for (int s = 0; s < nstr; ++s) {
+    const srj_column& c = cols[plan->string_columns[s]];
+    if (!c.offsets) { set_error("convert_to_rows: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
+    tab[2 * nc + s]        = c.offsets;
+    tab[2 * nc + nstr + s] = c.data;
+  }
+  Scratch sc(stream);
+  rc = sc.alloc(tab.size() * sizeof(void*));
+  if (rc != SRJ_OK) return rc;
+  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+  auto** d = static_cast<const void**>(sc.ptr);
+  for (int b = 0; b < num_batches; ++b) {
+    if (!batch_offsets[b] || (!batch_data[b] && batches[b].num_bytes > 0)) { set_error("convert_to_rows: batch %d buffers are null", b); return SRJ_EINVAL; }
+    rc = launch_to_rows(plan, d, reinterpret_cast<const uint32_t* const*>(d + nc),
+                        reinterpret_cast<const int32_t* const*>(d + 2 * nc),
+                        reinterpret_cast<const uint8_t* const*>(d + 2 * nc + nstr), batches[b].row_start,
+                        batches[b].row_count, nstr ? static_cast<const uint64_t*>(workspace) : nullptr,
+                        batch_offsets[b], batch_data[b], batches[b].num_bytes, stream);
+    if (rc != SRJ_OK) return rc;
+  }
+  return SRJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// convert_from_rows
+// ---------------------------------------------------------------------------------------------------
+int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
+                                int64_t rows_bytes, int64_t num_rows, const srj_column* cols, int64_t* d_null_counts,
+                                int64_t* d_char_totals, const srj_fused_hash* hash, void* stream_)
+{
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc              = check_cols(plan, cols, num_rows, "convert_from_rows");
+  if (rc != SRJ_OK) return rc;
+  const int nc = plan->num_columns, nstr = plan->num_string_columns;
+  if (nstr > 0 && !row_offsets && num_rows > 0) { set_error("convert_from_rows: a schema with STRING columns needs the LIST offsets"); return SRJ_EINVAL; }
+  if (nstr == 0) row_offsets = nullptr;  // fixed-width schemas ignore the offsets like the reference (RC:2317)
+  // RC:2197: size_per_row * num_rows <= child.size()
+  if (static_cast<int64_t>(plan->fixed_row_size) * num_rows > rows_bytes) {
+    set_error("convert_from_rows: The layout of the data appears to be off (%lld rows x %d bytes > %lld)", (long long)num_rows, plan->fixed_row_size, (long long)rows_bytes);
+    return SRJ_EINVAL;
+  }
+  if (num_rows > 0 && !rows) { set_error("convert_from_rows: rows is null"); return SRJ_EINVAL; }
+  if (hash && hash->kind != SRJ_HASH_NONE) {
+    if (hash->num_keys < 0 || hash->num_keys > 16 || !hash->out) { set_error("fused hash: bad key list / output"); return SRJ_EINVAL; }
+    for (int k = 0; k < hash->num_keys; ++k) {
+      const int c = hash->key_columns[k];
+      if (c < 0 || c >= nc) { set_error("fused hash: key column %d out of range", c); return SRJ_EINVAL; }
+      if (plan->type_ids[c] == SRJ_STRING) { set_error("fused hash: STRING keys are not supported in the fused path"); return SRJ_EUNSUPPORTED; }
+      if (hash->kind == SRJ_HASH_HIVE && !hash::hive_supported(plan->type_ids[c])) { set_error("fused hive hash: unsupported key type %d", plan->type_ids[c]); return SRJ_EUNSUPPORTED; }
+    }
+  }
+  const size_t nent = plan->fr_entries.size();
+  // pointer tables: [ent_dst nent][masks nc][str_offsets nstr] + scan partials
+  std::vector<void*> tab(nent + nc + nstr);
+  for (size_t e = 0; e < nent; ++e) {
+    const int c = plan->fr_entries[e].column;
+    if (plan->type_ids[c] == SRJ_STRING) {
+      if (!cols[c].offsets) { set_error("convert_from_rows: STRING column %d has no offsets buffer", c); return SRJ_EINVAL; }
+      tab[e] = reinterpret_cast<uint8_t*>(cols[c].offsets) + 4;  // lengths land at offsets[1..n]
+    } else {
+      if (!cols[c].data && num_rows > 0) { set_error("convert_from_rows: column %d has no data buffer", c); return SRJ_EINVAL; }
+      tab[e] = cols[c].data;
+    }
+  }
+  for (int c = 0; c < nc; ++c) {
+    if (!cols[c].null_mask && num_rows > 0) { set_error("convert_from_rows: column %d has no null mask buffer (always allocated, RC:2220)", c); return SRJ_EINVAL; }
+    tab[nent + c] = cols[c].null_mask;
+  }
+  for (int s = 0; s < nstr; ++s) tab[nent + nc + s] = cols[plan->string_columns[s]].offsets;
+  const size_t tab_bytes  = (tab.size() * sizeof(void*) + 15) & ~size_t{15};
+  const size_t part_bytes = static_cast<size_t>(string_scan_partials_bytes(nstr, num_rows));
+  Scratch sc(stream);
+  rc = sc.alloc(tab_bytes + part_bytes + 16);
+  if (rc != SRJ_OK) return rc;
+  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+  auto** d = static_cast<void**>(sc.ptr);
+  if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
+  if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * nc, stream));
+  rc = launch_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nent),
+                        d_null_counts, hash, stream);
+  if (rc != SRJ_OK) return rc;
+  if (nstr > 0) {
+    uint8_t* tail = static_cast<uint8_t*>(sc.ptr) + tab_bytes;
+    rc = launch_string_offsets_scan(reinterpret_cast<int32_t* const*>(d + nent + nc), plan->d_string_cols, nstr, num_rows,
+                                    d_char_totals, reinterpret_cast<int32_t*>(tail + part_bytes), tail, stream);
+    if (rc != SRJ_OK) return rc;
+  }
+  return SRJ_OK;
+}
+
+int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
+                                  int64_t num_rows, const srj_column* cols, void* stream_)
+{
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc              = check_cols(plan, cols, num_rows, "convert_from_rows_strings");
+  if (rc != SRJ_OK) return rc;
+  const int nstr = plan->num_string_columns;
+  if (nstr == 0 || num_rows == 0) return SRJ_OK;
+  if (!rows || !row_offsets) { set_error("convert_from_rows_strings: rows / offsets are null"); return SRJ_EINVAL; }
+  std::vector<void*> tab(2 * static_cast<size_t>(nstr));
+  for (int s = 0; s < nstr; ++s) {
+    const srj_column& c = cols[plan->string_columns[s]];
+    if (!c.offsets) { set_error("convert_from_rows_strings: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
+    tab[s]        = c.offsets;
+    tab[nstr + s] = c.data;  // may be NULL only when the column has no chars at all
+  }
+  Scratch sc(stream);
+  rc = sc.alloc(tab.size() * sizeof(void*));
+  if (rc != SRJ_OK) return rc;
+  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+  auto** d = static_cast<void**>(sc.ptr);
+  return launch_strings_from_rows(plan, rows, row_offsets, num_rows, reinterpret_cast<const int32_t* const*>(d),
+                                  reinterpret_cast<uint8_t* const*>(d + nstr), stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// hashes
+// ---------------------------------------------------------------------------------------------------
+int srj_get_max_stack_depth(void) { return SRJ_MAX_STACK_DEPTH; }
+
+int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, int64_t* out, void* stream)
+{
+  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("xxhash64: bad argument"); return SRJ_EINVAL; }
+  return launch_hash(SRJ_HASH_XXHASH64, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
+}
+
+int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num_rows, uint32_t seed, int32_t* out,
+                        void* stream)
+{
+  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("murmur_hash3_32: bad argument"); return SRJ_EINVAL; }
+  return launch_hash(SRJ_HASH_MURMUR3_32, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
+}
+
+int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* out, void* stream)
+{
+  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("hive_hash: bad argument"); return SRJ_EINVAL; }
+  return launch_hash(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer end-to-end path (fixed-width schemas): chunked H2D -> convert -> D2H on 3 streams
+// ---------------------------------------------------------------------------------------------------
+int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int64_t num_rows, const srj_column* h_cols,
+                               int64_t* h_null_counts, int64_t chunk_rows)
+{
+  int rc = check_cols(plan, h_cols, num_rows, "convert_from_rows_host");
+  if (rc != SRJ_OK) return rc;
+  if (plan->num_string_columns > 0) { set_error("convert_from_rows_host: fixed-width schemas only"); return SRJ_EUNSUPPORTED; }
+  const int nc = plan->num_columns;
+  if (h_null_counts) std::fill(h_null_counts, h_null_counts + nc, 0);
+  if (num_rows == 0) return SRJ_OK;
+  const int64_t S = plan->fixed_row_size;
+  if (chunk_rows <= 0) chunk_rows = std::max<int64_t>(32 * 1024, (256ll << 20) / S);  // ~256 MB of rows per chunk
+  const int64_t T = plan->tiling.tile_rows >= 32 ? plan->tiling.tile_rows : 32;
+  chunk_rows      = (chunk_rows + T - 1) / T * T;
+  chunk_rows      = std::min<int64_t>(chunk_rows, (num_rows + T - 1) / T * T);
+  constexpr int kSlots = 3;
+  cudaStream_t st[kSlots] = {};
+  uint8_t* d_rows[kSlots] = {};
+  uint8_t* d_cols[kSlots] = {};
+  void** d_tab[kSlots]    = {};
+  int64_t* d_nulls        = nullptr;
+  size_t col_bytes = 0;  // per slot: all column chunks + masks, 256-byte aligned pieces
+  std::vector<size_t> off_data(nc), off_mask(nc);
+  for (int c = 0; c < nc; ++c) {
+    off_data[c] = col_bytes;
+    col_bytes += (static_cast<size_t>(chunk_rows) * plan->col_size[c] + 255) & ~size_t{255};
+    off_mask[c] = col_bytes;
+    col_bytes += (static_cast<size_t>(chunk_rows) / 8 + 255) & ~size_t{255};
+  }
+  const size_t nent = plan->fr_entries.size();
+  auto cleanup = [&]() {
+    for (int s = 0; s < kSlots; ++s) {
+      if (st[s]) cudaStreamSynchronize(st[s]);
+      if (d_rows[s]) cudaFree(d_rows[s]);
+      if (d_cols[s]) cudaFree(d_cols[s]);
+      if (d_tab[s]) cudaFree(d_tab[s]);
+      if (st[s]) cudaStreamDestroy(st[s]);
+    }
+    if (d_nulls) cudaFree(d_nulls);
+  };
+#define SRJ_TRY_CLEAN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+  SRJ_TRY_CLEAN(cudaMalloc(&d_nulls, sizeof(int64_t) * nc));
+  SRJ_TRY_CLEAN(cudaMemset(d_nulls, 0, sizeof(int64_t) * nc));
+  const int nslots = static_cast<int>(std::min<int64_t>(kSlots, (num_rows + chunk_rows - 1) / chunk_rows));
+  for (int s = 0; s < nslots; ++s) {
+    SRJ_TRY_CLEAN(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+    SRJ_TRY_CLEAN(cudaMalloc(&d_rows[s], static_cast<size_t>(chunk_rows) * S));
+    SRJ_TRY_CLEAN(cudaMalloc(&d_cols[s], col_bytes));
+    SRJ_TRY_CLEAN(cudaMalloc(&d_tab[s], sizeof(void*) * (nent + nc)));
+    std::vector<void*> tab(nent + nc);
+    for (size_t e = 0; e < nent; ++e) tab[e] = d_cols[s] + off_data[plan->fr_entries[e].column];
+    for (int c = 0; c < nc; ++c) tab[nent + c] = d_cols[s] + off_mask[c];
+    SRJ_TRY_CLEAN(cudaMemcpy(d_tab[s], tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));
+  }
+  // null counts accumulate on the device across chunks: launch_from_rows only adds
+  int64_t k = 0;
+  for (int64_t r0 = 0; r0 < num_rows; r0 += chunk_rows, ++k) {
+    const int s      = static_cast<int>(k % nslots);
+    const int64_t n  = std::min(chunk_rows, num_rows - r0);
+    SRJ_TRY_CLEAN(cudaMemcpyAsync(d_rows[s], h_rows + r0 * S, static_cast<size_t>(n) * S, cudaMemcpyHostToDevice, st[s]));
+    // the kernel sees a chunk-local table whose last mask word is zero-tailed; chunk starts are multiples of 32
+    rc = launch_from_rows(plan, d_rows[s], nullptr, n * S, n, d_tab[s], reinterpret_cast<uint32_t* const*>(d_tab[s] + nent),
+                          d_nulls, nullptr, st[s]);
+    if (rc != SRJ_OK) { cleanup(); return rc; }
+    for (int c = 0; c < nc; ++c) {
+      SRJ_TRY_CLEAN(cudaMemcpyAsync(static_cast<uint8_t*>(h_cols[c].data) + r0 * plan->col_size[c], d_cols[s] + off_data[c],
+                                    static_cast<size_t>(n) * plan->col_size[c], cudaMemcpyDeviceToHost, st[s]));
+      if (h_cols[c].null_mask)
+        SRJ_TRY_CLEAN(cudaMemcpyAsync(h_cols[c].null_mask + r0 / 32, d_cols[s] + off_mask[c], static_cast<size_t>((n + 31) / 32) * 4,
+                                      cudaMemcpyDeviceToHost, st[s]));
+    }
+  }
+  for (int s = 0; s < nslots; ++s) SRJ_TRY_CLEAN(cudaStreamSynchronize(st[s]));
+  if (h_null_counts) SRJ_TRY_CLEAN(cudaMemcpy(h_null_counts, d_nulls, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost));
+#undef SRJ_TRY_CLEAN
+  cleanup();
+  return SRJ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,40 @@
+// kernels.hpp -- host-side launchers implemented in the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/srj_b200.h"
+#include "plan.hpp"
+
+namespace srj {
+
+// from_rows.cu
+int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
+                     int64_t num_rows, void* const* d_ent_dst, uint32_t* const* d_masks, int64_t* d_null_counts,
+                     const srj_fused_hash* fh, cudaStream_t stream);
+
+// strings.cu
+// In-place inclusive scan of the int32 lengths stored at offsets[c][1..n] for every STRING column
+// (offsets[c][0] = 0), per-column totals to d_char_totals[schema col] (int64), overflow -> *d_error.
+int launch_string_offsets_scan(int32_t* const* d_offsets /* device array [nstr] */, const int32_t* d_string_cols,
+                               int nstr, int64_t num_rows, int64_t* d_char_totals, int32_t* d_error,
+                               void* d_partials /* int64 [nstr * nchunks] */, cudaStream_t stream);
+int64_t string_scan_partials_bytes(int nstr, int64_t num_rows);
+// copy_strings_from_rows replacement
+int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
+                             int64_t num_rows, const int32_t* const* d_offsets, uint8_t* const* d_chars,
+                             cudaStream_t stream);
+
+// to_rows.cu
+int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,
+                     uint64_t* d_cum_sizes, cudaStream_t stream);
+int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                   const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
+                   int64_t row_count, const uint64_t* d_cum_sizes /* NULL for fixed */, int32_t* out_offsets,
+                   uint8_t* out_data, int64_t out_bytes, cudaStream_t stream);
+
+// hash.cu
+int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out,
+                cudaStream_t stream);
+
+}  // namespace srj

@@ -1,0 +1,59 @@
+// plan.hpp -- per-schema plan: JCUDF layout (compute_column_information, RC:1332-1371) plus the
+// static work schedule the kernels run (columns grouped by width class), mirrored on the device.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/srj_b200.h"
+
+namespace srj {
+
+// Width classes: element sizes 1, 2, 4, 8, 16 bytes.
+constexpr int kNumClasses = 5;
+inline int class_of_size(int sz) { return sz == 1 ? 0 : sz == 2 ? 1 : sz == 4 ? 2 : sz == 8 ? 3 : sz == 16 ? 4 : -1; }
+
+// One fixed-width "entry" = one field the fixed-width transpose moves.  A STRING column
+// contributes one 4-byte entry for its length word (second uint32 of the pair, RC:2163-2172) in
+// from_rows; in to_rows the pair is produced by the string stage instead.
+struct Entry {
+  int32_t start;   // byte offset in the row
+  int32_t column;  // schema column index
+};
+
+struct Tiling {
+  int32_t tile_rows;    // max rows per tile (multiple of rows_per_item)
+  int32_t rows_per_item;  // 8, 16 or 32: lanes of a warp item that map to rows
+  int32_t stage_bytes;  // shared-memory bytes per pipeline stage (payload)
+  int32_t num_stages;
+};
+
+}  // namespace srj
+
+struct srj_plan {
+  int32_t device;
+  int32_t num_columns;
+  int32_t num_string_columns;
+  int32_t validity_offset;
+  int32_t size_per_row;
+  int32_t fixed_row_size;
+  std::vector<int32_t> type_ids, scales, col_start, col_size;
+  std::vector<int32_t> string_columns;  // schema indices of STRING columns, in order
+
+  // from_rows schedule: entries grouped by width class; STRING columns add a 4-byte length entry
+  std::vector<srj::Entry> fr_entries;
+  int32_t fr_class_begin[srj::kNumClasses + 1];
+  // to_rows schedule: fixed-width columns only
+  std::vector<srj::Entry> tr_entries;
+  int32_t tr_class_begin[srj::kNumClasses + 1];
+
+  srj::Tiling tiling;
+
+  // device mirrors (one allocation)
+  void* d_blob;
+  const srj::Entry* d_fr_entries;
+  const srj::Entry* d_tr_entries;
+  const int32_t* d_col_start;     // [num_columns]
+  const int32_t* d_string_cols;   // [num_string_columns]
+  const int32_t* d_string_start;  // [num_string_columns] row byte offset of each pair
+};

@@ -1,0 +1,561 @@
+// to_rows.cu -- columns -> JCUDF rows (reference: convert_to_rows, RC:1762-2055).
+//
+// One kernel per output batch fuses copy_to_rows + copy_validity_to_rows + copy_strings_to_rows
+// (RC:574-688, 706-798, 816-861) and the batch's row-offset column:
+//   - a CTA owns a contiguous row range and assembles a tile of rows -- ONE contiguous byte range
+//     of the output -- in shared memory: zero fill (padding bytes are defined as 0), coalesced
+//     column reads (lane = row) scattered into the row images, validity bytes gathered from the
+//     column masks, (offset,len) pairs by a warp scan across the STRING columns of a row, chars
+//     appended in column order;
+//   - the finished tile leaves with a single 1-D TMA bulk store (cp.async.bulk.global.shared::cta),
+//     double-buffered so the store of tile k overlaps the assembly of tile k+1.
+// Rows too large for a stage, or unaligned output buffers, take the SAFE path: the same assembly
+// code writing global memory directly, byte-wise.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.hpp"
+#include "plan.hpp"
+
+namespace srj {
+
+constexpr int kTrThreads = 256;
+constexpr int kTrWarps   = kTrThreads / 32;
+constexpr int kTrSlack   = 32;
+
+struct ToRowsParams {
+  const void* const* col_data;        // [ncols] fixed-width values (STRING: unused)
+  const uint32_t* const* masks;       // [ncols], entries may be NULL
+  const int32_t* const* str_offsets;  // [nstr]
+  const uint8_t* const* str_chars;    // [nstr]
+  const uint64_t* cum;                // inclusive cumulative row sizes over the table, or NULL (fixed)
+  int64_t row_start;
+  int64_t row_count;
+  int32_t* out_offsets;
+  uint8_t* out_data;
+  int64_t out_bytes;
+  int64_t rows_per_cta;
+  int32_t ncols, nstr;
+  int32_t validity_offset, size_per_row, row_stride;
+  int32_t tile_rows, rpl, stage_bytes;
+  int32_t nentries;
+  int32_t class_begin[kNumClasses + 1];
+  const Entry* entries;
+  const int32_t* string_cols;
+  const int32_t* string_start;
+  int32_t max_str_entries;  // capacity of the per-tile string tables (rows * nstr)
+};
+
+struct TrHdr {
+  int64_t r;        // first batch-relative row of the tile
+  int64_t lo, hi;   // batch-relative output byte range
+  int32_t rows;
+  int32_t safe;
+  int32_t skew;     // stage byte of output byte `lo`
+  int32_t pad;
+};
+
+template <int W, bool SAFE>
+__device__ __forceinline__ void put_elem(uint8_t* dst, const uint8_t* src)
+{
+  if constexpr (W == 1) {
+    *dst = __ldg(src);
+  } else if constexpr (W == 2) {
+    const uint16_t v = __ldg(reinterpret_cast<const uint16_t*>(src));
+    if constexpr (SAFE) { dst[0] = v & 0xff; dst[1] = v >> 8; } else { *reinterpret_cast<uint16_t*>(dst) = v; }
+  } else if constexpr (W == 4) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src));
+    if constexpr (SAFE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = static_cast<uint8_t>(v >> (8 * i));
+    } else {
+      *reinterpret_cast<uint32_t*>(dst) = v;
+    }
+  } else if constexpr (W == 8) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(src));
+    if constexpr (SAFE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dst[i] = static_cast<uint8_t>(v.x >> (8 * i)); dst[4 + i] = static_cast<uint8_t>(v.y >> (8 * i)); }
+    } else {
+      *reinterpret_cast<uint2*>(dst) = v;
+    }
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+    if constexpr (SAFE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dst[i]      = static_cast<uint8_t>(v.x >> (8 * i));
+        dst[4 + i]  = static_cast<uint8_t>(v.y >> (8 * i));
+        dst[8 + i]  = static_cast<uint8_t>(v.z >> (8 * i));
+        dst[12 + i] = static_cast<uint8_t>(v.w >> (8 * i));
+      }
+    } else {
+      // rows are 8-byte aligned only: two 8-byte stores
+      *reinterpret_cast<uint2*>(dst)     = make_uint2(v.x, v.y);
+      *reinterpret_cast<uint2*>(dst + 8) = make_uint2(v.z, v.w);
+    }
+  }
+}
+
+struct TrTables {
+  const int32_t* ent_start;
+  const int32_t* ent_col;
+  const uint8_t* const* col_data;
+  const uint8_t* const* mask_bytes;
+  int32_t* str_src;  // [rows * nstr]
+  int32_t* str_len;
+  int32_t* str_dst;
+};
+
+// Assemble rows [r, r+rows) of the batch into `base` (+ row offsets).  All threads of the CTA.
+template <bool SAFE>
+__device__ __forceinline__ void assemble_tile(const ToRowsParams& p, const TrTables& t, uint8_t* base,
+                                              const int32_t* s_off, int64_t stride, int64_t r, int rows,
+                                              uint8_t* zero_base, int64_t zero_bytes)
+{
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  const int w    = warp_id();
+  auto rowptr    = [&](int i) -> uint8_t* {
+    return s_off ? base + static_cast<uint32_t>(s_off[i]) : base + static_cast<int64_t>(i) * stride;
+  };
+  const int64_t abs0 = p.row_start + r;  // table row of tile row 0
+
+  // ---- zero fill (padding bytes are 0) ------------------------------------------------------------
+  if constexpr (SAFE) {
+    for (int64_t i = tid; i < zero_bytes; i += kTrThreads) zero_base[i] = 0;
+  } else {
+    uint4* z        = reinterpret_cast<uint4*>(zero_base);  // stage start: 16-byte aligned
+    const int64_t n = (zero_bytes + 15) >> 4;
+    for (int64_t i = tid; i < n; i += kTrThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  // ---- fixed-width fields: coalesced column reads, scatter into the row images -----------------
+  const int rpl     = p.rpl;
+  const int cpi     = 32 / rpl;
+  const int sub     = lane / rpl;
+  const int lr      = lane - sub * rpl;
+  const int ngroups = (rows + rpl - 1) / rpl;
+  auto run_class    = [&](auto wtag, int k) {
+    constexpr int W  = decltype(wtag)::value;
+    const int nb     = p.class_begin[k];
+    const int ne     = p.class_begin[k + 1];
+    const int nslots = (ne - nb + cpi - 1) / cpi;
+    const int total  = nslots * ngroups;
+    for (int item = w; item < total; item += kTrWarps) {
+      const int g    = item / nslots;
+      const int slot = item - g * nslots;
+      const int e    = nb + slot * cpi + sub;
+      const int row  = g * rpl + lr;
+      if (e < ne && row < rows) {
+        const uint8_t* src = t.col_data[t.ent_col[e]] + (abs0 + row) * W;
+        put_elem<W, SAFE>(rowptr(row) + t.ent_start[e], src);
+      }
+    }
+  };
+  run_class(std::integral_constant<int, 16>{}, 4);
+  run_class(std::integral_constant<int, 8>{}, 3);
+  run_class(std::integral_constant<int, 4>{}, 2);
+  run_class(std::integral_constant<int, 2>{}, 1);
+  run_class(std::integral_constant<int, 1>{}, 0);
+
+  // ---- validity: column mask bits -> row validity bytes (bit c%8 of byte c/8, RC:764-773) -------
+  const int nvb    = (p.ncols + 7) >> 3;
+  const int ng32   = (rows + 31) >> 5;
+  const int vitems = nvb * ng32;
+  for (int item = w; item < vitems; item += kTrWarps) {
+    const int g   = item / nvb;
+    const int b   = item - g * nvb;
+    const int row = g * 32 + lane;
+    if (row < rows) {
+      const int64_t ra = abs0 + row;
+      uint32_t byte    = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = b * 8 + k;
+        if (c < p.ncols) {
+          const uint8_t* mb = t.mask_bytes[c];
+          const uint32_t v  = mb ? ((__ldg(mb + (ra >> 3)) >> (ra & 7)) & 1u) : 1u;
+          byte |= v << k;
+        }
+      }
+      rowptr(row)[p.validity_offset + b] = static_cast<uint8_t>(byte);
+    }
+  }
+
+  // ---- strings -------------------------------------------------------------------------------------
+  if (p.nstr > 0) {
+    const int nstr = p.nstr;
+    const int nent = rows * nstr;
+    // S1: (src offset, len) of every (row, string column); lanes run over rows => coalesced offsets
+    for (int idx = tid; idx < nent; idx += kTrThreads) {
+      const int s           = idx / rows;
+      const int row         = idx - s * rows;
+      const int32_t* so     = p.str_offsets[s] + abs0 + row;
+      const int32_t o0      = __ldg(so);
+      const int32_t o1      = __ldg(so + 1);
+      t.str_src[row * nstr + s] = o0;
+      t.str_len[row * nstr + s] = o1 - o0;
+    }
+    __syncthreads();
+    // S2: warp per row: running offset across the row's string columns, pairs into the row image
+    for (int row = w; row < rows; row += kTrWarps) {
+      uint32_t run = static_cast<uint32_t>(p.size_per_row);  // RC:838
+      uint8_t* rp  = rowptr(row);
+      for (int s0 = 0; s0 < nstr; s0 += 32) {
+        const int s        = s0 + lane;
+        const uint32_t len = s < nstr ? static_cast<uint32_t>(t.str_len[row * nstr + s]) : 0u;
+        uint32_t x         = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += y;
+        }
+        const uint32_t off = run + x - len;
+        if (s < nstr) {
+          t.str_dst[row * nstr + s] = static_cast<int32_t>(off);
+          uint8_t* pp               = rp + p.string_start[s];
+          if constexpr (SAFE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pp[i] = static_cast<uint8_t>(off >> (8 * i)); pp[4 + i] = static_cast<uint8_t>(len >> (8 * i)); }
+          } else {
+            reinterpret_cast<uint32_t*>(pp)[0] = off;  // RC:848
+            reinterpret_cast<uint32_t*>(pp)[1] = len;  // RC:849
+          }
+        }
+        run += __shfl_sync(0xffffffffu, x, 31);
+      }
+    }
+    __syncthreads();
+    // S3: chars.  Thread per (row, string): adjacent lanes read adjacent strings of one column.
+    for (int idx = tid; idx < nent; idx += kTrThreads) {
+      const int s        = idx / rows;
+      const int row      = idx - s * rows;
+      const int e        = row * nstr + s;
+      const int32_t len  = t.str_len[e];
+      const uint8_t* src = p.str_chars[s] + t.str_src[e];
+      uint8_t* dst       = rowptr(row) + static_cast<uint32_t>(t.str_dst[e]);
+      for (int32_t i = 0; i < len; ++i) dst[i] = __ldg(src + i);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_constant__ ToRowsParams p)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int stage_span = p.stage_bytes + kTrSlack;
+  uint8_t* stage0      = smem;
+  int32_t* s_off       = reinterpret_cast<int32_t*>(smem + 2 * static_cast<size_t>(stage_span));
+  const int soff_span  = (p.tile_rows + 4) & ~3;
+  TrHdr* hdr           = reinterpret_cast<TrHdr*>(s_off + soff_span);
+  int32_t* s_ent_start = reinterpret_cast<int32_t*>(hdr + 1);
+  int32_t* s_ent_col   = s_ent_start + p.nentries;
+  const uint8_t** s_col_data   = reinterpret_cast<const uint8_t**>(s_ent_col + p.nentries + ((2 * p.nentries) & 1));
+  const uint8_t** s_mask_bytes = s_col_data + p.ncols;
+  int32_t* s_str_src           = reinterpret_cast<int32_t*>(s_mask_bytes + p.ncols);
+  int32_t* s_str_len           = s_str_src + p.max_str_entries;
+  int32_t* s_str_dst           = s_str_len + p.max_str_entries;
+
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  for (int i = tid; i < p.nentries; i += kTrThreads) {
+    s_ent_start[i] = p.entries[i].start;
+    s_ent_col[i]   = p.entries[i].column;
+  }
+  for (int i = tid; i < p.ncols; i += kTrThreads) {
+    s_col_data[i]   = static_cast<const uint8_t*>(p.col_data[i]);
+    s_mask_bytes[i] = reinterpret_cast<const uint8_t*>(p.masks[i]);
+  }
+  __syncthreads();
+  TrTables t{s_ent_start, s_ent_col, s_col_data, s_mask_bytes, s_str_src, s_str_len, s_str_dst};
+
+  const int64_t c0   = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
+  const int64_t c1   = tmin(p.row_count, c0 + p.rows_per_cta);
+  const bool fixed   = p.cum == nullptr;
+  const bool base_ok = (reinterpret_cast<uintptr_t>(p.out_data) & 7) == 0;
+  const uint64_t cum0 = (!fixed && p.row_start > 0) ? p.cum[p.row_start - 1] : 0;
+  auto row_off = [&](int64_t i) -> int64_t {  // batch-relative byte offset of batch row i (i <= row_count)
+    if (fixed) return i * p.row_stride;
+    const int64_t a = p.row_start + i;
+    return a == 0 ? 0 : static_cast<int64_t>(p.cum[a - 1] - cum0);
+  };
+
+  int64_t r = c0;
+  for (int it = 0; r < c1; ++it) {
+    uint8_t* stage = stage0 + static_cast<size_t>(it & 1) * stage_span;
+    // ---- A: tile geometry (warp 0) -------------------------------------------------------------
+    if (tid == 0) tma_store_wait_read<1>();  // the store that last used this stage has drained
+    if (warp_id() == 0) {
+      int rows        = static_cast<int>(tmin<int64_t>(p.tile_rows, c1 - r));
+      const int64_t lo = row_off(r);
+      const int64_t base = lo - static_cast<int64_t>((reinterpret_cast<uintptr_t>(p.out_data) + lo) & 15);
+      bool safe       = !base_ok;
+      int64_t hi;
+      if (fixed) {
+        hi = lo + static_cast<int64_t>(rows) * p.row_stride;
+        if (hi - lo > p.stage_bytes) safe = true;
+        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(lo + static_cast<int64_t>(i) * p.row_stride);
+      } else {
+        int fit = 0;
+        for (int i0 = 0; i0 <= rows; i0 += 32) {
+          const int i = i0 + lane;
+          int64_t o   = 0;
+          if (i <= rows) {
+            o        = row_off(r + i);
+            s_off[i] = static_cast<int32_t>(o - base);
+          }
+          const bool ok = (i >= 1) && (i <= rows) && (round_up64(o - base, 16) <= p.stage_bytes + 16);
+          fit += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        if (fit < rows) fit &= ~7;
+        if (p.max_str_entries < rows * p.nstr) fit = 0;
+        if (fit == 0 || safe) {
+          safe = true;
+          rows = tmin(rows, 8);
+          while (rows > 1 && rows * p.nstr > p.max_str_entries) --rows;
+          __syncwarp();
+          for (int i = lane; i <= rows; i += 32) s_off[i] = static_cast<int32_t>(row_off(r + i) - lo);
+        } else {
+          rows = fit;
+        }
+        hi = row_off(r + rows);
+        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(row_off(r + i));
+      }
+      if (r + rows == p.row_count && lane == 0) p.out_offsets[p.row_count] = static_cast<int32_t>(hi);
+      if (lane == 0) {
+        hdr->r    = r;
+        hdr->lo   = lo;
+        hdr->hi   = hi;
+        hdr->rows = rows;
+        hdr->safe = safe ? 1 : 0;
+        hdr->skew = static_cast<int32_t>(lo - base);
+      }
+    }
+    __syncthreads();
+    const TrHdr h = *hdr;
+    // ---- B/C: assemble -------------------------------------------------------------------------
+    if (!h.safe) {
+      const int64_t zb = h.skew + (h.hi - h.lo);
+      if (fixed)
+        assemble_tile<false>(p, t, stage + h.skew, nullptr, p.row_stride, h.r, h.rows, stage, zb);
+      else
+        assemble_tile<false>(p, t, stage, s_off, 0, h.r, h.rows, stage, zb);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
+      __syncthreads();
+      // ---- D: write out ------------------------------------------------------------------------
+      if (tid == 0) {
+        const uintptr_t g_lo = reinterpret_cast<uintptr_t>(p.out_data) + h.lo;
+        const uintptr_t g_hi = reinterpret_cast<uintptr_t>(p.out_data) + h.hi;
+        const uintptr_t fl   = g_lo - h.skew;  // global address of stage byte 0
+        const uintptr_t t_lo = (g_lo + 15) & ~uintptr_t{15};
+        const uintptr_t t_hi = g_hi & ~uintptr_t{15};
+        uintptr_t h_end      = tmin(t_lo, g_hi);
+        uintptr_t t_beg      = tmax(t_hi, h_end);
+        if (t_hi > t_lo) {
+          tma_store_1d(reinterpret_cast<void*>(t_lo), stage + (t_lo - fl), static_cast<uint32_t>(t_hi - t_lo));
+        } else {
+          h_end = g_hi;
+          t_beg = g_hi;
+        }
+        tma_store_commit();
+        for (uintptr_t a = g_lo; a < h_end; a += 8)
+          *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(stage + (a - fl));
+        for (uintptr_t a = t_beg; a < g_hi; a += 8)
+          *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(stage + (a - fl));
+      }
+    } else {
+      if (fixed)
+        assemble_tile<true>(p, t, p.out_data + h.lo, nullptr, p.row_stride, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
+      else
+        assemble_tile<true>(p, t, p.out_data + h.lo, s_off, 0, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
+      __syncthreads();
+    }
+    r += h.rows;
+  }
+  if (tid == 0) tma_store_wait_read<0>();
+}
+
+// ---- row sizes: round_up(size_per_row + sum(len), 8), inclusive scan (RC:201-257, 1490-1491) -------
+// v1: per-row sizes by a simple kernel, then the same three-step scan structure (uint64).
+constexpr int kRsThreads = 256;
+constexpr int kRsChunk   = 4096;
+
+__global__ void __launch_bounds__(kRsThreads) row_sizes_kernel(const int32_t* const* str_offsets, int nstr,
+                                                                int32_t size_per_row, int64_t n, uint64_t* sizes)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kRsThreads + threadIdx.x;
+  if (i >= n) return;
+  uint64_t s = 0;
+  for (int c = 0; c < nstr; ++c) {
+    const int32_t* o = str_offsets[c] + i;
+    s += static_cast<uint64_t>(static_cast<uint32_t>(__ldg(o + 1) - __ldg(o)));
+  }
+  sizes[i] = (static_cast<uint64_t>(size_per_row) + s + 7) & ~uint64_t{7};
+}
+
+__global__ void __launch_bounds__(kRsThreads) u64_partials_kernel(const uint64_t* v, int64_t n, uint64_t* partials)
+{
+  __shared__ uint64_t s_w[kRsThreads / 32];
+  const int64_t beg = static_cast<int64_t>(blockIdx.x) * kRsChunk;
+  const int64_t end = tmin(n, beg + kRsChunk);
+  uint64_t acc      = 0;
+  for (int64_t i = beg + threadIdx.x; i < end; i += kRsThreads) acc += v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane_id() == 0) s_w[warp_id()] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int i = 0; i < kRsThreads / 32; ++i) t += s_w[i];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads) u64_scan_chunks_kernel(uint64_t* partials, int nchunks)
+{
+  __shared__ uint64_t s_w[kRsThreads / 32];
+  __shared__ uint64_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nchunks; base += kRsThreads) {
+    const int i      = base + threadIdx.x;
+    const uint64_t v = i < nchunks ? partials[i] : 0;
+    uint64_t x       = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) s_w[warp_id()] = x;
+    __syncthreads();
+    uint64_t wpre = 0;
+    for (int w = 0; w < warp_id(); ++w) wpre += s_w[w];
+    const uint64_t carry = s_carry;
+    if (i < nchunks) partials[i] = carry + wpre + x - v;
+    __syncthreads();
+    if (threadIdx.x == kRsThreads - 1) s_carry = carry + wpre + x;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads) u64_scan_apply_kernel(uint64_t* v, int64_t n, const uint64_t* partials)
+{
+  __shared__ uint64_t s_w[kRsThreads / 32];
+  __shared__ uint64_t s_carry;
+  if (threadIdx.x == 0) s_carry = partials[blockIdx.x];
+  __syncthreads();
+  const int64_t beg = static_cast<int64_t>(blockIdx.x) * kRsChunk;
+  const int64_t end = tmin(n, beg + kRsChunk);
+  for (int64_t base = beg; base < end; base += kRsThreads) {
+    const int64_t i  = base + threadIdx.x;
+    const uint64_t a = i < end ? v[i] : 0;
+    uint64_t x       = a;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) s_w[warp_id()] = x;
+    __syncthreads();
+    uint64_t wpre = 0;
+    for (int w = 0; w < warp_id(); ++w) wpre += s_w[w];
+    const uint64_t carry = s_carry;
+    if (i < end) v[i] = carry + wpre + x;
+    __syncthreads();
+    if (threadIdx.x == kRsThreads - 1) s_carry = carry + wpre + x;
+    __syncthreads();
+  }
+}
+
+// d_cum_sizes: uint64[num_rows] followed by uint64[nchunks] scratch (see srj_to_rows_workspace_bytes)
+int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,
+                     uint64_t* d_cum_sizes, cudaStream_t stream)
+{
+  if (num_rows == 0) return SRJ_OK;
+  const int nchunks  = static_cast<int>((num_rows + kRsChunk - 1) / kRsChunk);
+  uint64_t* partials = d_cum_sizes + num_rows;
+  row_sizes_kernel<<<static_cast<unsigned>((num_rows + kRsThreads - 1) / kRsThreads), kRsThreads, 0, stream>>>(
+    d_str_offsets, plan->num_string_columns, plan->size_per_row, num_rows, d_cum_sizes);
+  u64_partials_kernel<<<nchunks, kRsThreads, 0, stream>>>(d_cum_sizes, num_rows, partials);
+  u64_scan_chunks_kernel<<<1, kRsThreads, 0, stream>>>(partials, nchunks);
+  u64_scan_apply_kernel<<<nchunks, kRsThreads, 0, stream>>>(d_cum_sizes, num_rows, partials);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+static size_t to_rows_smem_bytes(const srj_plan* plan, int tile_rows, int stage_bytes, int max_str_entries)
+{
+  const int nent = static_cast<int>(plan->tr_entries.size());
+  size_t b       = 2 * static_cast<size_t>(stage_bytes + kTrSlack);
+  b += static_cast<size_t>((tile_rows + 4) & ~3) * 4;
+  b += sizeof(TrHdr);
+  b += static_cast<size_t>(2 * nent + ((2 * nent) & 1)) * 4;
+  b += static_cast<size_t>(plan->num_columns) * 16;
+  b += static_cast<size_t>(max_str_entries) * 12;
+  return (b + 127) & ~size_t{127};
+}
+
+int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                   const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
+                   int64_t row_count, const uint64_t* d_cum_sizes, int32_t* out_offsets, uint8_t* out_data,
+                   int64_t out_bytes, cudaStream_t stream)
+{
+  if (row_count == 0) return SRJ_OK;
+  ToRowsParams p{};
+  p.col_data        = d_col_data;
+  p.masks           = d_masks;
+  p.str_offsets     = d_str_offsets;
+  p.str_chars       = d_str_chars;
+  p.cum             = d_cum_sizes;
+  p.row_start       = row_start;
+  p.row_count       = row_count;
+  p.out_offsets     = out_offsets;
+  p.out_data        = out_data;
+  p.out_bytes       = out_bytes;
+  p.ncols           = plan->num_columns;
+  p.nstr            = plan->num_string_columns;
+  p.validity_offset = plan->validity_offset;
+  p.size_per_row    = plan->size_per_row;
+  p.row_stride      = plan->fixed_row_size;
+  p.nentries        = static_cast<int32_t>(plan->tr_entries.size());
+  for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->tr_class_begin[k];
+  p.entries      = plan->d_tr_entries;
+  p.string_cols  = plan->d_string_cols;
+  p.string_start = plan->d_string_start;
+
+  // to_rows tiling: two 48 KB stages so that two CTAs share an SM (their barrier bubbles overlap)
+  const int stage_bytes = 48 * 1024;
+  int tile_rows         = (stage_bytes / plan->fixed_row_size) / 32 * 32;
+  if (tile_rows > 512) tile_rows = 512;
+  if (tile_rows < 32) tile_rows = (stage_bytes / plan->fixed_row_size) >= 16 ? 16 : 8;
+  int max_str = 0;
+  if (p.nstr > 0) {
+    // cap the per-tile string tables at 2048 (row, string) entries
+    while (tile_rows > 8 && tile_rows * p.nstr > 2048) tile_rows = tile_rows > 32 ? tile_rows - 32 : tile_rows / 2;
+    max_str = std::min(tile_rows * p.nstr, 2048);
+    if (max_str < p.nstr) max_str = p.nstr;  // at least one row (SAFE path walks row by row)
+    if (max_str > 8192) return (set_error("to_rows: more than 8192 STRING columns is not supported"), SRJ_EUNSUPPORTED);
+  }
+  p.tile_rows       = tile_rows;
+  p.rpl             = tile_rows >= 32 ? 32 : tile_rows;
+  p.stage_bytes     = stage_bytes;
+  p.max_str_entries = max_str;
+
+  int dev = 0, nsm = 0;
+  SRJ_CUDA_TRY(cudaGetDevice(&dev));
+  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t T      = tile_rows;
+  const int64_t ntiles = (row_count + T - 1) / T;
+  int64_t grid         = std::min<int64_t>(static_cast<int64_t>(nsm) * 2, ntiles);
+  const int64_t per    = (ntiles + grid - 1) / grid;
+  p.rows_per_cta       = per * T;
+  grid                 = (row_count + p.rows_per_cta - 1) / p.rows_per_cta;
+  const size_t smem    = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str);
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  to_rows_kernel<<<static_cast<unsigned>(grid), kTrThreads, smem, stream>>>(p);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+}  // namespace srj
