@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path benchmark (contract in the task statement, tier section (4)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+                    [--rows R]
+
+A "step" is one pass of convert_from_rows over the whole synthetic workload.
+  value      : rows/s with the JCUDF row buffer already resident in HBM (CUDA events, max over ranks)
+  e2e        : the same pass through the host-buffer C-ABI entry point (pinned host rows in, host
+               columns out; H2D + kernel + D2H inside the timed region)
+  roofline   : algorithmic bytes per launch / measured kernel time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the oracle's threaded row->column loop (a stated stand-in for Spark's
+               InternalRow->ColumnarBatch) on a bounded sample, host cores
+--impl reference times that CPU path alone (no JVM / libcudf in this image: the reference itself
+cannot run).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spark-rapids-jni_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+# cudf type ids used by the workloads
+INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US, STRING, DEC32, DEC128 = 1, 2, 3, 4, 9, 10, 11, 15, 23, 25, 27
+SIZE = {INT8: 1, INT16: 2, INT32: 4, INT64: 8, FLOAT32: 4, FLOAT64: 8, BOOL8: 1, TS_US: 8, DEC32: 4, DEC128: 16}
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: 100M rows x 32 fixed-width cols convert_from_rows, 1xB200
+    "c2": dict(name="C2: 100M rows x 32 fixed-width cols ([INT8,INT16,INT32,INT64,FLOAT32,FLOAT64,BOOL8,TIMESTAMP_US]x4) "
+                    "convert_from_rows, 200 B rows, 20% nulls",
+               types=[INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US] * 4, rows=100_000_000, null_frac=0.2),
+    # BASELINE.json configs[3]: store_sales, from_rows fused with xxhash64(ss_item_sk, ss_ticket_number)
+    "c4": dict(name="C4: TPC-DS store_sales (23 cols, 104 B rows) convert_from_rows fused with xxhash64 partition key",
+               types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=400_000_000, null_frac=0.04, hash_keys=[1, 9]),
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes_per_row(types, row_size, hashed=False):
+    """read the padded row + write every column element + ncols/8 mask bytes (+ 8 B hash)."""
+    return row_size + sum(SIZE[t] for t in types) + len(types) / 8.0 + (8 if hashed else 0)
+
+
+# ---------------------------------------------------------------------------------------------------
+def synth_columns_gpu(torch, S, types, n, null_frac, seed):
+    """Seeded synthetic columns on the device (data = random bytes; BOOL8 in {0,1}; masks ~null_frac nulls)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    cols = []
+    words = (n + 31) // 32
+    for t in types:
+        sz = SIZE[t]
+        data = torch.empty(n * sz, dtype=torch.uint8, device="cuda")
+        step = 1 << 28
+        for o in range(0, n * sz, step):          # chunked: randint materialises int64 internally
+            m = min(step, n * sz - o)
+            data[o:o + m] = torch.randint(0, 256, (m,), dtype=torch.uint8, device="cuda", generator=g)
+        if t == BOOL8:
+            data &= 1
+        # valid with probability 1 - null_frac: compare a random byte per row, pack to words
+        mask = torch.empty(words, dtype=torch.int32, device="cuda")
+        wstep = 1 << 21
+        weights = (1 << torch.arange(32, device="cuda", dtype=torch.int64))
+        thr = int(round(null_frac * 256))
+        for o in range(0, words, wstep):
+            m = min(wstep, words - o)
+            bits = (torch.randint(0, 256, (m, 32), dtype=torch.uint8, device="cuda", generator=g) >= thr)
+            w = (bits.to(torch.int64) * weights).sum(dim=1)
+            mask[o:o + m] = torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+        cols.append(S.ColumnVector(S.DType(t), n, data, mask))
+    return cols
+
+
+def build_rows_gpu(torch, S, N, plan, cols, n, row_size):
+    """Produce the JCUDF rows of `cols` with OUR to_rows into ONE contiguous device buffer (the C ABI takes
+    caller-owned batch buffers, so the <=2 GiB batches are laid back to back)."""
+    import ctypes as C
+    lib = N.lib()
+    carr = (N.SrjColumn * len(cols))()
+    for i, c in enumerate(cols):
+        carr[i] = c._c()
+    batches = (N.SrjRowBatch * 4096)()
+    nb = C.c_int32(0)
+    st = int(torch.cuda.current_stream().cuda_stream)
+    N.check(lib.srj_to_rows_plan_batches(plan.handle, carr, n, None, batches, 4096, C.byref(nb), st))
+    rows = torch.empty(n * row_size, dtype=torch.uint8, device="cuda")
+    offs = torch.empty(n + nb.value, dtype=torch.int32, device="cuda")
+    optrs, dptrs = (C.c_void_p * nb.value)(), (C.c_void_p * nb.value)()
+    for b in range(nb.value):
+        optrs[b] = offs.data_ptr() + 4 * (batches[b].row_start + b)
+        dptrs[b] = rows.data_ptr() + batches[b].row_start * row_size
+    N.check(lib.srj_convert_to_rows(plan.handle, carr, n, None, batches, nb.value, optrs, dptrs, st))
+    torch.cuda.synchronize()
+    return rows, nb.value
+
+
+def run_ours(args, wl, rank, world):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    import srj_b200 as S
+    from srj_b200 import _native as N
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    types = wl["types"]
+    n = int(args.rows or wl["rows"])          # weak scaling: every rank converts the full per-GPU workload
+    plan = S.Plan.get([S.DType(t) for t in types])
+    row_size = plan.layout.fixed_row_size
+    hashed = "hash_keys" in wl
+    bpr = algorithmic_bytes_per_row(types, row_size, hashed)
+    lib = N.lib()
+
+    # ---- synthetic inputs (outside the timed region) ------------------------------------------------
+    src = synth_columns_gpu(torch, S, types, n, wl["null_frac"], seed=42 + rank)
+    rows, nbatches = build_rows_gpu(torch, S, N, plan, src, n, row_size)
+    words = (n + 31) // 32
+    outs = [S.ColumnVector(S.DType(t), n, torch.empty(n * SIZE[t], dtype=torch.uint8, device="cuda"),
+                           torch.empty(words, dtype=torch.int32, device="cuda")) for t in types]
+    carr = (N.SrjColumn * len(outs))()
+    for i, c in enumerate(outs):
+        carr[i] = c._c()
+    nulls = torch.zeros(len(types), dtype=torch.int64, device="cuda")
+    fh = None
+    hout = None
+    if hashed:
+        fh = N.SrjFusedHash()
+        fh.kind, fh.num_keys, fh.seed = N.HASH_XXHASH64, len(wl["hash_keys"]), 42
+        for i, k in enumerate(wl["hash_keys"]):
+            fh.key_columns[i] = k
+        hout = torch.empty(n, dtype=torch.int64, device="cuda")
+        fh.out = hout.data_ptr()
+    stream = torch.cuda.current_stream()
+    st = int(stream.cuda_stream)
+
+    def step():
+        N.check(lib.srj_convert_from_rows_fixed(plan.handle, rows.data_ptr(), None, rows.numel(), n, carr,
+                                                nulls.data_ptr(), None, C.byref(fh) if fh else None, st))
+
+    # correctness gate inside the bench: round trip equals the source columns (cheap, on device)
+    step()
+    torch.cuda.synchronize()
+    for a, b in zip(outs, src):
+        assert torch.equal(a.data, b.data) and torch.equal(a.mask, b.mask), "bench: from_rows(to_rows(x)) != x"
+    del src
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for a, b in evs:
+        a.record(stream)       # events on the launching stream: the conversion kernel is the only kernel between them
+        step()
+        b.record(stream)
+    t1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    tt = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    peak, peak_src = load_peaks()
+    achieved = bpr * n / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "srj::from_rows_kernel",
+                "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_row": bpr, "rows_per_launch": n,
+                "peak_source": peak_src}
+    tr = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(tr):
+        try:
+            j = json.load(open(tr))
+            roofline["traffic"] = j["dram_bytes_per_launch"] * (n / j["rows_per_launch"])
+            roofline["traffic_source"] = j.get("source")
+        except Exception:
+            pass
+
+    # ---- e2e: host rows -> host columns through the C-ABI host entry point --------------------------
+    e2e = None
+    cpu = None
+    if not args.no_e2e:
+        h_rows = torch.empty(n * row_size, dtype=torch.uint8, pin_memory=True)
+        h_rows.copy_(rows)
+        torch.cuda.synchronize()
+        h_cols = []
+        harr = (N.SrjColumn * len(types))()
+        for i, t in enumerate(types):
+            d = torch.empty(n * SIZE[t], dtype=torch.uint8, pin_memory=True)
+            m = torch.empty(words, dtype=torch.int32, pin_memory=True)
+            h_cols.append((d, m))
+            harr[i].type_id, harr[i].scale, harr[i].size = t, 0, n
+            harr[i].data, harr[i].null_mask, harr[i].offsets = d.data_ptr(), m.data_ptr(), None
+        h_nulls = np.zeros(len(types), np.int64)
+        h2d = n * row_size
+        d2h = sum(n * SIZE[t] + words * 4 for t in types) + 8 * len(types)
+
+        def e2e_step():
+            N.check(lib.srj_convert_from_rows_host(plan.handle, h_rows.data_ptr(), n, harr, h_nulls.ctypes.data, 0))
+
+        e2e_step()                                   # warm-up (also validates)
+        assert torch.equal(h_cols[3][0], outs[3].data.cpu()), "bench e2e: host result differs from device result"
+        barrier()
+        ksteps = max(1, min(args.steps, 3))
+        w0 = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()                               # synchronises internally (result is in host memory)
+        barrier()
+        e2e_s = (time.perf_counter() - w0) / ksteps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": ksteps, "ms_per_step": float(te[0]) * 1e3, "api": "srj_convert_from_rows_host (pinned host buffers)"}
+        if rank == 0:
+            cpu = cpu_baseline(types, row_size, h_rows.numpy(), min(n, args.cpu_sample_rows), bpr)
+        del h_rows, h_cols
+
+    if rank == 0:
+        line = {"metric": "rows_per_sec_convert_from_rows", "value": value, "unit": "rows/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": wl["name"], "rows_per_gpu": n, "row_bytes": row_size, "columns": len(types),
+                           "l2": "inputs+outputs (%.1f GB) >> 126 MB L2, no flush needed" % (bpr * n / 1e9),
+                           "launch": "one srj_convert_from_rows_fixed call over all rows (C ABI takes int64 row counts; "
+                                     "rows were produced by srj_convert_to_rows in %d <=2GiB batches)" % nbatches,
+                           "sharding": "contiguous row range per GPU, no data-path collective"},
+                "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": args.steps, "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthreads=None):
+    """Oracle's threaded row->column loop on a bounded sample of the same rows (host cores)."""
+    from oracle import oracle as O
+    nthreads = nthreads or os.cpu_count()
+    n = int(sample_rows)
+    cols = [O.HCol(t, np.empty(n * SIZE[t], np.uint8), np.empty((n + 31) // 32, np.uint32), None, 0, n) for t in types]
+    data = h_rows_np[: n * row_size]
+    O.from_rows_fixed_mt(data, n, cols, nthreads)            # warm-up / page-in
+    reps, t_total = 0, 0.0
+    while (t_total < 10.0 and reps < 50) if steps is None else reps < steps:
+        t0 = time.perf_counter()
+        O.from_rows_fixed_mt(data, n, cols, nthreads)
+        t_total += time.perf_counter() - t0
+        reps += 1
+    sec = t_total / reps
+    return {"value": n / sec, "unit": "rows/s", "cores": nthreads, "kind": "port",
+            "sample": f"{n} rows of the same workload x {reps} passes, {nthreads} OpenMP threads over row ranges "
+                      f"(oracle/srj_oracle.c orc_from_rows_fixed_mt), {bpr * n / sec / 1e9:.1f} GB/s algorithmic",
+            "ms_per_pass": sec * 1e3}
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (oracle port: the reference's own
+    code needs a JVM + libcudf, neither exists here).  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    types = wl["types"]
+    st, sz, voff, spr = O.compute_layout(types)
+    row_size = (spr + 7) // 8 * 8
+    n = int(min(args.rows or wl["rows"], args.cpu_sample_rows))
+    hashed = "hash_keys" in wl
+    bpr = algorithmic_bytes_per_row(types, row_size, hashed)
+    rng = np.random.Generator(np.random.Philox(42))
+    data = rng.integers(0, 256, n * row_size, dtype=np.uint8)      # any bytes are valid fixed-width JCUDF rows
+    nthreads = os.cpu_count()
+    cols = [O.HCol(t, np.empty(n * SIZE[t], np.uint8), np.empty((n + 31) // 32, np.uint32), None, 0, n) for t in types]
+    for _ in range(max(1, args.warmup)):
+        O.from_rows_fixed_mt(data, n, cols, nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.from_rows_fixed_mt(data, n, cols, nthreads)
+    sec = (time.perf_counter() - t0) / args.steps
+    v = n / sec
+    cpu = {"value": v, "unit": "rows/s", "cores": nthreads, "kind": "port",
+           "sample": f"{n} rows per step (bounded sample of the {wl['rows']}-row workload), {nthreads} OpenMP threads"}
+    print(json.dumps({"impl": "reference", "metric": "rows_per_sec_convert_from_rows", "value": v, "unit": "rows/s",
+                      "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": wl["name"], "rows_per_step": n, "row_bytes": row_size, "columns": len(types)},
+                      "cpu_baseline": cpu,
+                      "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0,
+                      "note": "CPU restatement of the reference algorithm (oracle port); the reference's CUDA path cannot be "
+                              "built here (needs libcudf+rmm+JDK)"}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (development only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+    else:
+        run_ours(args, wl, rank, world)
+
+
+if __name__ == "__main__":
+    main()

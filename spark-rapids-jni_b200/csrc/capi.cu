@@ -187,6 +187,7 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   int fitrows = tl.stage_bytes / S;
   int R       = fitrows / 32 * 32;
   if (R > 512) R = 512;
+  if (R >= 128) R = R / 128 * 128;  // 4 row groups per unit => predicate-free fast path
   if (R < 32) R = fitrows >= 16 ? 16 : 8;
   tl.tile_rows     = R;
   tl.rows_per_item = R >= 32 ? 32 : R;

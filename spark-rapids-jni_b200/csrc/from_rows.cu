@@ -7,15 +7,18 @@
 //                   byte range of the row buffer, moved global->shared by a single 1-D TMA bulk copy
 //                   (cp.async.bulk ... mbarrier::complete_tx) into a multi-stage ring, so ~2 stages
 //                   (>=100 KB) per SM are always in flight with no registers or LSU slots spent.
-//   consumer warps: lane = row.  For each width class (1/2/4/8/16 B) a warp item reads one field
-//                   of 32 consecutive rows from the tile and stores it to the column with one
-//                   coalesced store; validity bytes are bit-transposed with __ballot_sync into the
-//                   column masks; null counts are popc'd on the way; the row hash of the key
-//                   columns is computed in registers from the same tile.
+//   consumer warps: lane = row.  A work unit is (field, chunk of row groups): a few shared-memory
+//                   reads of one field of 32 consecutive rows, batched for ILP, then coalesced
+//                   st.global stores into the column; validity bytes are bit-transposed with
+//                   __ballot_sync into the column masks; null counts are popc'd on the way; the row
+//                   hash of the key columns is computed in registers from the same tile.
 //
-// Rows whose tile cannot be staged (row larger than a stage, unaligned buffers) take the SAFE
-// path: same code, reading global memory byte-wise.
+// The unit -> (field, chunk) map is a shift/mask of host-computed constants; full tiles of
+// fixed-stride tables run a predicate-free instantiation.  Rows whose tile cannot be staged (row
+// larger than a stage, unaligned buffers) take the SAFE path: same code, reading global memory
+// byte-wise.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -25,18 +28,16 @@
 
 namespace srj {
 
-constexpr int kConsumerWarps = 15;
-constexpr int kThreads       = (kConsumerWarps + 1) * 32;
-constexpr int kMaxStages     = 4;
-constexpr int kStageSlack    = 32;  // skew (<=8) + tail
+constexpr int kMaxStages  = 4;
+constexpr int kStageSlack = 32;  // skew (<=8) + tail
 
 struct StageHdr {
-  int64_t r0;        // first table row of the tile
-  int32_t rows;      // 0 = end of this CTA's range
-  int32_t safe;      // 1 = not staged: read rows from global memory byte-wise
-  int32_t skew;      // payload byte offset of global byte `gbase` (fixed-stride tiles)
+  int64_t r0;     // first table row of the tile
+  int32_t rows;   // 0 = end of this CTA's range
+  int32_t safe;   // 1 = not staged: read rows from global memory byte-wise
+  int32_t skew;   // payload byte offset of global byte `gbase` (fixed-stride tiles)
   int32_t pad;
-  int64_t gbase;     // global byte offset (from p.rows) that payload[skew] corresponds to
+  int64_t gbase;  // global byte offset (from p.rows) that payload[skew] corresponds to
 };
 
 struct FromRowsParams {
@@ -54,9 +55,15 @@ struct FromRowsParams {
   int32_t nstages;
   int32_t nentries;
   int32_t class_begin[kNumClasses + 1];
+  // static work schedule (host-computed): a unit = (entry slot, chunk of `gpu` row groups)
+  int32_t cs;                      // log2(chunks per slot)
+  int32_t gpu;                     // row groups per unit
+  int32_t cls_units[kNumClasses];  // units of each width class  (= slots << cs)
+  int32_t cls_ubase[kNumClasses];  // units before this class (balances warps across classes)
+  int32_t v_ubase;                 // units before the validity items
   const Entry* entries;
-  void* const* ent_dst;     // [nentries] column base pointers (STRING: offsets + 1)
-  uint32_t* const* masks;   // [ncols]
+  void* const* ent_dst;             // [nentries] column base pointers (STRING: offsets + 1)
+  uint32_t* const* masks;           // [ncols]
   unsigned long long* null_counts;  // [ncols] or NULL
   // fused hash
   int32_t hash_kind;
@@ -68,45 +75,61 @@ struct FromRowsParams {
   void* hash_out;
 };
 
-// ---- element movers ------------------------------------------------------------------------------
+// ---- element movers: load W bytes from the row image into registers, store them to the column -------
+template <int W>
+struct Reg {
+  uint32_t v[(W + 3) / 4];
+};
+
 template <int W, bool SAFE>
-__device__ __forceinline__ void move_elem(const uint8_t* src, uint8_t* dst)
+__device__ __forceinline__ Reg<W> ld_elem(const uint8_t* src)
 {
+  Reg<W> r;
   if constexpr (SAFE) {
-    uint8_t tmp[W];
 #pragma unroll
-    for (int i = 0; i < W; ++i) tmp[i] = src[i];
-    if constexpr (W == 1) {
-      *dst = tmp[0];
-    } else if constexpr (W == 2) {
-      *reinterpret_cast<uint16_t*>(dst) = static_cast<uint16_t>(tmp[0] | (tmp[1] << 8));
-    } else if constexpr (W == 4) {
-      *reinterpret_cast<uint32_t*>(dst) = hash::ld_u32_bytes(tmp);
-    } else if constexpr (W == 8) {
-      *reinterpret_cast<uint64_t*>(dst) = hash::ld_u64_bytes(tmp);
-    } else {
-      uint4 v;
-      v.x = hash::ld_u32_bytes(tmp);
-      v.y = hash::ld_u32_bytes(tmp + 4);
-      v.z = hash::ld_u32_bytes(tmp + 8);
-      v.w = hash::ld_u32_bytes(tmp + 12);
-      *reinterpret_cast<uint4*>(dst) = v;
-    }
+    for (int i = 0; i < (W + 3) / 4; ++i) r.v[i] = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) r.v[i / 4] |= static_cast<uint32_t>(src[i]) << (8 * (i & 3));
   } else {
     if constexpr (W == 1) {
-      *dst = *src;
+      r.v[0] = *src;
     } else if constexpr (W == 2) {
-      *reinterpret_cast<uint16_t*>(dst) = *reinterpret_cast<const uint16_t*>(src);
+      r.v[0] = *reinterpret_cast<const uint16_t*>(src);
     } else if constexpr (W == 4) {
-      *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(src);
+      r.v[0] = *reinterpret_cast<const uint32_t*>(src);
     } else if constexpr (W == 8) {
-      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
+      const uint2 a = *reinterpret_cast<const uint2*>(src);
+      r.v[0]        = a.x;
+      r.v[1]        = a.y;
     } else {
-      // rows are only 8-byte aligned (JCUDF_ROW_ALIGNMENT, RC:63): two 8-byte reads, one 16-byte store
+      // rows are only 8-byte aligned (JCUDF_ROW_ALIGNMENT, RC:63): two 8-byte reads
       const uint2 a = *reinterpret_cast<const uint2*>(src);
       const uint2 b = *reinterpret_cast<const uint2*>(src + 8);
-      *reinterpret_cast<uint4*>(dst) = make_uint4(a.x, a.y, b.x, b.y);
+      r.v[0]        = a.x;
+      r.v[1]        = a.y;
+      r.v[2]        = b.x;
+      r.v[3]        = b.y;
     }
+  }
+  return r;
+}
+
+// explicit st.global: the column pointers come out of a shared-memory table, so the compiler cannot
+// infer the address space on its own (it would emit generic ST)
+template <int W>
+__device__ __forceinline__ void st_elem(uint8_t* dst, const Reg<W>& r)
+{
+  if constexpr (W == 1) {
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(dst), "r"(r.v[0]));
+  } else if constexpr (W == 2) {
+    asm volatile("st.global.u16 [%0], %1;" ::"l"(dst), "h"(static_cast<uint16_t>(r.v[0])));
+  } else if constexpr (W == 4) {
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(r.v[0]));
+  } else if constexpr (W == 8) {
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(r.v[0]), "r"(r.v[1]));
+  } else {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+                 "r"(r.v[3]));
   }
 }
 
@@ -147,64 +170,101 @@ struct SmemTables {
   const int32_t* ent_start;  // [nentries]
   uint8_t* const* ent_dst;   // [nentries]
   uint32_t* const* masks;    // [ncols]
-  int32_t* nulls;            // [ncols]
+  int32_t* nulls;            // [ncols] or NULL
 };
 
-// Process one tile.  `base` + row offset gives the row's first byte:
-//   s_off != NULL : base + (uint32)s_off[i]
-//   s_off == NULL : base + i * stride
-template <bool SAFE>
-__device__ __forceinline__ void process_tile(const FromRowsParams& p, const SmemTables& t, const uint8_t* base,
-                                             const int32_t* s_off, int64_t stride, int64_t r0, int rows,
-                                             int cw /* consumer warp index */)
+// Per-consumer-warp schedule constants, computed once per CTA.
+struct WarpSched {
+  int ustart[kNumClasses];  // first unit of each width class for this warp
+  int vstart;               // first validity item for this warp
+  int sub, lr;              // lane -> (entry within slot, row within group)
+};
+
+// Where the rows of a tile are: base + s_off[i] (VAR) or base + i * stride.
+struct TileView {
+  const uint8_t* base;
+  const int32_t* s_off;
+  uint32_t stride;
+  int64_t r0;
+  int rows;
+};
+
+template <bool VAR>
+__device__ __forceinline__ const uint8_t* row_ptr(const TileView& tv, int i)
 {
-  const int lane = lane_id();
-  auto rowptr    = [&](int i) -> const uint8_t* {
-    return s_off ? base + static_cast<uint32_t>(s_off[i]) : base + static_cast<int64_t>(i) * stride;
-  };
+  if constexpr (VAR) return tv.base + static_cast<uint32_t>(tv.s_off[i]);
+  else return tv.base + static_cast<uint32_t>(i) * tv.stride;
+}
 
-  // ---- fixed-width fields ------------------------------------------------------------------------
-  const int rpl     = p.rpl;
-  const int cpi     = 32 / rpl;
-  const int sub     = lane / rpl;
-  const int lr      = lane - sub * rpl;
-  const int ngroups = (rows + rpl - 1) / rpl;
-
-  auto run_class = [&](auto wtag, int k) {
-    constexpr int W  = decltype(wtag)::value;
-    const int nb     = p.class_begin[k];
-    const int ne     = p.class_begin[k + 1];
-    const int nslots = (ne - nb + cpi - 1) / cpi;
-    const int total  = nslots * ngroups;
-    for (int item = cw; item < total; item += kConsumerWarps) {
-      const int g    = item / nslots;
-      const int slot = item - g * nslots;
-      const int e    = nb + slot * cpi + sub;
-      const int row  = g * rpl + lr;
-      if (e < ne && row < rows) {
-        const uint8_t* src = rowptr(row) + t.ent_start[e];
-        uint8_t* dst       = t.ent_dst[e] + (r0 + row) * W;
-        move_elem<W, SAFE>(src, dst);
+// ---- fixed-width fields of one width class -----------------------------------------------------------
+// PRED=false: full tile of a fixed-stride table -- no row predicates at all.
+template <int W, int NCW, int RPL, bool VAR, bool PRED, bool SAFE>
+__device__ __forceinline__ void transpose_class(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
+                                                const TileView& tv, int k)
+{
+  constexpr int CPI = 32 / RPL;
+  constexpr int B   = W >= 16 ? 2 : 4;  // loads in flight per lane before the stores
+  const int nb      = p.class_begin[k];
+  const int ne      = p.class_begin[k + 1];
+  const int total   = p.cls_units[k];
+  const int gpu     = p.gpu;
+  const int chmask  = (1 << p.cs) - 1;
+  for (int u = ws.ustart[k]; u < total; u += NCW) {
+    const int slot = u >> p.cs;
+    const int gc   = u & chmask;
+    const int e    = nb + slot * CPI + ws.sub;
+    if (CPI > 1 && e >= ne) continue;
+    const int32_t start = t.ent_start[e];
+    int row             = gc * gpu * RPL + ws.lr;
+    uint8_t* dst        = t.ent_dst[e] + (tv.r0 + row) * W;
+    if constexpr (!VAR && !PRED) {
+      const uint8_t* src     = tv.base + static_cast<uint32_t>(row) * tv.stride + start;
+      const uint32_t gstride = RPL * tv.stride;
+      for (int gi = 0; gi < gpu; gi += B) {  // host guarantees gpu % B == 0 for this instantiation
+        Reg<W> v[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) v[j] = ld_elem<W, false>(src + j * gstride);
+#pragma unroll
+        for (int j = 0; j < B; ++j) st_elem<W>(dst + j * RPL * W, v[j]);
+        src += B * gstride;
+        dst += B * RPL * W;
+      }
+    } else {
+      for (int gi = 0; gi < gpu; gi += B) {
+        Reg<W> v[B];
+        bool ok[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          const int rj = row + j * RPL;
+          ok[j]        = (gi + j < gpu) && (rj < tv.rows);
+          if (ok[j]) v[j] = ld_elem<W, SAFE>(row_ptr<VAR>(tv, rj) + start);
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+          if (ok[j]) st_elem<W>(dst + j * RPL * W, v[j]);
+        row += B * RPL;
+        dst += B * RPL * W;
       }
     }
-  };
-  run_class(std::integral_constant<int, 16>{}, 4);
-  run_class(std::integral_constant<int, 8>{}, 3);
-  run_class(std::integral_constant<int, 4>{}, 2);
-  run_class(std::integral_constant<int, 2>{}, 1);
-  run_class(std::integral_constant<int, 1>{}, 0);
+  }
+}
 
-  // ---- validity: bit-transpose row bytes -> column mask words (RC:1062-1071 semantics) ----------
+// ---- validity: bit-transpose row bytes -> column mask words (RC:1062-1071 semantics) -------------------
+template <int NCW, bool VAR, bool PRED>
+__device__ __forceinline__ void validity_tile(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
+                                              const TileView& tv)
+{
+  const int lane   = lane_id();
   const int nvb    = (p.ncols + 7) >> 3;
-  const int ng32   = (rows + 31) >> 5;
+  const int ng32   = (tv.rows + 31) >> 5;
   const int vitems = nvb * ng32;
-  for (int item = cw; item < vitems; item += kConsumerWarps) {
-    const int g       = item / nvb;
-    const int b       = item - g * nvb;
-    const int row     = g * 32 + lane;
-    const bool active = row < rows;
-    uint32_t byte     = 0;
-    if (active) byte = rowptr(row)[p.validity_offset + b];
+  if (ws.vstart >= vitems) return;
+  int g = ws.vstart / nvb;  // one division per tile; then incremental
+  int b = ws.vstart - g * nvb;
+  for (int item = ws.vstart; item < vitems; item += NCW) {
+    const int row = g * 32 + lane;
+    uint32_t byte = 0;
+    if (!PRED || row < tv.rows) byte = row_ptr<VAR>(tv, row)[p.validity_offset + b];
     uint32_t mine = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -213,63 +273,101 @@ __device__ __forceinline__ void process_tile(const FromRowsParams& p, const Smem
     }
     const int col = b * 8 + lane;
     if (lane < 8 && col < p.ncols) {
-      const int nact       = tmin(32, rows - g * 32);
-      const uint32_t amask = nact == 32 ? 0xffffffffu : ((1u << nact) - 1u);
-      const int nnull      = __popc(~mine & amask);
-      if (nnull && t.nulls) atomicAdd(&t.nulls[col], nnull);
-      const int64_t rg   = r0 + g * 32;  // multiple of 8
-      uint8_t* mp        = reinterpret_cast<uint8_t*>(t.masks[col]) + (rg >> 3);
-      const bool tbl_end = (rg + nact) == p.num_rows;
-      int nbytes         = (nact + 7) >> 3;
-      // the table's last mask word is written whole so its tail bits are 0 (RC:1081-1090)
-      if (tbl_end) nbytes = static_cast<int>(round_up64((rg >> 3) + nbytes, 4) - (rg >> 3));
-      if (nbytes == 4 && ((rg & 31) == 0)) {
-        *reinterpret_cast<uint32_t*>(mp) = mine;
+      const int64_t rg = tv.r0 + g * 32;  // multiple of 8 (of 32 when !PRED)
+      uint8_t* mp      = reinterpret_cast<uint8_t*>(t.masks[col]) + (rg >> 3);
+      if constexpr (!PRED) {
+        const int nnull = __popc(~mine);
+        if (nnull && t.nulls) atomicAdd(&t.nulls[col], nnull);
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(mp), "r"(mine));
       } else {
-        for (int i = 0; i < nbytes; ++i) mp[i] = static_cast<uint8_t>(static_cast<uint64_t>(mine) >> (8 * i));
+        const int nact       = tmin(32, tv.rows - g * 32);
+        const uint32_t amask = nact == 32 ? 0xffffffffu : ((1u << nact) - 1u);
+        const int nnull      = __popc(~mine & amask);
+        if (nnull && t.nulls) atomicAdd(&t.nulls[col], nnull);
+        const bool tbl_end = (rg + nact) == p.num_rows;
+        int nbytes         = (nact + 7) >> 3;
+        // the table's last mask word is written whole so its tail bits are 0 (RC:1081-1090)
+        if (tbl_end) nbytes = static_cast<int>(round_up64((rg >> 3) + nbytes, 4) - (rg >> 3));
+        if (nbytes == 4 && ((rg & 31) == 0)) {
+          asm volatile("st.global.u32 [%0], %1;" ::"l"(mp), "r"(mine));
+        } else {
+          for (int i = 0; i < nbytes; ++i) mp[i] = static_cast<uint8_t>(static_cast<uint64_t>(mine) >> (8 * i));
+        }
       }
     }
-  }
-
-  // ---- fused row hash of the key columns ----------------------------------------------------------
-  if (p.hash_kind != SRJ_HASH_NONE) {
-    for (int g = cw; g < ng32; g += kConsumerWarps) {
-      const int row = g * 32 + lane;
-      if (row >= rows) continue;
-      const uint8_t* rp = rowptr(row);
-      uint64_t hx       = static_cast<uint64_t>(p.hash_seed);
-      uint32_t hm       = static_cast<uint32_t>(p.hash_seed);
-      uint32_t hh       = 0;
-      for (int k = 0; k < p.hash_nkeys; ++k) {
-        const int c      = p.key_col[k];
-        const bool valid = (rp[p.validity_offset + (c >> 3)] >> (c & 7)) & 1u;
-        const int32_t ty = p.key_type[k];
-        const int sz     = key_size(ty);
-        uint64_t v = 0, v2 = 0;
-        if (valid) {
-          v = load_key<SAFE>(rp + p.key_start[k], sz);
-          if (sz == 16) v2 = load_key<SAFE>(rp + p.key_start[k] + 8, 8);
-        }
-        if (p.hash_kind == SRJ_HASH_XXHASH64) {
-          if (valid) hx = hash::xx_fixed(ty, v, v2, hx);
-        } else if (p.hash_kind == SRJ_HASH_MURMUR3_32) {
-          if (valid) hm = hash::mm_fixed(ty, v, v2, hm);
-        } else {
-          hh = 31u * hh + (valid ? static_cast<uint32_t>(hash::hive_fixed(ty, v)) : 0u);
-        }
-      }
-      if (p.hash_kind == SRJ_HASH_XXHASH64)
-        reinterpret_cast<uint64_t*>(p.hash_out)[r0 + row] = hx;
-      else if (p.hash_kind == SRJ_HASH_MURMUR3_32)
-        reinterpret_cast<uint32_t*>(p.hash_out)[r0 + row] = hm;
-      else
-        reinterpret_cast<uint32_t*>(p.hash_out)[r0 + row] = hh;
+    b += NCW;
+    while (b >= nvb) {
+      b -= nvb;
+      ++g;
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_constant__ FromRowsParams p)
+// ---- fused row hash of the key columns (lane = row), chained across keys with the Spark rules ------------
+template <int NCW, bool VAR, bool SAFE>
+__device__ __noinline__ void hash_tile(const FromRowsParams& p, const TileView& tv, int cw)
 {
+  const int lane = lane_id();
+  const int ng32 = (tv.rows + 31) >> 5;
+  for (int g = cw; g < ng32; g += NCW) {
+    const int row = g * 32 + lane;
+    if (row >= tv.rows) continue;
+    const uint8_t* rp = row_ptr<VAR>(tv, row);
+    uint64_t hx       = static_cast<uint64_t>(p.hash_seed);
+    uint32_t hm       = static_cast<uint32_t>(p.hash_seed);
+    uint32_t hh       = 0;
+    for (int k = 0; k < p.hash_nkeys; ++k) {
+      const int c      = p.key_col[k];
+      const bool valid = (rp[p.validity_offset + (c >> 3)] >> (c & 7)) & 1u;
+      const int32_t ty = p.key_type[k];
+      const int sz     = key_size(ty);
+      uint64_t v = 0, v2 = 0;
+      if (valid) {
+        v = load_key<SAFE>(rp + p.key_start[k], sz);
+        if (sz == 16) v2 = load_key<SAFE>(rp + p.key_start[k] + 8, 8);
+      }
+      if (p.hash_kind == SRJ_HASH_XXHASH64) {
+        if (valid) hx = hash::xx_fixed(ty, v, v2, hx);
+      } else if (p.hash_kind == SRJ_HASH_MURMUR3_32) {
+        if (valid) hm = hash::mm_fixed(ty, v, v2, hm);
+      } else {
+        hh = 31u * hh + (valid ? static_cast<uint32_t>(hash::hive_fixed(ty, v)) : 0u);
+      }
+    }
+    if (p.hash_kind == SRJ_HASH_XXHASH64)
+      reinterpret_cast<uint64_t*>(p.hash_out)[tv.r0 + row] = hx;
+    else if (p.hash_kind == SRJ_HASH_MURMUR3_32)
+      reinterpret_cast<uint32_t*>(p.hash_out)[tv.r0 + row] = hm;
+    else
+      reinterpret_cast<uint32_t*>(p.hash_out)[tv.r0 + row] = hh;
+  }
+}
+
+template <int NCW, int RPL, bool VAR, bool PRED, bool SAFE>
+__device__ __forceinline__ void process_tile(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
+                                             const TileView& tv, int cw)
+{
+  transpose_class<16, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 4);
+  transpose_class<8, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 3);
+  transpose_class<4, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 2);
+  transpose_class<2, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 1);
+  transpose_class<1, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 0);
+  validity_tile<NCW, VAR, PRED>(p, t, ws, tv);
+  if (p.hash_kind != SRJ_HASH_NONE) hash_tile<NCW, VAR, SAFE>(p, tv, cw);
+}
+
+// SAFE / partial tiles are kept out of line so they do not inflate the fast path's registers
+template <int NCW, int RPL, bool VAR, bool SAFE>
+__device__ __noinline__ void process_tile_slow(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
+                                               const TileView& tv, int cw)
+{
+  process_tile<NCW, RPL, VAR, true, SAFE>(p, t, ws, tv, cw);
+}
+
+template <int NCW, int RPL, bool VAR>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __grid_constant__ FromRowsParams p)
+{
+  constexpr int kThreads = (NCW + 1) * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int NS         = p.nstages;
   const int stage_span = p.stage_bytes + kStageSlack;
@@ -296,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumerWarps);
+      mbar_init(&empty[s], NCW);
     }
     fence_mbar_init();
   }
@@ -305,7 +403,6 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
   const int64_t c0 = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
   const int64_t c1 = tmin(p.num_rows, c0 + p.rows_per_cta);
   const int lane   = lane_id();
-  const bool fixed = p.row_offsets == nullptr;
   // the staged fast path needs 8-byte aligned rows
   const bool base_ok = (reinterpret_cast<uintptr_t>(p.rows) & 7) == 0;
 
@@ -316,7 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
     for (;; ++it) {
       const int s        = it % NS;
       const uint32_t par = ((it / NS) & 1) ^ 1;
-      mbar_wait(&empty[s], par);  // first pass over the ring returns immediately
+      if (lane == 0) mbar_wait(&empty[s], par);  // first pass over the ring returns immediately
+      __syncwarp();
       uint8_t* pay  = payload0 + static_cast<size_t>(s) * stage_span;
       int32_t* soff = soff0 + static_cast<size_t>(s) * soff_span;
       StageHdr* h   = hdr0 + s;
@@ -330,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
       int rows    = static_cast<int>(tmin<int64_t>(p.tile_rows, c1 - r));
       int64_t glo = 0, ghi = 0;  // global byte range [glo, ghi) from p.rows
       bool safe   = !base_ok;
-      if (fixed) {
+      if constexpr (!VAR) {
         glo = r * p.row_stride;
         ghi = (r + rows) * static_cast<int64_t>(p.row_stride);
         if (ghi - glo > p.stage_bytes) safe = true;
@@ -365,9 +463,9 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
         glo = a0;
         ghi = p.row_offsets[r + rows];
       }
-      uint32_t tx     = 0;
-      int32_t skew    = 0;
-      uintptr_t t_lo  = 0, fl = 0;
+      uint32_t tx    = 0;
+      int32_t skew   = 0;
+      uintptr_t t_lo = 0, fl = 0;
       if (!safe) {
         // 16-byte aligned TMA window inside [rows, rows + rows_bytes); <16-byte head/tail remainders
         // (8-byte units) are copied by hand
@@ -378,13 +476,13 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
         fl                   = a_lo & ~uintptr_t{15};
         skew                 = static_cast<int32_t>(a_lo - fl);  // payload[skew] == global byte glo
         t_lo                 = fl;
-        if (t_lo < b_lo) t_lo = fl + 16;                          // cannot read before the buffer
+        if (t_lo < b_lo) t_lo = fl + 16;  // cannot read before the buffer
         uintptr_t t_hi = (a_hi + 15) & ~uintptr_t{15};
-        if (t_hi > b_hi) t_hi = a_hi & ~uintptr_t{15};            // cannot read past the buffer
+        if (t_hi > b_hi) t_hi = a_hi & ~uintptr_t{15};  // cannot read past the buffer
         if (t_hi > t_lo) tx = static_cast<uint32_t>(t_hi - t_lo);
-        uintptr_t h_end = tmin(tmax(t_lo, a_lo), a_hi);             // head  [a_lo, h_end)
-        if (tx == 0) h_end = a_hi;                                // tiny tile: all by hand
-        const uintptr_t t_beg = tmax(tmin(t_hi, a_hi), h_end);      // tail  [t_beg, a_hi)
+        uintptr_t h_end = tmin(tmax(t_lo, a_lo), a_hi);  // head  [a_lo, h_end)
+        if (tx == 0) h_end = a_hi;                        // tiny tile: all by hand
+        const uintptr_t t_beg = tmax(tmin(t_hi, a_hi), h_end);  // tail  [t_beg, a_hi)
         if (lane == 0) {
           for (uintptr_t a = a_lo; a < h_end; a += 8)
             *reinterpret_cast<uint2*>(pay + (a - fl)) = *reinterpret_cast<const uint2*>(a);
@@ -414,6 +512,12 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
     // =================================== consumers ===================================
     const int cw = warp_id() - 1;
     SmemTables t{s_ent_start, s_ent_dst, s_masks, p.null_counts ? s_nulls : nullptr};
+    WarpSched ws;
+#pragma unroll
+    for (int k = 0; k < kNumClasses; ++k) ws.ustart[k] = (cw + NCW - (p.cls_ubase[k] % NCW)) % NCW;
+    ws.vstart = (cw + NCW - (p.v_ubase % NCW)) % NCW;
+    ws.sub    = lane / RPL;
+    ws.lr     = lane - ws.sub * RPL;
     for (int it = 0;; ++it) {
       const int s        = it % NS;
       const uint32_t par = (it / NS) & 1;
@@ -422,16 +526,22 @@ __global__ void __launch_bounds__(kThreads, 1) from_rows_kernel(const __grid_con
       if (h.rows == 0) break;
       const uint8_t* pay  = payload0 + static_cast<size_t>(s) * stage_span;
       const int32_t* soff = soff0 + static_cast<size_t>(s) * soff_span;
+      TileView tv;
+      tv.s_off  = soff;
+      tv.stride = static_cast<uint32_t>(p.row_stride);
+      tv.r0     = h.r0;
+      tv.rows   = h.rows;
       if (!h.safe) {
-        if (fixed)
-          process_tile<false>(p, t, pay + h.skew, nullptr, p.row_stride, h.r0, h.rows, cw);
+        tv.base = VAR ? pay : pay + h.skew;
+        if (!VAR && h.rows == p.tile_rows && (p.gpu & 3) == 0)
+          process_tile<NCW, RPL, VAR, false, false>(p, t, ws, tv, cw);
+        else if (VAR)
+          process_tile<NCW, RPL, VAR, true, false>(p, t, ws, tv, cw);  // var-width tiles are always predicated
         else
-          process_tile<false>(p, t, pay, soff, 0, h.r0, h.rows, cw);
+          process_tile_slow<NCW, RPL, VAR, false>(p, t, ws, tv, cw);
       } else {
-        if (fixed)
-          process_tile<true>(p, t, p.rows + h.gbase, nullptr, p.row_stride, h.r0, h.rows, cw);
-        else
-          process_tile<true>(p, t, p.rows, soff, 0, h.r0, h.rows, cw);
+        tv.base = VAR ? p.rows : p.rows + h.gbase;
+        process_tile_slow<NCW, RPL, VAR, true>(p, t, ws, tv, cw);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -456,6 +566,22 @@ size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols)
   return (b + 127) & ~size_t{127};
 }
 
+template <int NCW>
+static int launch_variant(const FromRowsParams& p, unsigned grid, size_t smem, cudaStream_t stream)
+{
+  auto go = [&](auto kern) -> int {
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    kern<<<grid, (NCW + 1) * 32, smem, stream>>>(p);
+    return SRJ_OK;
+  };
+  const bool var = p.row_offsets != nullptr;
+  switch (p.rpl) {
+    case 32: return var ? go(from_rows_kernel<NCW, 32, true>) : go(from_rows_kernel<NCW, 32, false>);
+    case 16: return var ? go(from_rows_kernel<NCW, 16, true>) : go(from_rows_kernel<NCW, 16, false>);
+    default: return var ? go(from_rows_kernel<NCW, 8, true>) : go(from_rows_kernel<NCW, 8, false>);
+  }
+}
+
 int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
                      int64_t num_rows, void* const* d_ent_dst, uint32_t* const* d_masks, int64_t* d_null_counts,
                      const srj_fused_hash* fh, cudaStream_t stream)
@@ -475,6 +601,25 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   p.nstages         = plan->tiling.num_stages;
   p.nentries        = static_cast<int32_t>(plan->fr_entries.size());
   for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->fr_class_begin[k];
+  {
+    // static schedule: split each slot's row groups into 2^cs chunks until there are enough units to
+    // balance the consumer warps; the predicate-free instantiation needs gpu % 4 == 0
+    const int cpi     = 32 / p.rpl;
+    const int ngroups = (p.tile_rows + p.rpl - 1) / p.rpl;
+    int slots         = 0;
+    for (int k = 0; k < kNumClasses; ++k) slots += (p.class_begin[k + 1] - p.class_begin[k] + cpi - 1) / cpi;
+    int cs = 0;
+    while ((slots << cs) < 96 && (ngroups % (8 << cs)) == 0) ++cs;  // keeps gpu a multiple of 4
+    p.cs  = cs;
+    p.gpu = (ngroups + (1 << cs) - 1) >> cs;
+    int ub = 0;
+    for (int k = kNumClasses - 1; k >= 0; --k) {  // kernel runs the classes 16,8,4,2,1
+      p.cls_ubase[k] = ub;
+      p.cls_units[k] = ((p.class_begin[k + 1] - p.class_begin[k] + cpi - 1) / cpi) << cs;
+      ub += p.cls_units[k];
+    }
+    p.v_ubase = ub;
+  }
   p.entries     = plan->d_fr_entries;
   p.ent_dst     = d_ent_dst;
   p.masks       = d_masks;
@@ -503,14 +648,14 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   p.rows_per_cta       = tiles_per * T;
   grid                 = (num_rows + p.rows_per_cta - 1) / p.rows_per_cta;
   const size_t smem    = from_rows_smem_bytes(plan->tiling, p.nentries, p.ncols);
-  static thread_local int configured_dev = -1;
-  static thread_local size_t configured_smem = 0;
-  if (configured_dev != dev || configured_smem < smem) {
-    SRJ_CUDA_TRY(cudaFuncSetAttribute(from_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    configured_dev  = dev;
-    configured_smem = 232448;
+  static const int variant = []() { const char* e = getenv("SRJ_FR_VARIANT"); return e ? atoi(e) : 0; }();
+  int rc;
+  switch (variant) {
+    case 1: rc = launch_variant<31>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 2: rc = launch_variant<7>(p, static_cast<unsigned>(grid), smem, stream); break;
+    default: rc = launch_variant<15>(p, static_cast<unsigned>(grid), smem, stream); break;
   }
-  from_rows_kernel<<<static_cast<unsigned>(grid), kThreads, smem, stream>>>(p);
+  if (rc != SRJ_OK) return rc;
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }
