@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -189,6 +190,9 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   if (R > 512) R = 512;
   if (R >= 128) R = R / 128 * 128;  // 4 row groups per unit => predicate-free fast path
   if (R < 32) R = fitrows >= 16 ? 16 : 8;
+  // development knobs (tuning only)
+  if (const char* e = getenv("SRJ_FR_STAGES")) tl.num_stages = atoi(e);
+  if (const char* e = getenv("SRJ_FR_TILE_ROWS")) { R = atoi(e); tl.stage_bytes = std::max(R * S, 4096); }
   tl.tile_rows     = R;
   tl.rows_per_item = R >= 32 ? 32 : R;
 

@@ -45,7 +45,7 @@ struct FromRowsParams {
   const int32_t* row_offsets;  // NULL => fixed stride
   int64_t rows_bytes;
   int64_t num_rows;
-  int64_t rows_per_cta;
+  int64_t super_rows;  // rows per super-tile; super-tiles are dealt round-robin to the CTAs
   int32_t ncols;
   int32_t validity_offset;
   int32_t row_stride;
@@ -249,30 +249,55 @@ __device__ __forceinline__ void transpose_class(const FromRowsParams& p, const S
   }
 }
 
-// ---- validity: bit-transpose row bytes -> column mask words (RC:1062-1071 semantics) -------------------
-template <int NCW, bool VAR, bool PRED>
+// ---- validity: 32x32 bit-matrix transpose across the warp ----------------------------------------------
+// lane = row holds 32 validity bits (32 columns) of its row; five shuffle/xor butterfly steps leave
+// lane = column holding the 32-row mask word of that column (RC:1062-1071 builds the same word with
+// one __ballot_sync per column; this does 32 columns in ~30 instructions).
+__device__ __forceinline__ uint32_t transpose32(uint32_t r, int lane)
+{
+  uint32_t m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, r, j);
+    if ((lane & j) == 0) {
+      const uint32_t t = ((r >> j) ^ other) & m;
+      r ^= t << j;
+    } else {
+      const uint32_t t = ((other >> j) ^ r) & m;
+      r ^= t;
+    }
+    m ^= m << (j >> 1);
+  }
+  return r;
+}
+
+template <int NCW, bool VAR, bool PRED, bool SAFE>
 __device__ __forceinline__ void validity_tile(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
                                               const TileView& tv)
 {
   const int lane   = lane_id();
   const int nvb    = (p.ncols + 7) >> 3;
+  const int nq     = (p.ncols + 31) >> 5;  // groups of 32 columns
   const int ng32   = (tv.rows + 31) >> 5;
-  const int vitems = nvb * ng32;
+  const int vitems = nq * ng32;
   if (ws.vstart >= vitems) return;
-  int g = ws.vstart / nvb;  // one division per tile; then incremental
-  int b = ws.vstart - g * nvb;
+  int g = ws.vstart / nq;  // one division per tile; then incremental
+  int q = ws.vstart - g * nq;
   for (int item = ws.vstart; item < vitems; item += NCW) {
     const int row = g * 32 + lane;
-    uint32_t byte = 0;
-    if (!PRED || row < tv.rows) byte = row_ptr<VAR>(tv, row)[p.validity_offset + b];
-    uint32_t mine = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t w = __ballot_sync(0xffffffffu, (byte >> k) & 1u);
-      if (lane == k) mine = w;
+    uint32_t r    = 0;
+    if (!PRED || row < tv.rows) {
+      const uint8_t* vp = row_ptr<VAR>(tv, row) + p.validity_offset + 4 * q;
+      const int nbv     = tmin(4, nvb - 4 * q);
+      if (!SAFE && nbv == 4 && ((p.validity_offset & 3) == 0)) {
+        r = *reinterpret_cast<const uint32_t*>(vp);  // rows are 8-byte aligned
+      } else {
+        for (int i = 0; i < nbv; ++i) r |= static_cast<uint32_t>(vp[i]) << (8 * i);
+      }
     }
-    const int col = b * 8 + lane;
-    if (lane < 8 && col < p.ncols) {
+    const uint32_t mine = transpose32(r, lane);  // lane = column 32q + lane, bit = row
+    const int col       = q * 32 + lane;
+    if (col < p.ncols) {
       const int64_t rg = tv.r0 + g * 32;  // multiple of 8 (of 32 when !PRED)
       uint8_t* mp      = reinterpret_cast<uint8_t*>(t.masks[col]) + (rg >> 3);
       if constexpr (!PRED) {
@@ -288,16 +313,17 @@ __device__ __forceinline__ void validity_tile(const FromRowsParams& p, const Sme
         int nbytes         = (nact + 7) >> 3;
         // the table's last mask word is written whole so its tail bits are 0 (RC:1081-1090)
         if (tbl_end) nbytes = static_cast<int>(round_up64((rg >> 3) + nbytes, 4) - (rg >> 3));
+        const uint32_t w = mine & amask;
         if (nbytes == 4 && ((rg & 31) == 0)) {
-          asm volatile("st.global.u32 [%0], %1;" ::"l"(mp), "r"(mine));
+          asm volatile("st.global.u32 [%0], %1;" ::"l"(mp), "r"(w));
         } else {
-          for (int i = 0; i < nbytes; ++i) mp[i] = static_cast<uint8_t>(static_cast<uint64_t>(mine) >> (8 * i));
+          for (int i = 0; i < nbytes; ++i) mp[i] = static_cast<uint8_t>(static_cast<uint64_t>(w) >> (8 * i));
         }
       }
     }
-    b += NCW;
-    while (b >= nvb) {
-      b -= nvb;
+    q += NCW;
+    while (q >= nq) {
+      q -= nq;
       ++g;
     }
   }
@@ -352,7 +378,7 @@ __device__ __forceinline__ void process_tile(const FromRowsParams& p, const Smem
   transpose_class<4, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 2);
   transpose_class<2, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 1);
   transpose_class<1, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 0);
-  validity_tile<NCW, VAR, PRED>(p, t, ws, tv);
+  validity_tile<NCW, VAR, PRED, SAFE>(p, t, ws, tv);
   if (p.hash_kind != SRJ_HASH_NONE) hash_tile<NCW, VAR, SAFE>(p, tv, cw);
 }
 
@@ -400,16 +426,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
   }
   __syncthreads();
 
-  const int64_t c0 = static_cast<int64_t>(blockIdx.x) * p.rows_per_cta;
-  const int64_t c1 = tmin(p.num_rows, c0 + p.rows_per_cta);
-  const int lane   = lane_id();
+  const int lane = lane_id();
   // the staged fast path needs 8-byte aligned rows
   const bool base_ok = (reinterpret_cast<uintptr_t>(p.rows) & 7) == 0;
 
   if (warp_id() == 0) {
     // =================================== producer ===================================
-    int64_t r = c0;
-    int it    = 0;
+    // Super-tiles (a few tiles of consecutive rows) are dealt round-robin to the CTAs, so at any moment
+    // the whole grid streams through one contiguous window of the row buffer and of every column --
+    // the access pattern of a plain copy kernel -- instead of 148 far-apart ranges.
+    int64_t sup = blockIdx.x;
+    int64_t r   = sup * p.super_rows;
+    int64_t c1  = tmin(p.num_rows, r + p.super_rows);
+    int it      = 0;
     for (;; ++it) {
       const int s        = it % NS;
       const uint32_t par = ((it / NS) & 1) ^ 1;
@@ -418,7 +447,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
       uint8_t* pay  = payload0 + static_cast<size_t>(s) * stage_span;
       int32_t* soff = soff0 + static_cast<size_t>(s) * soff_span;
       StageHdr* h   = hdr0 + s;
-      if (r >= c1) {
+      if (r >= c1) {  // next super-tile of this CTA
+        sup += gridDim.x;
+        r  = sup * p.super_rows;
+        c1 = tmin(p.num_rows, r + p.super_rows);
+      }
+      if (r >= p.num_rows) {
         if (lane == 0) {
           h->rows = 0;
           mbar_arrive(&full[s]);
@@ -640,20 +674,31 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  // contiguous row range per CTA, a multiple of the tile height (=> of 32 or 8|16: mask-byte aligned)
-  const int64_t T      = p.tile_rows;
-  const int64_t ntiles = (num_rows + T - 1) / T;
-  int64_t grid         = std::min<int64_t>(nsm, ntiles);
-  int64_t tiles_per    = (ntiles + grid - 1) / grid;
-  p.rows_per_cta       = tiles_per * T;
-  grid                 = (num_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+  // super-tile = a multiple of the tile height (=> of 32 or 8|16: mask-byte aligned).  Fixed-stride
+  // tables: one tile (pure round-robin).  Variable-width tables cut tiles adaptively inside a
+  // super-tile of >= 4 tiles so the last, shorter tile of a super-tile is amortised.
+  static const int sup_tiles_env = []() { const char* e = getenv("SRJ_FR_SUPER"); return e ? atoi(e) : 0; }();
+  const int64_t T  = p.tile_rows;
+  int sup_tiles    = row_offsets ? 8 : 1;
+  if (sup_tiles_env > 0) sup_tiles = sup_tiles_env;
+  p.super_rows     = T * sup_tiles;
+  const int64_t ns = (num_rows + p.super_rows - 1) / p.super_rows;
+  int64_t grid     = std::min<int64_t>(nsm, ns);
   const size_t smem    = from_rows_smem_bytes(plan->tiling, p.nentries, p.ncols);
   static const int variant = []() { const char* e = getenv("SRJ_FR_VARIANT"); return e ? atoi(e) : 0; }();
   int rc;
   switch (variant) {
     case 1: rc = launch_variant<31>(p, static_cast<unsigned>(grid), smem, stream); break;
     case 2: rc = launch_variant<7>(p, static_cast<unsigned>(grid), smem, stream); break;
-    default: rc = launch_variant<15>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 3: rc = launch_variant<5>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 4: rc = launch_variant<3>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 6: rc = launch_variant<9>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 7: rc = launch_variant<12>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 8: rc = launch_variant<13>(p, static_cast<unsigned>(grid), smem, stream); break;
+    case 9: rc = launch_variant<15>(p, static_cast<unsigned>(grid), smem, stream); break;
+    // 11 consumer warps: 384 threads x 168 registers fills the register file with no spills (15 warps cap
+    // the kernel at 128 registers and spill inside the transpose loop: 76% vs 95% of HBM peak on C2)
+    default: rc = launch_variant<11>(p, static_cast<unsigned>(grid), smem, stream); break;
   }
   if (rc != SRJ_OK) return rc;
   SRJ_CUDA_TRY(cudaGetLastError());
