@@ -43,6 +43,12 @@ WORKLOADS = {
     # BASELINE.json configs[3]: store_sales, from_rows fused with xxhash64(ss_item_sk, ss_ticket_number)
     "c4": dict(name="C4: TPC-DS store_sales (23 cols, 104 B rows) convert_from_rows fused with xxhash64 partition key",
                types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=400_000_000, null_frac=0.04, hash_keys=[1, 9]),
+    # BASELINE.json configs[2]: 100M rows x 256 mixed cols (int32/int64/decimal128/utf8, 20% null), to+from rows.
+    # ~390 GB of rows cannot be resident: a step streams 100M rows as `batches` x `batch_rows` conversions over a
+    # resident pool of distinct <=2 GiB batches (each batch is what one LIST<INT8> column / one JNI call carries).
+    "c3": dict(name="C3: 100M rows x 256 mixed cols ([INT32,INT64,DECIMAL128,STRING]x64, 20% nulls, strings ~N(16,8) in [0,32] B) "
+                    "convert_from_rows, streamed as 200 batches of 500K rows (<=2 GiB each)",
+               types=[INT32, INT64, DEC128, STRING] * 64, rows=100_000_000, null_frac=0.2, batch_rows=500_000, pool=4),
 }
 
 
@@ -316,6 +322,198 @@ def run_ours(args, wl, rank, world):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------
+# C3: variable-width (strings + decimal128), streamed in <=2 GiB batches
+# ---------------------------------------------------------------------------------------------------
+def synth_strings_gpu(torch, S, n, null_frac, g):
+    """STRING column: lengths ~ clamp(round(N(16, 8)), 0, 32), null strings have length 0, printable ASCII chars."""
+    words = (n + 31) // 32
+    valid = torch.rand(n, device="cuda", generator=g) >= null_frac
+    lens = torch.clamp(torch.round(torch.randn(n, device="cuda", generator=g) * 8 + 16), 0, 32).to(torch.int64)
+    lens = lens * valid
+    offs = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    offs[1:] = torch.cumsum(lens, 0)
+    total = int(offs[-1])
+    chars = torch.randint(32, 127, (total,), dtype=torch.uint8, device="cuda", generator=g)
+    pad = words * 32 - n
+    bits = torch.cat([valid, torch.zeros(pad, dtype=torch.bool, device="cuda")]).view(words, 32).to(torch.int64)
+    w = (bits * (1 << torch.arange(32, device="cuda", dtype=torch.int64))).sum(dim=1)
+    mask = torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+    return S.ColumnVector(S.DType(STRING), n, chars, mask, offs.to(torch.int32))
+
+
+def run_c3(args, wl, rank, world):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    import srj_b200 as S
+    from srj_b200 import _native as N
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    types = wl["types"]
+    nb = int(wl["batch_rows"])
+    total_rows = int(args.rows or wl["rows"])
+    nbatches = max(1, total_rows // nb)
+    pool = min(int(wl["pool"]), nbatches)
+    dts = [S.DType(t, -11 if t == DEC128 else 0) for t in types]
+    plan = S.Plan.get(dts)
+    lib = N.lib()
+    stream = torch.cuda.current_stream()
+    st = int(stream.cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    words = (nb + 31) // 32
+
+    # ---- resident pool of distinct batches: columns -> (our) to_rows -> rows ---------------------------
+    batches = []
+    for b in range(pool):
+        cols = []
+        fixed = synth_columns_gpu(torch, S, [t for t in types if t != STRING], nb, wl["null_frac"], seed=77 + 13 * b + rank)
+        fi = iter(fixed)
+        for t in types:
+            cols.append(synth_strings_gpu(torch, S, nb, wl["null_frac"], g) if t == STRING else next(fi))
+        for c, d in zip(cols, dts):
+            c.dtype = d
+        rows = S.RowConversion.convertToRows(S.Table(cols))
+        assert len(rows) == 1, "batch must fit one LIST column"
+        batches.append(dict(cols=cols, rows=rows[0]))
+    torch.cuda.synchronize()
+
+    # algorithmic bytes of one from_rows batch (SURVEY 8d): rows as stored + 4 B row offsets, all column bytes out
+    def alg_bytes(bt):
+        rb = bt["rows"].child.size + 4 * (nb + 1)
+        out = 0
+        for c in bt["cols"]:
+            out += words * 4
+            out += (4 * (nb + 1) + c.data.numel()) if c.dtype.type_id == STRING else c.data.numel()
+        return rb + out
+    alg = [alg_bytes(bt) for bt in batches]
+    alg_step = sum(alg[i % pool] for i in range(nbatches))
+
+    if args.direction == "from_rows":
+        # pre-sized outputs (one set per pool slot); chars sizes are known from generation, so the device-resident
+        # `value` runs fixed+strings back to back without the D2H size read (e2e below includes it)
+        outs = []
+        for bt in batches:
+            o = []
+            for c in bt["cols"]:
+                m = torch.empty(words, dtype=torch.int32, device="cuda")
+                if c.dtype.type_id == STRING:
+                    o.append(S.ColumnVector(c.dtype, nb, torch.empty(c.data.numel(), dtype=torch.uint8, device="cuda"), m,
+                                            torch.empty(nb + 1, dtype=torch.int32, device="cuda")))
+                else:
+                    o.append(S.ColumnVector(c.dtype, nb, torch.empty(c.data.numel(), dtype=torch.uint8, device="cuda"), m))
+            carr = (N.SrjColumn * len(o))()
+            for i, c in enumerate(o):
+                carr[i] = c._c()
+            outs.append((o, carr))
+        nulls = torch.zeros(len(types), dtype=torch.int64, device="cuda")
+        totals = torch.zeros(len(types), dtype=torch.int64, device="cuda")
+
+        def convert(i):
+            bt = batches[i % pool]
+            o, carr = outs[i % pool]
+            rv = bt["rows"]
+            N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, st))
+            N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), nb, carr, st))
+        kernels_per_batch = 1 + 3 + 1
+        metric = "rows_per_sec_convert_from_rows"
+    else:
+        # to_rows: plan (row sizes + scan; its size read-back is part of the API) + convert into preallocated buffers
+        outs = []
+        for bt in batches:
+            rv = bt["rows"]
+            carr = (N.SrjColumn * len(types))()
+            for i, c in enumerate(bt["cols"]):
+                carr[i] = c._c()
+            ws = torch.empty(max(8, lib.srj_to_rows_workspace_bytes(plan.handle, nb)), dtype=torch.uint8, device="cuda")
+            outs.append(dict(carr=carr, ws=ws, offs=torch.empty(nb + 1, dtype=torch.int32, device="cuda"),
+                             data=torch.empty(rv.child.size, dtype=torch.uint8, device="cuda")))
+        rb = (N.SrjRowBatch * 8)()
+        nbo = C.c_int32(0)
+
+        def convert(i):
+            o = outs[i % pool]
+            N.check(lib.srj_to_rows_plan_batches(plan.handle, o["carr"], nb, o["ws"].data_ptr(), rb, 8, C.byref(nbo), st))
+            op, dp = (C.c_void_p * 1)(o["offs"].data_ptr()), (C.c_void_p * 1)(o["data"].data_ptr())
+            N.check(lib.srj_convert_to_rows(plan.handle, o["carr"], nb, o["ws"].data_ptr(), rb, 1, op, dp, st))
+        kernels_per_batch = 4 + 1
+        metric = "rows_per_sec_convert_to_rows"
+
+    # correctness gate: every pool batch round-trips
+    for i in range(pool):
+        convert(i)
+    torch.cuda.synchronize()
+    for i in range(pool):
+        if args.direction == "from_rows":
+            for a, b in zip(outs[i][0], batches[i]["cols"]):
+                assert torch.equal(a.mask, b.mask), "bench c3: mask mismatch"
+                if a.dtype.type_id == STRING:
+                    assert torch.equal(a.offsets, b.offsets) and torch.equal(a.data, b.data), "bench c3: string mismatch"
+                else:
+                    assert torch.equal(a.data, b.data), "bench c3: data mismatch"
+        else:
+            assert torch.equal(outs[i]["data"], batches[i]["rows"].child.data), "bench c3: row bytes mismatch"
+            assert torch.equal(outs[i]["offs"], batches[i]["rows"].offsets), "bench c3: row offsets mismatch"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        for i in range(nbatches):
+            convert(i)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    cuprof = os.environ.get("SRJ_CUPROF") == "1"
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(args.steps):
+        step()
+    t1.record(stream)
+    barrier()
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt[0]) / args.steps
+    rows_step = nbatches * nb
+    value = world * rows_step / (ms_per_step * 1e-3)
+    peak, peak_src = load_peaks()
+    achieved = alg_step / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "kernel": "whole conversion of a batch (all kernels of the two C-ABI calls)",
+                "algorithmic_bytes_per_row": alg_step / rows_step, "rows_per_launch": nb, "peak_source": peak_src,
+                "ms_per_batch": ms_per_step / nbatches}
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": wl["name"], "direction": args.direction, "rows_per_step_per_gpu": rows_step,
+                                     "batch_rows": nb, "batches_per_step": nbatches, "resident_pool_batches": pool,
+                                     "avg_row_bytes": batches[0]["rows"].child.size / nb,
+                                     "l2": "each batch touches ~%.1f GB >> 126 MB L2; pool of %d distinct batches" % (alg[0] / 1e9, pool)},
+                          "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": None, "e2e": None,
+                          "gpu_launches": args.steps * nbatches * kernels_per_batch, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthreads=None):
     """Oracle's threaded row->column loop on a bounded sample of the same rows (host cores)."""
     from oracle import oracle as O
@@ -383,6 +581,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
+    ap.add_argument("--direction", default="from_rows", choices=["from_rows", "to_rows"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -390,6 +589,8 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
+    elif args.workload == "c3":
+        run_c3(args, wl, rank, world)
     else:
         run_ours(args, wl, rank, world)
 
