@@ -411,7 +411,7 @@ def run_c3(args, wl, rank, world):
                 carr[i] = c._c()
             outs.append((o, carr))
         nulls = torch.zeros(len(types), dtype=torch.int64, device="cuda")
-        totals = torch.zeros(len(types), dtype=torch.int64, device="cuda")
+        totals = torch.zeros(len(types) + 1, dtype=torch.int64, device="cuda")
 
         def convert(i):
             bt = batches[i % pool]
@@ -419,7 +419,8 @@ def run_c3(args, wl, rank, world):
             rv = bt["rows"]
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
                                                     nb, carr, nulls.data_ptr(), totals.data_ptr(), None, st))
-            N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), nb, carr, st))
+            N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                      nb, carr, totals.data_ptr(), st))
         kernels_per_batch = 1 + 3 + 1
         metric = "rows_per_sec_convert_from_rows"
     else:

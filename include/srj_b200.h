@@ -150,8 +150,13 @@ SRJ_API int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, in
  *   cols        : num_columns outputs; data (fixed-width), null_mask and (STRING) offsets must be
  *                 allocated; STRING data (chars) may be NULL in this phase
  *   d_null_counts : device int64[num_columns] or NULL
- *   d_char_totals : device int64[num_columns] (0 for non-STRING) or NULL; the caller reads it back
- *                 (that read is the one sync the reference also has, RC:2389) to size the chars.
+ *   d_char_totals : device int64[num_columns + 1] or NULL.  Entries [0, num_columns) receive the chars size
+ *                 of each STRING column (0 for the others); the caller reads them back (that read is the
+ *                 one sync the reference also has, RC:2389) to size the chars.  Entry [num_columns] is a
+ *                 status word for phase 2: bit 0 set = some row does not use the canonical string layout
+ *                 (pair.offset != size_per_row + lengths of the preceding STRING columns); phase 2 then
+ *                 follows the stored pair offsets exactly like copy_strings_from_rows (RC:1143) instead of
+ *                 its fast path.
  * If hash_kind != SRJ_HASH_NONE the row hash of the listed key columns is computed from the same
  * shared-memory tile and written to hash_out (int64 for xxhash64, int32 otherwise): the fused
  * from_rows + partition-hash of BASELINE config 4.  Keys must be fixed-width columns.
@@ -171,10 +176,13 @@ SRJ_API int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* row
                                         int64_t num_rows, const srj_column* cols,
                                         int64_t* d_null_counts, int64_t* d_char_totals,
                                         const srj_fused_hash* hash /* may be NULL */, void* stream);
-/* Phase 2 (async): gather the chars of every STRING column (copy_strings_from_rows, RC:1110-1150). */
+/* Phase 2 (async): gather the chars of every STRING column (copy_strings_from_rows, RC:1110-1150).
+ * d_char_totals is the buffer phase 1 filled (its status word selects the fast path); NULL = always
+ * follow the stored pair offsets. */
 SRJ_API int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows,
-                                          const int32_t* row_offsets, int64_t num_rows,
-                                          const srj_column* cols, void* stream);
+                                          const int32_t* row_offsets, int64_t rows_bytes, int64_t num_rows,
+                                          const srj_column* cols, const int64_t* d_char_totals,
+                                          void* stream);
 
 /* ---- row hashes: Hash.xxhash64 / murmurHash32 / hiveHash, hash/hash.hpp:40-74 ------------------ */
 #define SRJ_DEFAULT_XXHASH64_SEED 42 /* hash/hash.hpp:27 */

@@ -80,18 +80,50 @@ static int compute_layout(const int32_t* types, int32_t n, srj_layout* out, std:
   return SRJ_OK;
 }
 
-struct Scratch {  // stream-ordered per-call device scratch
-  void* ptr = nullptr;
+// RAII lease of one TableRing slot (see plan.hpp).  upload() copies `host_bytes` of pointer tables to the
+// device buffer; the device buffer may be larger (`total_bytes`) to carry device-only scratch behind them.
+struct TableLease {
+  const srj_plan* plan;
   cudaStream_t stream;
-  explicit Scratch(cudaStream_t s) : stream(s) {}
-  int alloc(size_t bytes)
+  TableSlot* slot = nullptr;
+  TableLease(const srj_plan* p, cudaStream_t s) : plan(p), stream(s) {}
+  int acquire(size_t total_bytes)
   {
-    SRJ_CUDA_TRY(cudaMallocAsync(&ptr, bytes ? bytes : 16, stream));
+    TableRing& r = plan->ring;
+    {
+      std::lock_guard<std::mutex> lk(r.mu);
+      slot = &r.slots[r.next++ % TableRing::kSlots];
+    }
+    slot->busy.lock();  // > kSlots concurrent callers: the 9th waits for the 1st call to return
+    if (slot->used) SRJ_CUDA_TRY(cudaEventSynchronize(slot->ev));  // previous user of this slot has drained
+    if (!slot->ev) SRJ_CUDA_TRY(cudaEventCreateWithFlags(&slot->ev, cudaEventDisableTiming));
+    if (slot->cap < total_bytes) {
+      const size_t cap = std::max<size_t>(total_bytes * 2, 16384);
+      if (slot->d_buf) cudaFree(slot->d_buf);
+      if (slot->h_pinned) cudaFreeHost(slot->h_pinned);
+      slot->d_buf = slot->h_pinned = nullptr;
+      slot->cap = 0;
+      SRJ_CUDA_TRY(cudaMalloc(&slot->d_buf, cap));
+      SRJ_CUDA_TRY(cudaMallocHost(&slot->h_pinned, cap));
+      slot->cap = cap;
+    }
     return SRJ_OK;
   }
-  ~Scratch()
+  void* host() const { return slot->h_pinned; }
+  void* dev() const { return slot->d_buf; }
+  int upload(size_t host_bytes)
   {
-    if (ptr) cudaFreeAsync(ptr, stream);
+    SRJ_CUDA_TRY(cudaMemcpyAsync(slot->d_buf, slot->h_pinned, host_bytes, cudaMemcpyHostToDevice, stream));
+    return SRJ_OK;
+  }
+  ~TableLease()
+  {
+    if (!slot) return;
+    if (slot->ev) {
+      cudaEventRecord(slot->ev, stream);
+      slot->used = true;
+    }
+    slot->busy.unlock();
   }
 };
 
@@ -229,6 +261,12 @@ void srj_plan_destroy(srj_plan* plan)
 {
   if (!plan) return;
   if (plan->d_blob) cudaFree(plan->d_blob);
+  for (auto& sl : plan->ring.slots) {
+    if (sl.used && sl.ev) cudaEventSynchronize(sl.ev);
+    if (sl.d_buf) cudaFree(sl.d_buf);
+    if (sl.h_pinned) cudaFreeHost(sl.h_pinned);
+    if (sl.ev) cudaEventDestroy(sl.ev);
+  }
   delete plan;
 }
 
@@ -299,12 +337,14 @@ int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64
     h_off[s] = cols[plan->string_columns[s]].offsets;
     if (!h_off[s]) { set_error("to_rows: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
   }
-  Scratch sc(stream);
-  rc = sc.alloc(sizeof(void*) * nstr);
+  TableLease sc(plan, stream);
+  rc = sc.acquire(sizeof(void*) * nstr);
   if (rc != SRJ_OK) return rc;
-  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, h_off.data(), sizeof(void*) * nstr, cudaMemcpyHostToDevice, stream));
+  memcpy(sc.host(), h_off.data(), sizeof(void*) * nstr);
+  rc = sc.upload(sizeof(void*) * nstr);
+  if (rc != SRJ_OK) return rc;
   uint64_t* cum = static_cast<uint64_t*>(workspace);
-  rc            = launch_row_sizes(plan, static_cast<const int32_t* const*>(sc.ptr), num_rows, cum, stream);
+  rc            = launch_row_sizes(plan, static_cast<const int32_t* const*>(sc.dev()), num_rows, cum, stream);
   if (rc != SRJ_OK) return rc;
   uint64_t total = 0;
   rc             = read_u64(cum, num_rows - 1, &total, stream);
@@ -375,11 +415,13 @@ int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t nu
     tab[2 * nc + s]        = c.offsets;
     tab[2 * nc + nstr + s] = c.data;
   }
-  Scratch sc(stream);
-  rc = sc.alloc(tab.size() * sizeof(void*));
+  TableLease sc(plan, stream);
+  rc = sc.acquire(tab.size() * sizeof(void*));
   if (rc != SRJ_OK) return rc;
-  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
-  auto** d = static_cast<const void**>(sc.ptr);
+  memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
+  rc = sc.upload(tab.size() * sizeof(void*));
+  if (rc != SRJ_OK) return rc;
+  auto** d = static_cast<const void**>(sc.dev());
   for (int b = 0; b < num_batches; ++b) {
     if (!batch_offsets[b] || (!batch_data[b] && batches[b].num_bytes > 0)) { set_error("convert_to_rows: batch %d buffers are null", b); return SRJ_EINVAL; }
     rc = launch_to_rows(plan, d, reinterpret_cast<const uint32_t* const*>(d + nc),
@@ -440,18 +482,20 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
   for (int s = 0; s < nstr; ++s) tab[nent + nc + s] = cols[plan->string_columns[s]].offsets;
   const size_t tab_bytes  = (tab.size() * sizeof(void*) + 15) & ~size_t{15};
   const size_t part_bytes = static_cast<size_t>(string_scan_partials_bytes(nstr, num_rows));
-  Scratch sc(stream);
-  rc = sc.alloc(tab_bytes + part_bytes + 16);
+  TableLease sc(plan, stream);
+  rc = sc.acquire(tab_bytes + part_bytes + 16);
   if (rc != SRJ_OK) return rc;
-  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
-  auto** d = static_cast<void**>(sc.ptr);
+  memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
+  rc = sc.upload(tab.size() * sizeof(void*));
+  if (rc != SRJ_OK) return rc;
+  auto** d = static_cast<void**>(sc.dev());
   if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
-  if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * nc, stream));
+  if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * (nc + 1), stream));
   rc = launch_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nent),
-                        d_null_counts, hash, stream);
+                        d_null_counts, d_char_totals ? d_char_totals + nc : nullptr, hash, stream);
   if (rc != SRJ_OK) return rc;
   if (nstr > 0) {
-    uint8_t* tail = static_cast<uint8_t*>(sc.ptr) + tab_bytes;
+    uint8_t* tail = static_cast<uint8_t*>(sc.dev()) + tab_bytes;
     rc = launch_string_offsets_scan(reinterpret_cast<int32_t* const*>(d + nent + nc), plan->d_string_cols, nstr, num_rows,
                                     d_char_totals, reinterpret_cast<int32_t*>(tail + part_bytes), tail, stream);
     if (rc != SRJ_OK) return rc;
@@ -460,7 +504,8 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
 }
 
 int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
-                                  int64_t num_rows, const srj_column* cols, void* stream_)
+                                  int64_t rows_bytes, int64_t num_rows, const srj_column* cols,
+                                  const int64_t* d_char_totals, void* stream_)
 {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_from_rows_strings");
@@ -475,13 +520,16 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
     tab[s]        = c.offsets;
     tab[nstr + s] = c.data;  // may be NULL only when the column has no chars at all
   }
-  Scratch sc(stream);
-  rc = sc.alloc(tab.size() * sizeof(void*));
+  TableLease sc(plan, stream);
+  rc = sc.acquire(tab.size() * sizeof(void*));
   if (rc != SRJ_OK) return rc;
-  SRJ_CUDA_TRY(cudaMemcpyAsync(sc.ptr, tab.data(), tab.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
-  auto** d = static_cast<void**>(sc.ptr);
-  return launch_strings_from_rows(plan, rows, row_offsets, num_rows, reinterpret_cast<const int32_t* const*>(d),
-                                  reinterpret_cast<uint8_t* const*>(d + nstr), stream);
+  memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
+  rc = sc.upload(tab.size() * sizeof(void*));
+  if (rc != SRJ_OK) return rc;
+  auto** d = static_cast<void**>(sc.dev());
+  return launch_strings_from_rows(plan, rows, row_offsets, rows_bytes, num_rows,
+                                  reinterpret_cast<const int32_t* const*>(d), reinterpret_cast<uint8_t* const*>(d + nstr),
+                                  d_char_totals ? d_char_totals + plan->num_columns : nullptr, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -572,7 +620,7 @@ int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int6
     SRJ_TRY_CLEAN(cudaMemcpyAsync(d_rows[s], h_rows + r0 * S, static_cast<size_t>(n) * S, cudaMemcpyHostToDevice, st[s]));
     // the kernel sees a chunk-local table whose last mask word is zero-tailed; chunk starts are multiples of 32
     rc = launch_from_rows(plan, d_rows[s], nullptr, n * S, n, d_tab[s], reinterpret_cast<uint32_t* const*>(d_tab[s] + nent),
-                          d_nulls, nullptr, st[s]);
+                          d_nulls, nullptr, nullptr, st[s]);
     if (rc != SRJ_OK) { cleanup(); return rc; }
     for (int c = 0; c < nc; ++c) {
       SRJ_TRY_CLEAN(cudaMemcpyAsync(static_cast<uint8_t*>(h_cols[c].data) + r0 * plan->col_size[c], d_cols[s] + off_data[c],

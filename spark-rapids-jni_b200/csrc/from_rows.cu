@@ -65,6 +65,11 @@ struct FromRowsParams {
   void* const* ent_dst;             // [nentries] column base pointers (STRING: offsets + 1)
   uint32_t* const* masks;           // [ncols]
   unsigned long long* null_counts;  // [ncols] or NULL
+  // canonical-layout check of the STRING pairs (variable-width tables)
+  int32_t nstr;
+  int32_t size_per_row;
+  const int32_t* string_start;   // [nstr] row byte offset of each (offset, len) pair
+  unsigned long long* status;    // bit 0 <- 1 when a row's pair.offset differs from the canonical position
   // fused hash
   int32_t hash_kind;
   int32_t hash_nkeys;
@@ -171,6 +176,7 @@ struct SmemTables {
   uint8_t* const* ent_dst;   // [nentries]
   uint32_t* const* masks;    // [ncols]
   int32_t* nulls;            // [ncols] or NULL
+  const int32_t* string_start;  // [nstr]
 };
 
 // Per-consumer-warp schedule constants, computed once per CTA.
@@ -187,6 +193,7 @@ struct TileView {
   uint32_t stride;
   int64_t r0;
   int rows;
+  const uint8_t* lane_row;  // single-row-group tiles: this lane's row (NULL if lane >= rows)
 };
 
 template <bool VAR>
@@ -198,7 +205,7 @@ __device__ __forceinline__ const uint8_t* row_ptr(const TileView& tv, int i)
 
 // ---- fixed-width fields of one width class -----------------------------------------------------------
 // PRED=false: full tile of a fixed-stride table -- no row predicates at all.
-template <int W, int NCW, int RPL, bool VAR, bool PRED, bool SAFE>
+template <int W, int NCW, int RPL, bool VAR, bool PRED, bool SAFE, bool ONEG>
 __device__ __forceinline__ void transpose_class(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
                                                 const TileView& tv, int k)
 {
@@ -209,6 +216,37 @@ __device__ __forceinline__ void transpose_class(const FromRowsParams& p, const S
   const int total   = p.cls_units[k];
   const int gpu     = p.gpu;
   const int chmask  = (1 << p.cs) - 1;
+  if constexpr (VAR && !SAFE && ONEG) {
+    {
+      // wide rows: one row group per tile; the lane's row address is hoisted per tile and four units are
+      // in flight per warp (table reads, then field reads, then stores) to hide the shared-memory latency
+      const int64_t roff = (tv.r0 + ws.lr) * W;
+      constexpr int U    = W >= 16 ? 2 : 4;
+      for (int u = ws.ustart[k]; u < total; u += U * NCW) {
+        Reg<W> v[U];
+        uint8_t* dst[U];
+        bool ok[U];
+        int32_t start[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int uj = u + j * NCW;
+          const int e  = nb + (uj >> p.cs) * CPI + ws.sub;
+          ok[j]        = uj < total && e < ne && tv.lane_row != nullptr;
+          if (ok[j]) {
+            start[j] = t.ent_start[e];
+            dst[j]   = t.ent_dst[e] + roff;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (ok[j]) v[j] = ld_elem<W, false>(tv.lane_row + start[j]);
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+          if (ok[j]) st_elem<W>(dst[j], v[j]);
+      }
+      return;
+    }
+  }
   for (int u = ws.ustart[k]; u < total; u += NCW) {
     const int slot = u >> p.cs;
     const int gc   = u & chmask;
@@ -369,28 +407,65 @@ __device__ __noinline__ void hash_tile(const FromRowsParams& p, const TileView& 
   }
 }
 
-template <int NCW, int RPL, bool VAR, bool PRED, bool SAFE>
+// Variable-width tables: does every row place its strings where convert_to_rows would (chars of the
+// STRING columns back to back, in column order, from byte size_per_row -- RC:838-858)?  Phase 2's fast
+// path relies on it; a mismatch only flips a status bit that routes phase 2 to the generic gather.
+// A warp takes a row: lane = STRING column, the expected offset is a warp exclusive scan of the lengths.
+template <int NCW, bool SAFE>
+__device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const TileView& tv, int cw,
+                                                  const int32_t* s_string_start)
+{
+  const int lane = lane_id();
+  bool bad       = false;
+  for (int row = cw; row < tv.rows; row += NCW) {
+    const uint8_t* rp = row_ptr<true>(tv, row);
+    uint32_t carry    = static_cast<uint32_t>(p.size_per_row);
+    for (int s0 = 0; s0 < p.nstr; s0 += 32) {
+      const int s = s0 + lane;
+      uint32_t so = 0, ln = 0;
+      if (s < p.nstr) {
+        const uint8_t* pp = rp + s_string_start[s];
+        so                = static_cast<uint32_t>(load_key<SAFE>(pp, 4));
+        ln                = static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
+      }
+      uint32_t x = ln;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (s < p.nstr) bad |= so != carry + x - ln;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status, 1ull);
+}
+
+template <int NCW, int RPL, bool VAR, bool PRED, bool SAFE, bool ONEG>
 __device__ __forceinline__ void process_tile(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
                                              const TileView& tv, int cw)
 {
-  transpose_class<16, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 4);
-  transpose_class<8, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 3);
-  transpose_class<4, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 2);
-  transpose_class<2, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 1);
-  transpose_class<1, NCW, RPL, VAR, PRED, SAFE>(p, t, ws, tv, 0);
+  transpose_class<16, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 4);
+  transpose_class<8, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 3);
+  transpose_class<4, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 2);
+  transpose_class<2, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 1);
+  transpose_class<1, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 0);
   validity_tile<NCW, VAR, PRED, SAFE>(p, t, ws, tv);
   if (p.hash_kind != SRJ_HASH_NONE) hash_tile<NCW, VAR, SAFE>(p, tv, cw);
+  if constexpr (VAR) {
+    if (p.status && p.nstr > 0) canonical_check_tile<NCW, SAFE>(p, tv, cw, t.string_start);
+  }
 }
 
 // SAFE / partial tiles are kept out of line so they do not inflate the fast path's registers
-template <int NCW, int RPL, bool VAR, bool SAFE>
+template <int NCW, int RPL, bool VAR, bool SAFE, bool ONEG>
 __device__ __noinline__ void process_tile_slow(const FromRowsParams& p, const SmemTables& t, const WarpSched& ws,
                                                const TileView& tv, int cw)
 {
-  process_tile<NCW, RPL, VAR, true, SAFE>(p, t, ws, tv, cw);
+  process_tile<NCW, RPL, VAR, true, SAFE, ONEG>(p, t, ws, tv, cw);
 }
 
-template <int NCW, int RPL, bool VAR>
+template <int NCW, int RPL, bool VAR, bool ONEG>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __grid_constant__ FromRowsParams p)
 {
   constexpr int kThreads = (NCW + 1) * 32;
@@ -407,6 +482,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
   uint8_t** s_ent_dst  = reinterpret_cast<uint8_t**>(s_ent_start + ((p.nentries + 1) & ~1));
   uint32_t** s_masks   = reinterpret_cast<uint32_t**>(s_ent_dst + p.nentries);
   int32_t* s_nulls     = reinterpret_cast<int32_t*>(s_masks + p.ncols);
+  int32_t* s_next_off  = s_nulls + ((p.ncols + 3) & ~3);  // producer scratch: offsets of the NEXT tile
+  int32_t* s_str_start = s_next_off + ((p.tile_rows + 4) & ~3);
 
   const int tid = threadIdx.x;
   for (int i = tid; i < p.nentries; i += kThreads) {
@@ -417,6 +494,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
     s_masks[i] = p.masks[i];
     s_nulls[i] = 0;
   }
+  for (int i = tid; i < p.nstr; i += kThreads) s_str_start[i] = p.string_start[i];
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
@@ -438,34 +516,26 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
     int64_t sup = blockIdx.x;
     int64_t r   = sup * p.super_rows;
     int64_t c1  = tmin(p.num_rows, r + p.super_rows);
-    int it      = 0;
-    for (;; ++it) {
-      const int s        = it % NS;
-      const uint32_t par = ((it / NS) & 1) ^ 1;
-      if (lane == 0) mbar_wait(&empty[s], par);  // first pass over the ring returns immediately
-      __syncwarp();
-      uint8_t* pay  = payload0 + static_cast<size_t>(s) * stage_span;
-      int32_t* soff = soff0 + static_cast<size_t>(s) * soff_span;
-      StageHdr* h   = hdr0 + s;
+
+    // Geometry of the tile starting at row `r` (computed one tile AHEAD, while the previous TMA load is
+    // in flight, so the global reads of the LIST offsets never sit on the critical path).
+    int g_rows  = 0;
+    bool g_safe = false, g_end = false;
+    int64_t g_lo = 0, g_hi = 0;
+    auto next_geometry = [&]() {
       if (r >= c1) {  // next super-tile of this CTA
         sup += gridDim.x;
         r  = sup * p.super_rows;
         c1 = tmin(p.num_rows, r + p.super_rows);
       }
-      if (r >= p.num_rows) {
-        if (lane == 0) {
-          h->rows = 0;
-          mbar_arrive(&full[s]);
-        }
-        break;
-      }
-      int rows    = static_cast<int>(tmin<int64_t>(p.tile_rows, c1 - r));
-      int64_t glo = 0, ghi = 0;  // global byte range [glo, ghi) from p.rows
-      bool safe   = !base_ok;
+      g_end = r >= p.num_rows;
+      if (g_end) return;
+      int rows  = static_cast<int>(tmin<int64_t>(p.tile_rows, c1 - r));
+      bool safe = !base_ok;
       if constexpr (!VAR) {
-        glo = r * p.row_stride;
-        ghi = (r + rows) * static_cast<int64_t>(p.row_stride);
-        if (ghi - glo > p.stage_bytes) safe = true;
+        g_lo = r * p.row_stride;
+        g_hi = (r + rows) * static_cast<int64_t>(p.row_stride);
+        if (g_hi - g_lo > p.stage_bytes) safe = true;
       } else {
         // load off[r .. r+rows] (coalesced) and pick the largest multiple-of-8 row count that fits
         const int64_t a0   = p.row_offsets[r];
@@ -476,8 +546,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
           const int i = i0 + lane;
           int64_t o   = 0;
           if (i <= rows) {
-            o       = p.row_offsets[r + i];
-            soff[i] = static_cast<int32_t>(o - base);
+            o             = p.row_offsets[r + i];
+            s_next_off[i] = static_cast<int32_t>(o - base);
             if (i < rows && (o & 7)) misaligned = true;
           }
           const bool ok = (i >= 1) && (i <= rows) && (round_up64(o - base, 16) <= p.stage_bytes + 16);
@@ -490,12 +560,40 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
           safe = true;
           rows = tmin(rows, 8);
           __syncwarp();
-          for (int i = lane; i <= rows; i += 32) soff[i] = p.row_offsets[r + i];  // absolute offsets
+          for (int i = lane; i <= rows; i += 32) s_next_off[i] = p.row_offsets[r + i];  // absolute offsets
         } else {
           rows = fit;
         }
-        glo = a0;
-        ghi = p.row_offsets[r + rows];
+        g_lo = a0;
+        g_hi = p.row_offsets[r + rows];
+      }
+      g_rows = rows;
+      g_safe = safe;
+      __syncwarp();
+    };
+    next_geometry();
+
+    int it = 0;
+    for (;; ++it) {
+      const int s        = it % NS;
+      const uint32_t par = ((it / NS) & 1) ^ 1;
+      if (lane == 0) mbar_wait(&empty[s], par);  // first pass over the ring returns immediately
+      __syncwarp();
+      uint8_t* pay  = payload0 + static_cast<size_t>(s) * stage_span;
+      int32_t* soff = soff0 + static_cast<size_t>(s) * soff_span;
+      StageHdr* h   = hdr0 + s;
+      if (g_end) {
+        if (lane == 0) {
+          h->rows = 0;
+          mbar_arrive(&full[s]);
+        }
+        break;
+      }
+      const int rows    = g_rows;
+      const bool safe   = g_safe;
+      const int64_t glo = g_lo, ghi = g_hi;
+      if constexpr (VAR) {
+        for (int i = lane; i <= rows; i += 32) soff[i] = s_next_off[i];
       }
       uint32_t tx    = 0;
       int32_t skew   = 0;
@@ -541,11 +639,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
         }
       }
       r += rows;
+      next_geometry();  // overlaps with the load just issued
     }
   } else {
     // =================================== consumers ===================================
     const int cw = warp_id() - 1;
-    SmemTables t{s_ent_start, s_ent_dst, s_masks, p.null_counts ? s_nulls : nullptr};
+    SmemTables t{s_ent_start, s_ent_dst, s_masks, p.null_counts ? s_nulls : nullptr, s_str_start};
     WarpSched ws;
 #pragma unroll
     for (int k = 0; k < kNumClasses; ++k) ws.ustart[k] = (cw + NCW - (p.cls_ubase[k] % NCW)) % NCW;
@@ -565,17 +664,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
       tv.stride = static_cast<uint32_t>(p.row_stride);
       tv.r0     = h.r0;
       tv.rows   = h.rows;
+      tv.lane_row = nullptr;
       if (!h.safe) {
         tv.base = VAR ? pay : pay + h.skew;
+        if (VAR && ONEG && ws.lr < h.rows) tv.lane_row = pay + static_cast<uint32_t>(soff[ws.lr]);
         if (!VAR && h.rows == p.tile_rows && (p.gpu & 3) == 0)
-          process_tile<NCW, RPL, VAR, false, false>(p, t, ws, tv, cw);
+          process_tile<NCW, RPL, VAR, false, false, false>(p, t, ws, tv, cw);
         else if (VAR)
-          process_tile<NCW, RPL, VAR, true, false>(p, t, ws, tv, cw);  // var-width tiles are always predicated
+          process_tile<NCW, RPL, VAR, true, false, ONEG>(p, t, ws, tv, cw);  // var-width tiles are always predicated
         else
-          process_tile_slow<NCW, RPL, VAR, false>(p, t, ws, tv, cw);
+          process_tile_slow<NCW, RPL, VAR, false, false>(p, t, ws, tv, cw);
       } else {
         tv.base = VAR ? p.rows : p.rows + h.gbase;
-        process_tile_slow<NCW, RPL, VAR, true>(p, t, ws, tv, cw);
+        process_tile_slow<NCW, RPL, VAR, true, false>(p, t, ws, tv, cw);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
@@ -589,14 +690,16 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
 }
 
 // ---- host launcher -------------------------------------------------------------------------------
-size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols)
+size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols, int nstr)
 {
   size_t b = static_cast<size_t>(tl.num_stages) * (tl.stage_bytes + kStageSlack);
   b += static_cast<size_t>(tl.num_stages) * ((tl.tile_rows + 4) & ~3) * 4;
   b += static_cast<size_t>(tl.num_stages) * sizeof(StageHdr);
   b += 2 * kMaxStages * 8;
   b += static_cast<size_t>((nentries + 1) & ~1) * 4;
-  b += static_cast<size_t>(nentries) * 8 + static_cast<size_t>(ncols) * 8 + static_cast<size_t>(ncols) * 4;
+  b += static_cast<size_t>(nentries) * 8 + static_cast<size_t>(ncols) * 8 + static_cast<size_t>((ncols + 3) & ~3) * 4;
+  b += static_cast<size_t>((tl.tile_rows + 4) & ~3) * 4;
+  b += static_cast<size_t>(nstr + 4) * 4;
   return (b + 127) & ~size_t{127};
 }
 
@@ -608,17 +711,24 @@ static int launch_variant(const FromRowsParams& p, unsigned grid, size_t smem, c
     kern<<<grid, (NCW + 1) * 32, smem, stream>>>(p);
     return SRJ_OK;
   };
-  const bool var = p.row_offsets != nullptr;
+  const bool var  = p.row_offsets != nullptr;
+  const bool oneg = var && p.gpu == 1;  // one row group per tile (wide rows): hoisted row address, 4 units in flight
   switch (p.rpl) {
-    case 32: return var ? go(from_rows_kernel<NCW, 32, true>) : go(from_rows_kernel<NCW, 32, false>);
-    case 16: return var ? go(from_rows_kernel<NCW, 16, true>) : go(from_rows_kernel<NCW, 16, false>);
-    default: return var ? go(from_rows_kernel<NCW, 8, true>) : go(from_rows_kernel<NCW, 8, false>);
+    case 32:
+      if (!var) return go(from_rows_kernel<NCW, 32, false, false>);
+      return oneg ? go(from_rows_kernel<NCW, 32, true, true>) : go(from_rows_kernel<NCW, 32, true, false>);
+    case 16:
+      if (!var) return go(from_rows_kernel<NCW, 16, false, false>);
+      return oneg ? go(from_rows_kernel<NCW, 16, true, true>) : go(from_rows_kernel<NCW, 16, true, false>);
+    default:
+      if (!var) return go(from_rows_kernel<NCW, 8, false, false>);
+      return oneg ? go(from_rows_kernel<NCW, 8, true, true>) : go(from_rows_kernel<NCW, 8, true, false>);
   }
 }
 
 int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
                      int64_t num_rows, void* const* d_ent_dst, uint32_t* const* d_masks, int64_t* d_null_counts,
-                     const srj_fused_hash* fh, cudaStream_t stream)
+                     int64_t* d_status, const srj_fused_hash* fh, cudaStream_t stream)
 {
   if (num_rows == 0) return SRJ_OK;
   FromRowsParams p{};
@@ -657,8 +767,12 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   p.entries     = plan->d_fr_entries;
   p.ent_dst     = d_ent_dst;
   p.masks       = d_masks;
-  p.null_counts = reinterpret_cast<unsigned long long*>(d_null_counts);
-  p.hash_kind   = SRJ_HASH_NONE;
+  p.null_counts  = reinterpret_cast<unsigned long long*>(d_null_counts);
+  p.nstr         = plan->num_string_columns;
+  p.size_per_row = plan->size_per_row;
+  p.string_start = plan->d_string_start;
+  p.status       = reinterpret_cast<unsigned long long*>(d_status);
+  p.hash_kind    = SRJ_HASH_NONE;
   if (fh && fh->kind != SRJ_HASH_NONE) {
     p.hash_kind  = fh->kind;
     p.hash_nkeys = fh->num_keys;
@@ -684,18 +798,11 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   p.super_rows     = T * sup_tiles;
   const int64_t ns = (num_rows + p.super_rows - 1) / p.super_rows;
   int64_t grid     = std::min<int64_t>(nsm, ns);
-  const size_t smem    = from_rows_smem_bytes(plan->tiling, p.nentries, p.ncols);
+  const size_t smem    = from_rows_smem_bytes(plan->tiling, p.nentries, p.ncols, plan->num_string_columns);
   static const int variant = []() { const char* e = getenv("SRJ_FR_VARIANT"); return e ? atoi(e) : 0; }();
   int rc;
   switch (variant) {
-    case 1: rc = launch_variant<31>(p, static_cast<unsigned>(grid), smem, stream); break;
     case 2: rc = launch_variant<7>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 3: rc = launch_variant<5>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 4: rc = launch_variant<3>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 6: rc = launch_variant<9>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 7: rc = launch_variant<12>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 8: rc = launch_variant<13>(p, static_cast<unsigned>(grid), smem, stream); break;
-    case 9: rc = launch_variant<15>(p, static_cast<unsigned>(grid), smem, stream); break;
     // 11 consumer warps: 384 threads x 168 registers fills the register file with no spills (15 warps cap
     // the kernel at 128 registers and spill inside the transpose loop: 76% vs 95% of HBM peak on C2)
     default: rc = launch_variant<11>(p, static_cast<unsigned>(grid), smem, stream); break;

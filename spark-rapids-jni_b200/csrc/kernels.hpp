@@ -11,7 +11,7 @@ namespace srj {
 // from_rows.cu
 int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
                      int64_t num_rows, void* const* d_ent_dst, uint32_t* const* d_masks, int64_t* d_null_counts,
-                     const srj_fused_hash* fh, cudaStream_t stream);
+                     int64_t* d_status, const srj_fused_hash* fh, cudaStream_t stream);
 
 // strings.cu
 // In-place inclusive scan of the int32 lengths stored at offsets[c][1..n] for every STRING column
@@ -22,8 +22,8 @@ int launch_string_offsets_scan(int32_t* const* d_offsets /* device array [nstr] 
 int64_t string_scan_partials_bytes(int nstr, int64_t num_rows);
 // copy_strings_from_rows replacement
 int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
-                             int64_t num_rows, const int32_t* const* d_offsets, uint8_t* const* d_chars,
-                             cudaStream_t stream);
+                             int64_t rows_bytes, int64_t num_rows, const int32_t* const* d_offsets,
+                             uint8_t* const* d_chars, const int64_t* d_status, cudaStream_t stream);
 
 // to_rows.cu
 int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,

@@ -3,6 +3,9 @@
 #pragma once
 #include <stdint.h>
 
+#include <cuda_runtime.h>
+
+#include <mutex>
 #include <vector>
 
 #include "../../include/srj_b200.h"
@@ -26,6 +29,25 @@ struct Tiling {
   int32_t rows_per_item;  // 8, 16 or 32: lanes of a warp item that map to rows
   int32_t stage_bytes;  // shared-memory bytes per pipeline stage (payload)
   int32_t num_stages;
+};
+
+// Per-call pointer tables (column/mask/offset pointers differ on every call) go host -> device through
+// a small ring of pinned staging buffers + device buffers owned by the plan: one truly asynchronous
+// cudaMemcpyAsync per call, no allocation, re-entrant (a slot is reused only after the event recorded
+// behind its last use has completed).
+struct TableSlot {
+  void* h_pinned = nullptr;
+  void* d_buf    = nullptr;
+  size_t cap     = 0;
+  cudaEvent_t ev = nullptr;
+  bool used      = false;
+  std::mutex busy;  // held for the duration of one API call's lease
+};
+struct TableRing {
+  static constexpr int kSlots = 8;
+  std::mutex mu;
+  TableSlot slots[kSlots];
+  unsigned next = 0;
 };
 
 }  // namespace srj
@@ -56,4 +78,6 @@ struct srj_plan {
   const int32_t* d_col_start;     // [num_columns]
   const int32_t* d_string_cols;   // [num_string_columns]
   const int32_t* d_string_start;  // [num_string_columns] row byte offset of each pair
+
+  mutable srj::TableRing ring;
 };

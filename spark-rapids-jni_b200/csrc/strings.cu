@@ -154,7 +154,7 @@ int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_strin
 }
 
 // --------------------------------------------------------------------------------------------------
-// chars gather (v1): a warp owns (32-row tile, STRING column); lane = row reads the (offset,len)
+// chars gather, GENERIC path (follows the stored pair offsets, RC:1143): a warp owns (32-row tile, STRING column); lane = row reads the (offset,len)
 // pair from the row, then the warp copies the tile's chars for that column -- a contiguous
 // destination range -- with lane = destination byte, locating the source row by a shuffle search.
 // Destination stores are fully coalesced; source reads stay inside 2-3 sectors per instruction.
@@ -164,8 +164,10 @@ constexpr int kStrWarps = 8;
 __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
   const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets, int64_t row_stride, int64_t num_rows,
   int nstr, const int32_t* __restrict__ string_start, const int32_t* const* __restrict__ offsets,
-  uint8_t* const* __restrict__ chars, int64_t ntiles)
+  uint8_t* const* __restrict__ chars, int64_t ntiles, const int64_t* __restrict__ status)
 {
+  // runs only when phase 1 flagged non-canonical rows (or no status word was passed)
+  if (status && !(*status & 1)) return;
   const int lane = lane_id();
   const int w    = warp_id();
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -210,18 +212,405 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
   }
 }
 
-int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t num_rows,
-                             const int32_t* const* d_offsets, uint8_t* const* d_chars, cudaStream_t stream)
+
+// --------------------------------------------------------------------------------------------------
+// chars gather, FAST path (canonical rows: a row's chars follow its fixed section in column order,
+// which is what convert_to_rows writes and what phase 1 verified).
+//
+//   producer warp : per tile of <= 32 rows, one TMA bulk load per row of JUST the row's variable
+//                   section (lane = row) into a shared-memory ring, plus the [r0, r0+rows] slice of
+//                   every STRING column's offsets via 16-byte cp.async (completion on the same
+//                   mbarrier) -- so the consumers never wait on a global load;
+//   consumer warps: each owns a block of STRING columns.  lane = row: the string's position in the
+//                   row is the running sum of the lengths of the preceding STRING columns; it is
+//                   read as aligned words, funnel-shifted to the destination's byte alignment and
+//                   written word-wise into a per-warp staging line laid out like the destination;
+//                   the line (the tile's chars of that column: one contiguous range of the chars
+//                   buffer) is flushed with aligned 16-byte st.global.
+// --------------------------------------------------------------------------------------------------
+constexpr int kS2Consumers  = 11;
+constexpr int kS2Threads    = (kS2Consumers + 1) * 32;
+constexpr int kS2Rows       = 32;
+constexpr int kS2Stages     = 3;
+constexpr int kS2StageBytes = 44 * 1024;
+constexpr int kS2Front      = 16;   // slack before the payload (word reads may start 4 bytes early)
+constexpr int kS2Back       = 48;   // slack after it (word reads may run past a string)
+constexpr int kS2Slice      = 36;   // ints per offsets slice: rows + 1 <= 33, padded to 16-byte chunks
+constexpr int kS2StageLine  = 16 + 1024 + 32;  // per-warp staging line
+constexpr int kS2MaxCols    = 160;  // offsets slices must fit shared memory
+
+struct S2Hdr {
+  int64_t r0;
+  int32_t rows;
+  int32_t safe;
+};
+
+struct S2Params {
+  const uint8_t* rows;
+  const int32_t* row_offsets;
+  int64_t rows_bytes;
+  int64_t num_rows;
+  int64_t super_rows;
+  int32_t nstr;
+  int32_t size_per_row;
+  const int32_t* const* offsets;
+  uint8_t* const* chars;
+  const int64_t* status;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (does not bump the pending count)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
+{
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_constant__ S2Params p)
+{
+  if (p.status && (*p.status & 1)) return;  // non-canonical rows: the generic kernel does the work
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NS        = kS2Stages;
+  constexpr int stage_span = kS2Front + kS2StageBytes + kS2Back;
+  uint8_t* payload0  = smem;
+  int32_t* rowsm0    = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(NS) * stage_span);  // [NS][36]
+  int32_t* slice0    = rowsm0 + NS * kS2Slice;                                                    // [NS][nstr][36]
+  const int slice_sp = p.nstr * kS2Slice;
+  S2Hdr* hdr0        = reinterpret_cast<S2Hdr*>(slice0 + static_cast<size_t>(NS) * slice_sp);
+  uint64_t* full     = reinterpret_cast<uint64_t*>(hdr0 + NS);
+  uint64_t* empty    = full + NS;
+  const int32_t** s_offs = reinterpret_cast<const int32_t**>(empty + NS);
+  uint8_t** s_chars      = reinterpret_cast<uint8_t**>(const_cast<int32_t**>(s_offs) + p.nstr);
+  uint8_t* stg0          = reinterpret_cast<uint8_t*>(s_chars + p.nstr);
+  stg0                   = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stg0) + 15) & ~uintptr_t{15});
+
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  for (int i = tid; i < p.nstr; i += kS2Threads) {
+    s_offs[i]  = p.offsets[i];
+    s_chars[i] = p.chars[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1 + 32);  // lane 0's arrive.expect_tx + one cp.async arrive per producer lane
+      mbar_init(&empty[s], kS2Consumers);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uintptr_t b_lo = reinterpret_cast<uintptr_t>(p.rows);
+  const uintptr_t b_hi = b_lo + p.rows_bytes;
+
+  if (warp_id() == 0) {
+    // =================================== producer ===================================
+    int64_t sup = blockIdx.x;
+    int64_t r   = sup * p.super_rows;
+    int64_t c1  = tmin(p.num_rows, r + p.super_rows);
+    // per-lane geometry of the NEXT tile (lane = row)
+    int g_rows = 0;
+    bool g_end = false, g_safe = false;
+    uintptr_t a_lo = 0, a_hi = 0, t_lo = 0, t_hi = 0, fl = 0;
+    int32_t slot = 0;
+    auto next_geometry = [&]() {
+      if (r >= c1) {
+        sup += gridDim.x;
+        r  = sup * p.super_rows;
+        c1 = tmin(p.num_rows, r + p.super_rows);
+      }
+      g_end = r >= p.num_rows;
+      if (g_end) return;
+      int rows = static_cast<int>(tmin<int64_t>(kS2Rows, c1 - r));
+      int64_t o0 = 0, o1 = 0;
+      if (lane < rows) {
+        o0 = p.row_offsets[r + lane];
+        o1 = p.row_offsets[r + lane + 1];
+      }
+      int64_t gs = o0 + p.size_per_row, ge = o1;
+      if (ge < gs) ge = gs;
+      a_lo = b_lo + gs;
+      a_hi = b_lo + ge;
+      fl   = a_lo & ~uintptr_t{15};
+      t_lo = fl < b_lo ? fl + 16 : fl;
+      t_hi = (a_hi + 15) & ~uintptr_t{15};
+      if (t_hi > b_hi) t_hi = a_hi & ~uintptr_t{15};
+      if (t_hi < t_lo) t_hi = t_lo;
+      if (lane >= rows || a_hi == a_lo) { t_hi = t_lo; }
+      int32_t span = (lane < rows) ? static_cast<int32_t>(tmin<uintptr_t>(((a_hi + 15) & ~uintptr_t{15}) - fl, 1u << 30)) : 0;
+      // exclusive scan of the window spans -> slot of each row; rows that fit the stage
+      int32_t x = span;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      slot = x - span;
+      const bool ok = lane < rows && x <= kS2StageBytes;
+      int fit       = __popc(__ballot_sync(0xffffffffu, ok));
+      // ballot counts lanes that fit; spans are non-negative so the set is a prefix
+      if (fit < rows) fit &= ~7;
+      g_safe = false;
+      if (fit == 0) {
+        g_safe = true;
+        rows   = tmin(rows, 8);
+      } else {
+        rows = fit;
+      }
+      g_rows = rows;
+    };
+    next_geometry();
+
+    for (int it = 0;; ++it) {
+      const int s        = it % NS;
+      const uint32_t par = ((it / NS) & 1) ^ 1;
+      if (lane == 0) mbar_wait(&empty[s], par);
+      __syncwarp();
+      uint8_t* pay   = payload0 + static_cast<size_t>(s) * stage_span + kS2Front;
+      int32_t* rowsm = rowsm0 + s * kS2Slice;
+      int32_t* slice = slice0 + static_cast<size_t>(s) * slice_sp;
+      S2Hdr* h       = hdr0 + s;
+      if (g_end) {
+        if (lane == 0) {
+          h->rows = 0;
+          mbar_arrive(&full[s]);
+        }
+        // the other 32 expected arrivals: complete the phase so the consumers wake up
+        cp_async_mbar_arrive_noinc(&full[s]);
+        break;
+      }
+      const int rows  = g_rows;
+      const bool safe = g_safe;
+      uint32_t tx     = 0;
+      if (!safe && lane < rows) {
+        tx           = static_cast<uint32_t>(t_hi - t_lo);
+        rowsm[lane]  = slot + static_cast<int32_t>(a_lo - fl);
+        // bytes of [a_lo, a_hi) outside the TMA window [t_lo, t_hi): copy by hand
+        for (uintptr_t a = a_lo; a < tmin(tmax(t_lo, a_lo), a_hi); ++a) pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
+        for (uintptr_t a = tmax(tmin(t_hi, a_hi), tmin(tmax(t_lo, a_lo), a_hi)); a < a_hi; ++a)
+          pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
+      }
+      uint32_t total = tx;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) {
+        h->r0   = r;
+        h->rows = rows;
+        h->safe = safe ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], total);  // release: header / rowsm / hand copies visible
+      __syncwarp();
+      if (tx) tma_load_1d(pay + slot + (t_lo - fl), reinterpret_cast<const void*>(t_lo), tx, &full[s]);
+      // offsets slices [r, r + rows] of every STRING column
+      const int nchunk = (rows + 4) >> 2;  // 16-byte chunks holding entries 0..rows
+      for (int idx = lane; idx < p.nstr * nchunk; idx += 32) {
+        const int sc       = idx / nchunk;
+        const int q        = idx - sc * nchunk;
+        const int32_t* src = s_offs[sc] + r + 4 * q;
+        int32_t* dst       = slice + sc * kS2Slice + 4 * q;
+        const int64_t last = r + 4 * q + 3;  // entries [0, num_rows] exist
+        if (last <= p.num_rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+          cp_async16(dst, src);
+        } else {
+          for (int e = 0; e < 4; ++e)
+            if (r + 4 * q + e <= p.num_rows) cp_async4(dst + e, src + e);
+        }
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+      r += rows;
+      next_geometry();
+    }
+  } else {
+    // =================================== consumers ===================================
+    const int cw       = warp_id() - 1;
+    const int s0       = (cw * p.nstr) / kS2Consumers;
+    const int s1       = ((cw + 1) * p.nstr) / kS2Consumers;
+    uint8_t* stg       = stg0 + static_cast<size_t>(cw) * kS2StageLine;
+    const uint32_t stg_s = smem_u32(stg);
+    for (int it = 0;; ++it) {
+      const int s        = it % NS;
+      const uint32_t par = (it / NS) & 1;
+      mbar_wait(&full[s], par);
+      const S2Hdr h = hdr0[s];
+      if (h.rows == 0) break;
+      const uint8_t* pay   = payload0 + static_cast<size_t>(s) * stage_span + kS2Front;
+      const int32_t* rowsm = rowsm0 + s * kS2Slice;
+      const int32_t* slice = slice0 + static_cast<size_t>(s) * slice_sp;
+      const int rows       = h.rows;
+      const bool active    = lane < rows;
+      const uint32_t pay_s = smem_u32(pay);
+      const int32_t rowsm_lane = (!h.safe && active) ? rowsm[lane] : 0;
+      // this lane's row: start of its variable section
+      const uint8_t* var0;
+      if (!h.safe) {
+        var0 = pay + (active ? rowsm[lane] : 0);
+      } else {
+        var0 = p.rows + (active ? static_cast<int64_t>(p.row_offsets[h.r0 + lane]) + p.size_per_row : 0);
+      }
+      // running position inside the variable section: lengths of the STRING columns before s0
+      int32_t run = 0;
+      if (active)
+        for (int sc = 0; sc < s0; ++sc) run += slice[sc * kS2Slice + lane + 1] - slice[sc * kS2Slice + lane];
+      for (int sc = s0; sc < s1; ++sc) {
+        const int32_t* sl  = slice + sc * kS2Slice;
+        const int32_t base = sl[0];
+        const int32_t T    = sl[rows] - base;
+        int32_t o0 = 0, L = 0;
+        if (active) {
+          o0 = sl[lane];
+          L  = tmax(sl[lane + 1] - o0, 0);
+        }
+        const int32_t pe         = o0 - base;
+        const int32_t run_before = run;
+        const uint8_t* src       = var0 + run;
+        run += L;
+        if (T <= 0) continue;
+        uint8_t* D     = s_chars[sc] + base;
+        const int maxL = __reduce_max_sync(0xffffffffu, L);
+        if (!h.safe && maxL <= 32 && T <= 1024) {
+          // ---- fast: word-granular copy into the staging line, then aligned 16-byte flush ----------
+          // everything below addresses shared memory through 32-bit shared-space addresses (explicit
+          // ld.shared / st.shared: the generic pointers above would compile to LD/ST + 64-bit math)
+          const int a         = static_cast<int>(reinterpret_cast<uintptr_t>(D) & 15);
+          const int d         = a + pe;
+          const int dsh       = d & 3;
+          const uint32_t srcs = pay_s + static_cast<uint32_t>(rowsm_lane + run_before);
+          const int ssh       = static_cast<int>(srcs & 3u);
+          const int dlt       = ssh - dsh;  // source byte offset of dst word 0, relative to the aligned source word
+          const uint32_t sp   = (srcs - ssh) + (dlt < 0 ? -4 : 0);
+          const int sh        = (dlt < 0 ? 4 + dlt : dlt) * 8;
+          const int end       = dsh + L;                 // one past the last staging byte, relative to word w0
+          const int kfull0    = dsh ? 1 : 0;             // first full word
+          const int kfull1    = end >> 2;                // one past the last full word
+          const uint32_t w0s  = stg_s + static_cast<uint32_t>(d & ~3);
+          const int Kmax      = (3 + maxL + 3) >> 2;     // warp-uniform bound on the words any lane touches
+          uint32_t prev       = 0;
+          if (L > 0) prev = lds_u32(sp);
+          uint32_t first = 0, lastw = 0;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            if (k < Kmax) {
+              uint32_t y = 0;
+              if (4 * k < end) {
+                const uint32_t nxt = lds_u32(sp + 4 * (k + 1));
+                y                  = __funnelshift_r(prev, nxt, sh);
+                prev               = nxt;
+                if (k >= kfull0 && k < kfull1) sts_u32(w0s + 4 * k, y);
+              }
+              if (k == 0) first = y;
+              if (k == kfull1) lastw = y;
+            }
+          }
+          if (L > 0) {
+            // head bytes [dsh, min(4, end)) of word 0 and tail bytes [0, end & 3) of word kfull1
+            if (dsh) {
+              const int hi = tmin(end, 4);
+              for (int t = dsh; t < hi; ++t) sts_u8(w0s + t, first >> (8 * t));
+            }
+            if ((end & 3) && (kfull1 > 0 || !dsh)) {
+              for (int t = 0; t < (end & 3); ++t) sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
+            }
+          }
+          __syncwarp();
+          uint8_t* Dal      = D - a;  // 16-byte aligned
+          const int nchunks = (a + T + 15) >> 4;
+          for (int c = lane; c < nchunks; c += 32) {
+            const int lo = c * 16, hi = lo + 16;
+            if (lo >= a && hi <= a + T) {
+              uint32_t v0, v1, v2, v3;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + lo));
+              asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + lo), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+            } else {
+              for (int b = tmax(lo, a); b < tmin(hi, a + T); ++b) Dal[b] = stg[b];
+            }
+          }
+          __syncwarp();
+        } else {
+          // ---- slow: long strings / SAFE tiles: lane = destination byte, source row by shuffle search ----
+          const int last       = rows - 1;
+          const uint32_t upe   = static_cast<uint32_t>(pe);
+          const uint32_t bound = (static_cast<uint32_t>(T) + 31u) & ~31u;
+          const uint64_t sbase = reinterpret_cast<uint64_t>(src);
+          for (uint32_t q = lane; q < bound; q += 32) {
+            int j = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const int cand   = j + step;
+              const uint32_t v = __shfl_sync(0xffffffffu, upe, cand & 31);
+              if (cand <= last && v <= q) j = cand;
+            }
+            const uint32_t pj = __shfl_sync(0xffffffffu, upe, j);
+            const uint64_t sj = __shfl_sync(0xffffffffu, sbase, j);
+            if (q < static_cast<uint32_t>(T)) D[q] = *reinterpret_cast<const uint8_t*>(sj + (q - pj));
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
+}
+
+static size_t strings2_smem_bytes(int nstr)
+{
+  size_t b = static_cast<size_t>(kS2Stages) * (kS2Front + kS2StageBytes + kS2Back);
+  b += static_cast<size_t>(kS2Stages) * kS2Slice * 4;
+  b += static_cast<size_t>(kS2Stages) * nstr * kS2Slice * 4;
+  b += static_cast<size_t>(kS2Stages) * sizeof(S2Hdr) + 2 * kS2Stages * 8;
+  b += static_cast<size_t>(nstr) * 16 + 16;
+  b += static_cast<size_t>(kS2Consumers) * kS2StageLine;
+  return (b + 127) & ~size_t{127};
+}
+
+int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
+                             int64_t num_rows, const int32_t* const* d_offsets, uint8_t* const* d_chars,
+                             const int64_t* d_status, cudaStream_t stream)
 {
   const int nstr = plan->num_string_columns;
   if (nstr == 0 || num_rows == 0) return SRJ_OK;
-  const int64_t ntiles = (num_rows + 31) / 32;
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t grid = std::min<int64_t>(ntiles, static_cast<int64_t>(nsm) * 8);
+  const bool fast = d_status != nullptr && nstr <= kS2MaxCols;
+  if (fast) {
+    S2Params p{};
+    p.rows         = rows;
+    p.row_offsets  = row_offsets;
+    p.rows_bytes   = rows_bytes;
+    p.num_rows     = num_rows;
+    p.super_rows   = kS2Rows * 8;
+    p.nstr         = nstr;
+    p.size_per_row = plan->size_per_row;
+    p.offsets      = d_offsets;
+    p.chars        = d_chars;
+    p.status       = d_status;
+    const int64_t ns   = (num_rows + p.super_rows - 1) / p.super_rows;
+    const int64_t grid = std::min<int64_t>(nsm, ns);
+    const size_t smem  = strings2_smem_bytes(nstr);
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(strings2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    strings2_kernel<<<static_cast<unsigned>(grid), kS2Threads, smem, stream>>>(p);
+  }
+  // generic kernel: does the work only when the status word flags non-canonical rows (or is absent)
+  const int64_t ntiles = (num_rows + 31) / 32;
+  const int64_t grid   = std::min<int64_t>(ntiles, static_cast<int64_t>(nsm) * 8);
   strings_from_rows_kernel<<<static_cast<unsigned>(grid), kStrWarps * 32, 0, stream>>>(
-    rows, row_offsets, plan->fixed_row_size, num_rows, nstr, plan->d_string_start, d_offsets, d_chars, ntiles);
+    rows, row_offsets, plan->fixed_row_size, num_rows, nstr, plan->d_string_start, d_offsets, d_chars, ntiles,
+    fast ? d_status : nullptr);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }

@@ -316,7 +316,7 @@ class RowConversion:
                     outs.append(ColumnVector(d, n, _empty(n * d.size_in_bytes(), torch.uint8, dev), mask))
             nc = len(dts)
             nulls = torch.zeros(max(nc, 1), dtype=torch.int64, device=dev)
-            totals = torch.zeros(max(nc, 1), dtype=torch.int64, device=dev)
+            totals = torch.zeros(nc + 1, dtype=torch.int64, device=dev)   # + status word for phase 2
             carr = _carray(outs)
             rows_ptr = child.data.data_ptr() if child.data is not None and child.data.numel() else None
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rows_ptr, vec.offsets.data_ptr(), child.size, n,
@@ -330,8 +330,8 @@ class RowConversion:
                             raise CudfColumnSizeOverflowException(f"string column {i} exceeds the int32 chars limit")
                         outs[i].data = _empty(int(h_tot[i]), torch.uint8, dev)
                 carr = _carray(outs)
-                N.check(lib.srj_convert_from_rows_strings(plan.handle, rows_ptr, vec.offsets.data_ptr(), n, carr,
-                                                          stream), "convertFromRows")
+                N.check(lib.srj_convert_from_rows_strings(plan.handle, rows_ptr, vec.offsets.data_ptr(), child.size, n,
+                                                          carr, totals.data_ptr(), stream), "convertFromRows")
             h_nulls = nulls.cpu().numpy()
             for i, o in enumerate(outs):
                 o._null_count = int(h_nulls[i])

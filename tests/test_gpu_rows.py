@@ -249,3 +249,29 @@ def test_batch_split_over_2gib():
                      None, 0, 1000) for t, c in zip(types, dcols)]
     (_, odata), = O.convert_to_rows(sample)
     assert np.array_equal(out[1].child.data[: len(odata)].cpu().numpy(), odata)
+
+
+def test_non_canonical_string_layout_follows_pair_offsets():
+    """copy_strings_from_rows reads chars at row + pair.offset (RC:1143), whatever the order inside the
+    row.  Rows whose variable section is permuted (pairs updated) must still convert correctly: phase 1
+    flags them and phase 2 falls back from its canonical fast path to the generic gather."""
+    G = _gpu()
+    import srj_b200 as S
+    types = [O.INT32, O.STRING, O.INT64, O.STRING]
+    n = 3000
+    cols = random_table(types, n, seed=21)
+    (offs, data), = O.convert_to_rows(cols)
+    st, sz, voff, spr = O.compute_layout(types)
+    data = data.copy()
+    for r in range(n):
+        row = data[offs[r]:offs[r + 1]]
+        (o1, l1), (o3, l3) = row[st[1]:st[1] + 8].view(np.uint32), row[st[3]:st[3] + 8].view(np.uint32)
+        a, b = row[o1:o1 + l1].copy(), row[o3:o3 + l3].copy()
+        row[spr:spr + l3] = b                      # column 3's chars first ...
+        row[spr + l3:spr + l3 + l1] = a            # ... then column 1's
+        row[st[3]:st[3] + 8].view(np.uint32)[:] = (spr, l3)
+        row[st[1]:st[1] + 8].view(np.uint32)[:] = (spr + l3, l1)
+    want, _ = O.convert_from_rows(data, offs, n, types)
+    tbl = S.RowConversion.convertFromRows(G.rows_to_device(offs, data), [S.DType(t) for t in types])
+    for g, w, c in zip(tbl.columns, want, cols):
+        assert cols_equal(G.to_host(g), w) and cols_equal(G.to_host(g), c)
