@@ -225,6 +225,7 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   // development knobs (tuning only)
   if (const char* e = getenv("SRJ_FR_STAGES")) tl.num_stages = atoi(e);
   if (const char* e = getenv("SRJ_FR_TILE_ROWS")) { R = atoi(e); tl.stage_bytes = std::max(R * S, 4096); }
+  if (const char* e = getenv("SRJ_FR_STAGE_KB")) tl.stage_bytes = atoi(e) * 1024;
   tl.tile_rows     = R;
   tl.rows_per_item = R >= 32 ? 32 : R;
 

@@ -319,8 +319,11 @@ __device__ __forceinline__ void validity_tile(const FromRowsParams& p, const Sme
   const int ng32   = (tv.rows + 31) >> 5;
   const int vitems = nq * ng32;
   if (ws.vstart >= vitems) return;
-  int g = ws.vstart / nq;  // one division per tile; then incremental
-  int q = ws.vstart - g * nq;
+  int g = 0, q = ws.vstart;
+  if (ng32 > 1) {  // one division per tile; then incremental
+    g = ws.vstart / nq;
+    q = ws.vstart - g * nq;
+  }
   for (int item = ws.vstart; item < vitems; item += NCW) {
     const int row = g * 32 + lane;
     uint32_t r    = 0;
@@ -410,7 +413,8 @@ __device__ __noinline__ void hash_tile(const FromRowsParams& p, const TileView& 
 // Variable-width tables: does every row place its strings where convert_to_rows would (chars of the
 // STRING columns back to back, in column order, from byte size_per_row -- RC:838-858)?  Phase 2's fast
 // path relies on it; a mismatch only flips a status bit that routes phase 2 to the generic gather.
-// A warp takes a row: lane = STRING column, the expected offset is a warp exclusive scan of the lengths.
+// A warp takes a row, lane = STRING column: a row is canonical iff the first pair starts at size_per_row
+// and every pair starts where its left neighbour ends -- one shuffle per 32 columns, no scan.
 template <int NCW, bool SAFE>
 __device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const TileView& tv, int cw,
                                                   const int32_t* s_string_start)
@@ -419,7 +423,7 @@ __device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const
   bool bad       = false;
   for (int row = cw; row < tv.rows; row += NCW) {
     const uint8_t* rp = row_ptr<true>(tv, row);
-    uint32_t carry    = static_cast<uint32_t>(p.size_per_row);
+    uint32_t expect   = static_cast<uint32_t>(p.size_per_row);
     for (int s0 = 0; s0 < p.nstr; s0 += 32) {
       const int s = s0 + lane;
       uint32_t so = 0, ln = 0;
@@ -428,14 +432,11 @@ __device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const
         so                = static_cast<uint32_t>(load_key<SAFE>(pp, 4));
         ln                = static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
       }
-      uint32_t x = ln;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-      }
-      if (s < p.nstr) bad |= so != carry + x - ln;
-      carry += __shfl_sync(0xffffffffu, x, 31);
+      const uint32_t end = so + ln;
+      uint32_t prev_end  = __shfl_up_sync(0xffffffffu, end, 1);
+      if (lane == 0) prev_end = expect;
+      if (s < p.nstr) bad |= so != prev_end;
+      expect = __shfl_sync(0xffffffffu, end, tmin(31, p.nstr - s0 - 1));
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status, 1ull);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
 //                   the line (the tile's chars of that column: one contiguous range of the chars
 //                   buffer) is flushed with aligned 16-byte st.global.
 // --------------------------------------------------------------------------------------------------
-constexpr int kS2Consumers  = 11;
+constexpr int kS2Consumers  = 19;  // issue/latency-bound gather: more independent warps (80 registers each)
 constexpr int kS2Threads    = (kS2Consumers + 1) * 32;
 constexpr int kS2Rows       = 32;
 constexpr int kS2Stages     = 3;
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
   }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1 + 32);  // lane 0's arrive.expect_tx + one cp.async arrive per producer lane
+      mbar_init(&full[s], 1);  // lane 0's arrive.expect_tx; every byte of the stage arrives by TMA
       mbar_init(&empty[s], kS2Consumers);
     }
     fence_mbar_init();
@@ -389,8 +389,6 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
           h->rows = 0;
           mbar_arrive(&full[s]);
         }
-        // the other 32 expected arrivals: complete the phase so the consumers wake up
-        cp_async_mbar_arrive_noinc(&full[s]);
         break;
       }
       const int rows  = g_rows;
@@ -404,7 +402,24 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
         for (uintptr_t a = tmax(tmin(t_hi, a_hi), tmin(tmax(t_lo, a_lo), a_hi)); a < a_hi; ++a)
           pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
       }
-      uint32_t total = tx;
+      // offsets slices [r, r + rows] of every STRING column: one small TMA bulk copy per column (r is a
+      // multiple of 8, so &offsets[c][r] is 16-byte aligned whenever the buffer is).  Entries past the end
+      // of the array (last tile) and unaligned buffers are copied by hand.
+      const int need     = rows + 1;                                   // entries wanted
+      const int64_t have = p.num_rows + 1 - r;                         // entries that exist from r on
+      const int nbulk    = static_cast<int>(tmin<int64_t>((need + 3) & ~3, have & ~int64_t{3}));  // whole 16-byte chunks
+      uint32_t stx       = 0;
+      for (int sc = lane; sc < p.nstr; sc += 32) {
+        const int32_t* src = s_offs[sc] + r;
+        int32_t* dst       = slice + sc * kS2Slice;
+        int done           = 0;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && nbulk > 0) {
+          stx += static_cast<uint32_t>(nbulk) * 4u;
+          done = nbulk;
+        }
+        for (int e = done; e < need && e < have; ++e) dst[e] = src[e];
+      }
+      uint32_t total = tx + stx;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
       if (lane == 0) {
@@ -416,22 +431,11 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
       if (lane == 0) mbar_arrive_expect_tx(&full[s], total);  // release: header / rowsm / hand copies visible
       __syncwarp();
       if (tx) tma_load_1d(pay + slot + (t_lo - fl), reinterpret_cast<const void*>(t_lo), tx, &full[s]);
-      // offsets slices [r, r + rows] of every STRING column
-      const int nchunk = (rows + 4) >> 2;  // 16-byte chunks holding entries 0..rows
-      for (int idx = lane; idx < p.nstr * nchunk; idx += 32) {
-        const int sc       = idx / nchunk;
-        const int q        = idx - sc * nchunk;
-        const int32_t* src = s_offs[sc] + r + 4 * q;
-        int32_t* dst       = slice + sc * kS2Slice + 4 * q;
-        const int64_t last = r + 4 * q + 3;  // entries [0, num_rows] exist
-        if (last <= p.num_rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-          cp_async16(dst, src);
-        } else {
-          for (int e = 0; e < 4; ++e)
-            if (r + 4 * q + e <= p.num_rows) cp_async4(dst + e, src + e);
-        }
+      for (int sc = lane; sc < p.nstr; sc += 32) {
+        const int32_t* src = s_offs[sc] + r;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && nbulk > 0)
+          tma_load_1d(slice + sc * kS2Slice, src, static_cast<uint32_t>(nbulk) * 4u, &full[s]);
       }
-      cp_async_mbar_arrive_noinc(&full[s]);
       r += rows;
       next_geometry();
     }
@@ -499,32 +503,33 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
           const int kfull1    = end >> 2;                // one past the last full word
           const uint32_t w0s  = stg_s + static_cast<uint32_t>(d & ~3);
           const int Kmax      = (3 + maxL + 3) >> 2;     // warp-uniform bound on the words any lane touches
-          uint32_t prev       = 0;
-          if (L > 0) prev = lds_u32(sp);
+          // all source words first (independent loads), then shift + store
+          uint32_t w[10];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            w[k] = 0;
+            if (k <= Kmax && 4 * (k - 1) < end) w[k] = lds_u32(sp + 4 * k);
+          }
           uint32_t first = 0, lastw = 0;
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
             if (k < Kmax) {
-              uint32_t y = 0;
-              if (4 * k < end) {
-                const uint32_t nxt = lds_u32(sp + 4 * (k + 1));
-                y                  = __funnelshift_r(prev, nxt, sh);
-                prev               = nxt;
-                if (k >= kfull0 && k < kfull1) sts_u32(w0s + 4 * k, y);
-              }
+              const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+              if (k >= kfull0 && k < kfull1) sts_u32(w0s + 4 * k, y);
               if (k == 0) first = y;
               if (k == kfull1) lastw = y;
             }
           }
           if (L > 0) {
             // head bytes [dsh, min(4, end)) of word 0 and tail bytes [0, end & 3) of word kfull1
-            if (dsh) {
-              const int hi = tmin(end, 4);
-              for (int t = dsh; t < hi; ++t) sts_u8(w0s + t, first >> (8 * t));
-            }
-            if ((end & 3) && (kfull1 > 0 || !dsh)) {
-              for (int t = 0; t < (end & 3); ++t) sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
-            }
+            const int hh = dsh ? tmin(end, 4) : 0;
+#pragma unroll
+            for (int t = 1; t < 4; ++t)
+              if (t >= dsh && t < hh) sts_u8(w0s + t, first >> (8 * t));
+            const int tt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
+#pragma unroll
+            for (int t = 0; t < 3; ++t)
+              if (t < tt) sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
           }
           __syncwarp();
           uint8_t* Dal      = D - a;  // 16-byte aligned
