@@ -235,7 +235,15 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   const size_t b_tr = p->tr_entries.size() * sizeof(Entry);
   const size_t b_cs = static_cast<size_t>(num_columns) * 4;
   const size_t b_sc = p->string_columns.size() * 4;
-  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + 64;
+  std::vector<int32_t> tr_chunk(p->tr_entries.size());
+  {
+    // staging layout of to_rows2: widest class first so that every piece stays 16-byte aligned
+    int32_t acc = 0;
+    for (int k = kNumClasses - 1; k >= 0; --k)
+      for (int e = p->tr_class_begin[k]; e < p->tr_class_begin[k + 1]; ++e) { tr_chunk[e] = acc; acc += 1 << k; }
+  }
+  const size_t b_tc = tr_chunk.size() * 4;
+  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + b_tc + 64;
   std::vector<uint8_t> blob(tot, 0);
   size_t o = 0;
   auto put = [&](const void* src, size_t n) { size_t at = o; if (n) memcpy(blob.data() + o, src, n); o += (n + 7) & ~size_t{7}; return at; };
@@ -244,6 +252,7 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   const size_t o_cs = put(st.data(), b_cs);
   const size_t o_sc = put(p->string_columns.data(), b_sc);
   const size_t o_ss = put(string_start.data(), b_sc);
+  const size_t o_tc = put(tr_chunk.data(), b_tc);
   cudaError_t e = cudaMalloc(&p->d_blob, tot);
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
   e = cudaMemcpy(p->d_blob, blob.data(), tot, cudaMemcpyHostToDevice);
@@ -254,6 +263,7 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   p->d_col_start    = reinterpret_cast<const int32_t*>(base + o_cs);
   p->d_string_cols  = reinterpret_cast<const int32_t*>(base + o_sc);
   p->d_string_start = reinterpret_cast<const int32_t*>(base + o_ss);
+  p->d_tr_chunk_off = reinterpret_cast<const int32_t*>(base + o_tc);
   *out              = p;
   return SRJ_OK;
 }
@@ -429,7 +439,7 @@ int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t nu
                         reinterpret_cast<const int32_t* const*>(d + 2 * nc),
                         reinterpret_cast<const uint8_t* const*>(d + 2 * nc + nstr), batches[b].row_start,
                         batches[b].row_count, nstr ? static_cast<const uint64_t*>(workspace) : nullptr,
-                        batch_offsets[b], batch_data[b], batches[b].num_bytes, stream);
+                        batch_offsets[b], batch_data[b], batches[b].num_bytes, stream, tab.data());
     if (rc != SRJ_OK) return rc;
   }
   return SRJ_OK;

@@ -78,6 +78,7 @@ struct srj_plan {
   const int32_t* d_col_start;     // [num_columns]
   const int32_t* d_string_cols;   // [num_string_columns]
   const int32_t* d_string_start;  // [num_string_columns] row byte offset of each pair
+  const int32_t* d_tr_chunk_off;  // [tr_entries] staging byte offset per row unit (to_rows2)
 
   mutable srj::TableRing ring;
 };

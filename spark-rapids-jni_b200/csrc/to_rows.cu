@@ -12,6 +12,7 @@
 // Rows too large for a stage, or unaligned output buffers, take the SAFE path: the same assembly
 // code writing global memory directly, byte-wise.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -44,6 +45,7 @@ struct ToRowsParams {
   const int32_t* string_cols;
   const int32_t* string_start;
   int32_t max_str_entries;  // capacity of the per-tile string tables (rows * nstr)
+  int64_t offset_bias;      // added to the values written to out_offsets (tail launches of a batch)
 };
 
 struct TrHdr {
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
       if (fixed) {
         hi = lo + static_cast<int64_t>(rows) * p.row_stride;
         if (hi - lo > p.stage_bytes) safe = true;
-        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(lo + static_cast<int64_t>(i) * p.row_stride);
+        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(p.offset_bias + lo + static_cast<int64_t>(i) * p.row_stride);
       } else {
         int fit = 0;
         for (int i0 = 0; i0 <= rows; i0 += 32) {
@@ -320,9 +322,9 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
           rows = fit;
         }
         hi = row_off(r + rows);
-        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(row_off(r + i));
+        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(p.offset_bias + row_off(r + i));
       }
-      if (r + rows == p.row_count && lane == 0) p.out_offsets[p.row_count] = static_cast<int32_t>(hi);
+      if (r + rows == p.row_count && lane == 0) p.out_offsets[p.row_count] = static_cast<int32_t>(p.offset_bias + hi);
       if (lane == 0) {
         hdr->r    = r;
         hdr->lo   = lo;
@@ -374,6 +376,260 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
     r += h.rows;
   }
   if (tid == 0) tma_store_wait_read<0>();
+}
+
+
+// ==================================================================================================
+// to_rows, fixed-width tables, full tiles: TMA in, TMA out.
+//
+//   producer warp : per tile of R rows, one TMA bulk load per column (lane = column) of the R values
+//                   -- a contiguous, 16-byte aligned piece of the column -- into a staging ring;
+//   consumer warps: lane = row.  unit = (column, 4 row groups): conflict-free LDS of 32 consecutive
+//                   values from the staging piece, STS into the row images at the column's byte
+//                   offset; column mask words (fetched with plain loads at the top of the tile so
+//                   their latency hides behind the transpose) are bit-transposed by the 32x32
+//                   butterfly into per-row validity bytes; the LIST offsets are written on the way;
+//   one thread    : the finished row images -- ONE contiguous byte range of the output -- leave with
+//                   a single 1-D TMA bulk store; images are double buffered.
+// Padding bytes are zeroed once per CTA (the layout is static: no tile ever writes them again).
+// Tails (< R rows), strings, unaligned buffers and very wide rows go to to_rows_kernel above.
+// ==================================================================================================
+constexpr int kT2Consumers = 11;
+constexpr int kT2Threads   = (kT2Consumers + 1) * 32;
+constexpr int kT2MaxStages = 3;
+
+struct ToRows2Params {
+  const void* const* col_data;
+  const uint32_t* const* masks;
+  int64_t row_start;   // table row of the batch start
+  int64_t num_tiles;   // full tiles to convert
+  int32_t* out_offsets;
+  uint8_t* out_data;
+  int64_t offset_bias;
+  int32_t write_last;  // 1: this launch covers the whole batch, also write out_offsets[row_count]
+  int32_t ncols, nentries;
+  int32_t validity_offset, row_stride;
+  int32_t R;           // rows per tile (multiple of 32)
+  int32_t nstages;
+  int32_t data_bytes;  // sum of the column element sizes (bytes of staging per row)
+  int32_t class_begin[kNumClasses + 1];
+  int32_t cs, gpu;
+  int32_t cls_units[kNumClasses];
+  int32_t cls_ubase[kNumClasses];
+  int32_t v_ubase;
+  const Entry* entries;
+  const int32_t* chunk_off;  // [nentries] byte offset of the entry's piece in a staging stage, per row unit (multiply by R)
+};
+
+__device__ __forceinline__ uint32_t transpose32_t(uint32_t r, int lane)
+{
+  uint32_t m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, r, j);
+    if ((lane & j) == 0) {
+      const uint32_t t = ((r >> j) ^ other) & m;
+      r ^= t << j;
+    } else {
+      const uint32_t t = ((other >> j) ^ r) & m;
+      r ^= t;
+    }
+    m ^= m << (j >> 1);
+  }
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ void t2_class(const ToRows2Params& p, const int32_t* s_start, const int32_t* s_coff,
+                                         uint32_t stage_s, uint32_t image_s, int ustart, int k, int lane)
+{
+  constexpr int B = W >= 16 ? 2 : 4;
+  const int nb     = p.class_begin[k];
+  const int total  = p.cls_units[k];
+  const int gpu    = p.gpu;
+  const int chmask = (1 << p.cs) - 1;
+  for (int u = ustart; u < total; u += kT2Consumers) {
+    const int e      = nb + (u >> p.cs);
+    const int gc     = u & chmask;
+    const int row    = gc * gpu * 32 + lane;
+    uint32_t src     = stage_s + static_cast<uint32_t>(s_coff[e]) * p.R + row * W;
+    uint32_t dst     = image_s + row * p.row_stride + s_start[e];
+    const uint32_t dstep = 32u * p.row_stride;
+    for (int gi = 0; gi < gpu; gi += B) {  // host guarantees gpu % 4 == 0
+      uint32_t v[B][4];
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint32_t a = src + j * 32 * W;
+        if constexpr (W == 1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v[j][0]) : "r"(a));
+        else if constexpr (W == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v[j][0]) : "r"(a));
+        else if constexpr (W == 4) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[j][0]) : "r"(a));
+        else if constexpr (W == 8) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v[j][0]), "=r"(v[j][1]) : "r"(a));
+        else asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3]) : "r"(a));
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint32_t a = dst + j * dstep;
+        if constexpr (W == 1) asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v[j][0]));
+        else if constexpr (W == 2) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v[j][0]));
+        else if constexpr (W == 4) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v[j][0]));
+        else if constexpr (W == 8) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v[j][0]), "r"(v[j][1]));
+        else {  // rows are 8-byte aligned only
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v[j][0]), "r"(v[j][1]));
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a + 8), "r"(v[j][2]), "r"(v[j][3]));
+        }
+      }
+      src += B * 32 * W;
+      dst += B * dstep;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1) to_rows2_kernel(const __grid_constant__ ToRows2Params p)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int NS           = p.nstages;
+  const int stage_bytes  = p.R * p.data_bytes;             // multiple of 32
+  const int image_bytes  = p.R * p.row_stride;             // multiple of 256
+  uint8_t* stage0        = smem;
+  uint8_t* image0        = smem + static_cast<size_t>(NS) * stage_bytes;
+  uint64_t* full         = reinterpret_cast<uint64_t*>(image0 + 2 * static_cast<size_t>(image_bytes));
+  uint64_t* empty        = full + kT2MaxStages;
+  int32_t* s_start       = reinterpret_cast<int32_t*>(empty + kT2MaxStages);
+  int32_t* s_coff        = s_start + p.nentries;
+  const uint8_t** s_col  = reinterpret_cast<const uint8_t**>(s_coff + p.nentries + ((2 * p.nentries) & 1));
+  const uint32_t** s_msk = reinterpret_cast<const uint32_t**>(s_col + p.nentries);
+  int32_t* s_w           = reinterpret_cast<int32_t*>(s_msk + p.ncols);  // [nentries] element size
+
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  for (int i = tid; i < p.nentries; i += kT2Threads) {
+    s_start[i] = p.entries[i].start;
+    s_coff[i]  = p.chunk_off[i];
+    s_col[i]   = static_cast<const uint8_t*>(p.col_data[p.entries[i].column]);
+    int w      = 1;
+    for (int k = 0; k < kNumClasses; ++k)
+      if (i >= p.class_begin[k] && i < p.class_begin[k + 1]) w = 1 << k;
+    s_w[i] = w;
+  }
+  for (int i = tid; i < p.ncols; i += kT2Threads) s_msk[i] = p.masks[i];
+  // zero both row images once: padding bytes are never written again
+  {
+    uint4* z        = reinterpret_cast<uint4*>(image0);
+    const int n16   = (2 * image_bytes) >> 4;
+    for (int i = tid; i < n16; i += kT2Threads) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();  // every thread orders its own zero fill before the later TMA stores
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kT2Consumers);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp_id() == 0) {
+    // =================================== producer ===================================
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int s        = it % NS;
+      const uint32_t par = ((it / NS) & 1) ^ 1;
+      if (lane == 0) {
+        mbar_wait(&empty[s], par);
+        mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(stage_bytes));
+      }
+      __syncwarp();
+      uint8_t* st        = stage0 + static_cast<size_t>(s) * stage_bytes;
+      const int64_t arow = p.row_start + tile * p.R;
+      for (int e = lane; e < p.nentries; e += 32) {
+        const int w = s_w[e];
+        tma_load_1d(st + static_cast<size_t>(s_coff[e]) * p.R, s_col[e] + arow * w, static_cast<uint32_t>(p.R * w), &full[s]);
+      }
+    }
+  } else {
+    // =================================== consumers ===================================
+    const int cw = warp_id() - 1;
+    int ustart[kNumClasses];
+#pragma unroll
+    for (int k = 0; k < kNumClasses; ++k) ustart[k] = (cw + kT2Consumers - (p.cls_ubase[k] % kT2Consumers)) % kT2Consumers;
+    const int vstart = (cw + kT2Consumers - (p.v_ubase % kT2Consumers)) % kT2Consumers;
+    const int nq     = (p.ncols + 31) >> 5;
+    const int nvb    = (p.ncols + 7) >> 3;
+    const int ng32   = p.R >> 5;
+    const int vitems = nq * ng32;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int s        = it % NS;
+      const uint32_t par = (it / NS) & 1;
+      const int b        = it & 1;
+      const int64_t r0   = tile * p.R;             // batch-relative row
+      const int64_t arow = p.row_start + r0;       // table row
+      // mask words for this warp's validity items: issued now, consumed after the transpose
+      uint32_t mw[4];
+      int nmine = 0;
+      for (int item = vstart; item < vitems && nmine < 4; item += kT2Consumers, ++nmine) {
+        const int g = item / nq, q = item - g * nq;
+        const int c = q * 32 + lane;
+        uint32_t w  = 0;
+        if (c < p.ncols) {
+          const uint32_t* mp = s_msk[c];
+          w                  = mp ? __ldg(mp + ((arow >> 5) + g)) : 0xffffffffu;
+        }
+        mw[nmine] = w;
+      }
+      mbar_wait(&full[s], par);
+      const uint32_t stage_s = smem_u32(stage0 + static_cast<size_t>(s) * stage_bytes);
+      const uint32_t image_s = smem_u32(image0 + static_cast<size_t>(b) * image_bytes);
+      t2_class<16>(p, s_start, s_coff, stage_s, image_s, ustart[4], 4, lane);
+      t2_class<8>(p, s_start, s_coff, stage_s, image_s, ustart[3], 3, lane);
+      t2_class<4>(p, s_start, s_coff, stage_s, image_s, ustart[2], 2, lane);
+      t2_class<2>(p, s_start, s_coff, stage_s, image_s, ustart[1], 1, lane);
+      t2_class<1>(p, s_start, s_coff, stage_s, image_s, ustart[0], 0, lane);
+      // validity
+      {
+        int k = 0;
+        for (int item = vstart; item < vitems; item += kT2Consumers, ++k) {
+          const int g = item / nq, q = item - g * nq;
+          uint32_t w;
+          if (k < 4) {
+            w = mw[k];
+          } else {
+            const int c = q * 32 + lane;
+            w           = 0;
+            if (c < p.ncols) {
+              const uint32_t* mp = s_msk[c];
+              w                  = mp ? __ldg(mp + ((arow >> 5) + g)) : 0xffffffffu;
+            }
+          }
+          const uint32_t bits = transpose32_t(w, lane);   // lane = row g*32+lane, bit = column 32q + bit
+          const uint32_t a    = image_s + (g * 32 + lane) * p.row_stride + p.validity_offset + 4 * q;
+          const int nbv       = tmin(4, nvb - 4 * q);
+          if (nbv == 4 && ((p.validity_offset & 3) == 0)) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(bits));
+          } else {
+            for (int i = 0; i < nbv; ++i) asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + i), "r"(bits >> (8 * i)));
+          }
+        }
+      }
+      // LIST offsets of the tile's rows
+      for (int i = cw * 32 + lane; i < p.R; i += kT2Consumers * 32)
+        p.out_offsets[r0 + i] = static_cast<int32_t>(p.offset_bias + (r0 + i) * p.row_stride);
+      if (p.write_last && tile == p.num_tiles - 1 && cw == 0 && lane == 0)
+        p.out_offsets[r0 + p.R] = static_cast<int32_t>(p.offset_bias + (r0 + p.R) * p.row_stride);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      named_bar_sync(1, kT2Consumers * 32);  // every consumer has finished writing image b
+      if (cw == 0 && lane == 0) {
+        tma_store_1d(p.out_data + r0 * p.row_stride, image0 + static_cast<size_t>(b) * image_bytes,
+                     static_cast<uint32_t>(image_bytes));
+        tma_store_commit();
+        tma_store_wait_read<1>();  // the store of the previous tile (other image) has drained
+      }
+      named_bar_sync(2, kT2Consumers * 32);  // the other image is free for the next tile
+    }
+    if (cw == 0 && lane == 0) tma_store_wait_read<0>();
+  }
 }
 
 // ---- row sizes: round_up(size_per_row + sum(len), 8), inclusive scan (RC:201-257, 1490-1491) -------
@@ -496,10 +752,103 @@ static size_t to_rows_smem_bytes(const srj_plan* plan, int tile_rows, int stage_
   return (b + 127) & ~size_t{127};
 }
 
+static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                                  const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars,
+                                  int64_t row_start, int64_t row_count, const uint64_t* d_cum_sizes,
+                                  int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes, int64_t offset_bias,
+                                  cudaStream_t stream);
+
+// static unit schedule shared by the two directions (see from_rows.cu)
+static void t2_schedule(ToRows2Params& p)
+{
+  const int ngroups = p.R / 32;
+  int slots         = 0;
+  for (int k = 0; k < kNumClasses; ++k) slots += p.class_begin[k + 1] - p.class_begin[k];
+  int cs = 0;
+  while ((slots << cs) < 96 && (ngroups % (8 << cs)) == 0) ++cs;
+  p.cs  = cs;
+  p.gpu = (ngroups + (1 << cs) - 1) >> cs;
+  int ub = 0;
+  for (int k = kNumClasses - 1; k >= 0; --k) {
+    p.cls_ubase[k] = ub;
+    p.cls_units[k] = (p.class_begin[k + 1] - p.class_begin[k]) << cs;
+    ub += p.cls_units[k];
+  }
+  p.v_ubase = ub;
+}
+
 int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
                    const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
                    int64_t row_count, const uint64_t* d_cum_sizes, int32_t* out_offsets, uint8_t* out_data,
-                   int64_t out_bytes, cudaStream_t stream)
+                   int64_t out_bytes, cudaStream_t stream, const void* const* h_col_data)
+{
+  if (row_count == 0) return SRJ_OK;
+  // ---- fast kernel: fixed-width tables, full tiles, 16-byte aligned buffers ------------------------
+  const int S = plan->fixed_row_size;
+  int D       = 0;
+  for (int sz : plan->col_size) D += sz;
+  bool fast = plan->num_string_columns == 0 && plan->d_tr_chunk_off != nullptr && getenv("SRJ_TR_GENERIC") == nullptr;
+  int R = 0, NS = 3;
+  if (fast) {
+    // smem: NS staging stages of R*D bytes + 2 row images of R*S bytes (+ tables)
+    const int tables = static_cast<int>(plan->tr_entries.size()) * 28 + plan->num_columns * 8 + 1024;
+    const int budget = 225 * 1024 - tables;
+    R                = budget / (NS * D + 2 * S) / 128 * 128;
+    if (R < 128) { NS = 2; R = budget / (NS * D + 2 * S) / 32 * 32; }
+    if (R > 512) R = 512;
+    if (R >= 128) R = R / 128 * 128;
+    fast = R >= 128 && row_count >= R && (reinterpret_cast<uintptr_t>(out_data) & 15) == 0 && (row_start % 32) == 0;
+    if (fast && h_col_data)
+      for (int c = 0; c < plan->num_columns && fast; ++c) fast = (reinterpret_cast<uintptr_t>(h_col_data[c]) & 15) == 0;
+    else
+      fast = false;
+  }
+  int64_t done = 0;
+  if (fast) {
+    ToRows2Params p{};
+    p.col_data        = d_col_data;
+    p.masks           = d_masks;
+    p.row_start       = row_start;
+    p.num_tiles       = row_count / R;
+    p.out_offsets     = out_offsets;
+    p.out_data        = out_data;
+    p.offset_bias     = 0;
+    p.write_last      = (row_count % R) == 0;
+    p.ncols           = plan->num_columns;
+    p.nentries        = static_cast<int32_t>(plan->tr_entries.size());
+    p.validity_offset = plan->validity_offset;
+    p.row_stride      = S;
+    p.R               = R;
+    p.nstages         = NS;
+    p.data_bytes      = D;
+    for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->tr_class_begin[k];
+    p.entries   = plan->d_tr_entries;
+    p.chunk_off = plan->d_tr_chunk_off;
+    t2_schedule(p);
+    int dev = 0, nsm = 0;
+    SRJ_CUDA_TRY(cudaGetDevice(&dev));
+    SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t grid = std::min<int64_t>(nsm, p.num_tiles);
+    size_t smem        = static_cast<size_t>(NS) * R * D + 2 * static_cast<size_t>(R) * S + 2 * kT2MaxStages * 8;
+    smem += static_cast<size_t>(p.nentries) * (4 + 4 + 8 + 4) + 8 + static_cast<size_t>(p.ncols) * 8 + 64;
+    smem = (smem + 127) & ~size_t{127};
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    to_rows2_kernel<<<static_cast<unsigned>(grid), kT2Threads, smem, stream>>>(p);
+    SRJ_CUDA_TRY(cudaGetLastError());
+    done = p.num_tiles * R;
+    if (done == row_count) return SRJ_OK;
+  }
+  // ---- generic kernel: everything else, and the tail rows of a fast launch ---------------------------
+  return launch_to_rows_generic(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start + done, row_count - done,
+                                d_cum_sizes, out_offsets + done, out_data + done * S * (plan->num_string_columns == 0 ? 1 : 0),
+                                out_bytes, done * S, stream);
+}
+
+static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                                  const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars,
+                                  int64_t row_start, int64_t row_count, const uint64_t* d_cum_sizes,
+                                  int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes, int64_t offset_bias,
+                                  cudaStream_t stream)
 {
   if (row_count == 0) return SRJ_OK;
   ToRowsParams p{};
@@ -523,6 +872,7 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
   p.entries      = plan->d_tr_entries;
   p.string_cols  = plan->d_string_cols;
   p.string_start = plan->d_string_start;
+  p.offset_bias  = offset_bias;
 
   // to_rows tiling: two 48 KB stages so that two CTAs share an SM (their barrier bubbles overlap)
   const int stage_bytes = 48 * 1024;
