@@ -566,16 +566,19 @@ __global__ void __launch_bounds__(kT2Threads, 1) to_rows2_kernel(const __grid_co
       const int64_t arow = p.row_start + r0;       // table row
       // mask words for this warp's validity items: issued now, consumed after the transpose
       uint32_t mw[4];
-      int nmine = 0;
-      for (int item = vstart; item < vitems && nmine < 4; item += kT2Consumers, ++nmine) {
-        const int g = item / nq, q = item - g * nq;
-        const int c = q * 32 + lane;
-        uint32_t w  = 0;
-        if (c < p.ncols) {
-          const uint32_t* mp = s_msk[c];
-          w                  = mp ? __ldg(mp + ((arow >> 5) + g)) : 0xffffffffu;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // static indices: the loads stay in flight until the words are used
+        const int item = vstart + k * kT2Consumers;
+        mw[k]          = 0;
+        if (item < vitems) {
+          const int g = nq == 1 ? item : item / nq;
+          const int q = nq == 1 ? 0 : item - g * nq;
+          const int c = q * 32 + lane;
+          if (c < p.ncols) {
+            const uint32_t* mp = s_msk[c];
+            mw[k]              = mp ? __ldg(mp + ((arow >> 5) + g)) : 0xffffffffu;
+          }
         }
-        mw[nmine] = w;
       }
       mbar_wait(&full[s], par);
       const uint32_t stage_s = smem_u32(stage0 + static_cast<size_t>(s) * stage_bytes);
@@ -589,10 +592,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) to_rows2_kernel(const __grid_co
       {
         int k = 0;
         for (int item = vstart; item < vitems; item += kT2Consumers, ++k) {
-          const int g = item / nq, q = item - g * nq;
+          const int g = nq == 1 ? item : item / nq;
+          const int q = nq == 1 ? 0 : item - g * nq;
           uint32_t w;
           if (k < 4) {
-            w = mw[k];
+            w = k == 0 ? mw[0] : k == 1 ? mw[1] : k == 2 ? mw[2] : mw[3];
           } else {
             const int c = q * 32 + lane;
             w           = 0;
