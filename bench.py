@@ -105,6 +105,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def box_copy_gbs(torch):
+    """STREAM-style copy on THIS box (same recipe as MEASURED_PEAKS.json: b.copy_(a), read+write bytes, best of 10).
+    Reported for context only -- the roofline denominator stays the driver-measured peak."""
+    a = torch.empty(1 << 30, dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); b.copy_(a); e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2 * a.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del a, b
+    return round(best, 1)
+
+
 def algorithmic_bytes_per_row(types, row_size, hashed=False):
     """read the padded row + write every column element + ncols/8 mask bytes (+ 8 B hash)."""
     return row_size + sum(SIZE[t] for t in types) + len(types) / 8.0 + (8 if hashed else 0)
@@ -178,7 +193,7 @@ def run_ours(args, wl, rank, world):
     n = int(args.rows or wl["rows"])          # weak scaling: every rank converts the full per-GPU workload
     plan = S.Plan.get([S.DType(t) for t in types])
     row_size = plan.layout.fixed_row_size
-    hashed = "hash_keys" in wl
+    hashed = "hash_keys" in wl and os.environ.get("SRJ_BENCH_NOHASH") != "1"
     bpr = algorithmic_bytes_per_row(types, row_size, hashed)
     lib = N.lib()
 

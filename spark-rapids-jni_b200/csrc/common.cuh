@@ -62,7 +62,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-  while (!mbar_try_wait(bar, parity)) {}
+  while (!mbar_try_wait(bar, parity)) {}  // try_wait suspends in hardware up to the hint; no software back-off
+                                          // (a __nanosleep here cost 4% on C2: slower wake-up)
 }
 
 // TMA 1-D bulk load global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP).

@@ -170,6 +170,17 @@ __device__ __forceinline__ int key_size(int32_t t)
   }
 }
 
+// Fused-hash parameters, copied to shared memory once per CTA: the out-of-line hash code must not reach
+// into the kernel parameter struct through a generic pointer (each access becomes a global-path load).
+struct HashSpec {
+  int32_t kind, nkeys, validity_offset, pad;
+  int32_t key_start[16];
+  int32_t key_type[16];
+  int32_t key_col[16];
+  int64_t seed;
+  void* out;
+};
+
 // Shared-memory resident copies of the schedule (filled once per CTA).
 struct SmemTables {
   const int32_t* ent_start;  // [nentries]
@@ -177,12 +188,14 @@ struct SmemTables {
   uint32_t* const* masks;    // [ncols]
   int32_t* nulls;            // [ncols] or NULL
   const int32_t* string_start;  // [nstr]
+  const HashSpec* hash;         // NULL when no hash is fused
 };
 
 // Per-consumer-warp schedule constants, computed once per CTA.
 struct WarpSched {
   int ustart[kNumClasses];  // first unit of each width class for this warp
   int vstart;               // first validity item for this warp
+  int vdq, vdg;             // NCW = vdg * nq + vdq  (validity item stepping without a division)
   int sub, lr;              // lane -> (entry within slot, row within group)
 };
 
@@ -221,7 +234,7 @@ __device__ __forceinline__ void transpose_class(const FromRowsParams& p, const S
       // wide rows: one row group per tile; the lane's row address is hoisted per tile and four units are
       // in flight per warp (table reads, then field reads, then stores) to hide the shared-memory latency
       const int64_t roff = (tv.r0 + ws.lr) * W;
-      constexpr int U    = W >= 16 ? 2 : 4;
+      constexpr int U    = 2;
       for (int u = ws.ustart[k]; u < total; u += U * NCW) {
         Reg<W> v[U];
         uint8_t* dst[U];
@@ -362,51 +375,68 @@ __device__ __forceinline__ void validity_tile(const FromRowsParams& p, const Sme
         }
       }
     }
-    q += NCW;
-    while (q >= nq) {
-      q -= nq;
-      ++g;
+    if (nq == 1) {
+      g += NCW;
+    } else {
+      q += ws.vdq;
+      g += ws.vdg;
+      if (q >= nq) {
+        q -= nq;
+        ++g;
+      }
     }
   }
 }
 
 // ---- fused row hash of the key columns (lane = row), chained across keys with the Spark rules ------------
 template <int NCW, bool VAR, bool SAFE>
-__device__ __noinline__ void hash_tile(const FromRowsParams& p, const TileView& tv, int cw)
+__device__ __noinline__ void hash_tile(const HashSpec* hs, const uint8_t* base, const int32_t* s_off, uint32_t stride,
+                                       int64_t r0, int rows, int cw)
 {
-  const int lane = lane_id();
-  const int ng32 = (tv.rows + 31) >> 5;
-  for (int g = cw; g < ng32; g += NCW) {
+  TileView tv;
+  tv.base   = base;
+  tv.s_off  = s_off;
+  tv.stride = stride;
+  const int lane  = lane_id();
+  const int ng32  = (rows + 31) >> 5;
+  const int kind  = hs->kind;
+  const int nkeys = hs->nkeys;
+  const int voff  = hs->validity_offset;
+  // The hash of a row is one long dependent multiply chain, so a 32-row group is slow on its warp.  The
+  // groups are dealt to the warps starting at a different warp every tile: consumers only meet at the
+  // stage barriers (up to two tiles apart), so the extra group a warp gets on one tile is absorbed.
+  const int rot = static_cast<int>((r0 / tmax(rows, 1)) % NCW);
+  for (int g = (cw + NCW - rot) % NCW; g < ng32; g += NCW) {
     const int row = g * 32 + lane;
-    if (row >= tv.rows) continue;
+    if (row >= rows) continue;
     const uint8_t* rp = row_ptr<VAR>(tv, row);
-    uint64_t hx       = static_cast<uint64_t>(p.hash_seed);
-    uint32_t hm       = static_cast<uint32_t>(p.hash_seed);
+    uint64_t hx       = static_cast<uint64_t>(hs->seed);
+    uint32_t hm       = static_cast<uint32_t>(hs->seed);
     uint32_t hh       = 0;
-    for (int k = 0; k < p.hash_nkeys; ++k) {
-      const int c      = p.key_col[k];
-      const bool valid = (rp[p.validity_offset + (c >> 3)] >> (c & 7)) & 1u;
-      const int32_t ty = p.key_type[k];
+    for (int k = 0; k < nkeys; ++k) {
+      const int c      = hs->key_col[k];
+      const bool valid = (rp[voff + (c >> 3)] >> (c & 7)) & 1u;
+      const int32_t ty = hs->key_type[k];
       const int sz     = key_size(ty);
       uint64_t v = 0, v2 = 0;
       if (valid) {
-        v = load_key<SAFE>(rp + p.key_start[k], sz);
-        if (sz == 16) v2 = load_key<SAFE>(rp + p.key_start[k] + 8, 8);
+        v = load_key<SAFE>(rp + hs->key_start[k], sz);
+        if (sz == 16) v2 = load_key<SAFE>(rp + hs->key_start[k] + 8, 8);
       }
-      if (p.hash_kind == SRJ_HASH_XXHASH64) {
+      if (kind == SRJ_HASH_XXHASH64) {
         if (valid) hx = hash::xx_fixed(ty, v, v2, hx);
-      } else if (p.hash_kind == SRJ_HASH_MURMUR3_32) {
+      } else if (kind == SRJ_HASH_MURMUR3_32) {
         if (valid) hm = hash::mm_fixed(ty, v, v2, hm);
       } else {
         hh = 31u * hh + (valid ? static_cast<uint32_t>(hash::hive_fixed(ty, v)) : 0u);
       }
     }
-    if (p.hash_kind == SRJ_HASH_XXHASH64)
-      reinterpret_cast<uint64_t*>(p.hash_out)[tv.r0 + row] = hx;
-    else if (p.hash_kind == SRJ_HASH_MURMUR3_32)
-      reinterpret_cast<uint32_t*>(p.hash_out)[tv.r0 + row] = hm;
+    if (kind == SRJ_HASH_XXHASH64)
+      reinterpret_cast<uint64_t*>(hs->out)[r0 + row] = hx;
+    else if (kind == SRJ_HASH_MURMUR3_32)
+      reinterpret_cast<uint32_t*>(hs->out)[r0 + row] = hm;
     else
-      reinterpret_cast<uint32_t*>(p.hash_out)[tv.r0 + row] = hh;
+      reinterpret_cast<uint32_t*>(hs->out)[r0 + row] = hh;
   }
 }
 
@@ -416,18 +446,22 @@ __device__ __noinline__ void hash_tile(const FromRowsParams& p, const TileView& 
 // A warp takes a row, lane = STRING column: a row is canonical iff the first pair starts at size_per_row
 // and every pair starts where its left neighbour ends -- one shuffle per 32 columns, no scan.
 template <int NCW, bool SAFE>
-__device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const TileView& tv, int cw,
-                                                  const int32_t* s_string_start)
+__device__ __noinline__ void canonical_check_tile(const uint8_t* base, const int32_t* s_off, int rows, int cw,
+                                                  const int32_t* s_string_start, int nstr, int size_per_row,
+                                                  unsigned long long* status)
 {
+  TileView tv;
+  tv.base  = base;
+  tv.s_off = s_off;
   const int lane = lane_id();
   bool bad       = false;
-  for (int row = cw; row < tv.rows; row += NCW) {
+  for (int row = cw; row < rows; row += NCW) {
     const uint8_t* rp = row_ptr<true>(tv, row);
-    uint32_t expect   = static_cast<uint32_t>(p.size_per_row);
-    for (int s0 = 0; s0 < p.nstr; s0 += 32) {
+    uint32_t expect   = static_cast<uint32_t>(size_per_row);
+    for (int s0 = 0; s0 < nstr; s0 += 32) {
       const int s = s0 + lane;
       uint32_t so = 0, ln = 0;
-      if (s < p.nstr) {
+      if (s < nstr) {
         const uint8_t* pp = rp + s_string_start[s];
         so                = static_cast<uint32_t>(load_key<SAFE>(pp, 4));
         ln                = static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
@@ -435,11 +469,11 @@ __device__ __noinline__ void canonical_check_tile(const FromRowsParams& p, const
       const uint32_t end = so + ln;
       uint32_t prev_end  = __shfl_up_sync(0xffffffffu, end, 1);
       if (lane == 0) prev_end = expect;
-      if (s < p.nstr) bad |= so != prev_end;
-      expect = __shfl_sync(0xffffffffu, end, tmin(31, p.nstr - s0 - 1));
+      if (s < nstr) bad |= so != prev_end;
+      expect = __shfl_sync(0xffffffffu, end, tmin(31, nstr - s0 - 1));
     }
   }
-  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.status, 1ull);
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, 1ull);
 }
 
 template <int NCW, int RPL, bool VAR, bool PRED, bool SAFE, bool ONEG>
@@ -452,9 +486,10 @@ __device__ __forceinline__ void process_tile(const FromRowsParams& p, const Smem
   transpose_class<2, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 1);
   transpose_class<1, NCW, RPL, VAR, PRED, SAFE, ONEG>(p, t, ws, tv, 0);
   validity_tile<NCW, VAR, PRED, SAFE>(p, t, ws, tv);
-  if (p.hash_kind != SRJ_HASH_NONE) hash_tile<NCW, VAR, SAFE>(p, tv, cw);
+  if (t.hash) hash_tile<NCW, VAR, SAFE>(t.hash, tv.base, tv.s_off, tv.stride, tv.r0, tv.rows, cw);
   if constexpr (VAR) {
-    if (p.status && p.nstr > 0) canonical_check_tile<NCW, SAFE>(p, tv, cw, t.string_start);
+    if (p.status && p.nstr > 0)
+      canonical_check_tile<NCW, SAFE>(tv.base, tv.s_off, tv.rows, cw, t.string_start, p.nstr, p.size_per_row, p.status);
   }
 }
 
@@ -485,6 +520,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
   int32_t* s_nulls     = reinterpret_cast<int32_t*>(s_masks + p.ncols);
   int32_t* s_next_off  = s_nulls + ((p.ncols + 3) & ~3);  // producer scratch: offsets of the NEXT tile
   int32_t* s_str_start = s_next_off + ((p.tile_rows + 4) & ~3);
+  HashSpec* s_hash     = reinterpret_cast<HashSpec*>(s_str_start + ((p.nstr + 3) & ~3));  // 16-byte aligned
 
   const int tid = threadIdx.x;
   for (int i = tid; i < p.nentries; i += kThreads) {
@@ -496,6 +532,18 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
     s_nulls[i] = 0;
   }
   for (int i = tid; i < p.nstr; i += kThreads) s_str_start[i] = p.string_start[i];
+  if (tid == 0 && p.hash_kind != SRJ_HASH_NONE) {
+    s_hash->kind            = p.hash_kind;
+    s_hash->nkeys           = p.hash_nkeys;
+    s_hash->validity_offset = p.validity_offset;
+    s_hash->seed            = p.hash_seed;
+    s_hash->out             = p.hash_out;
+    for (int k = 0; k < 16; ++k) {
+      s_hash->key_start[k] = p.key_start[k];
+      s_hash->key_type[k]  = p.key_type[k];
+      s_hash->key_col[k]   = p.key_col[k];
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
@@ -645,11 +693,17 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
   } else {
     // =================================== consumers ===================================
     const int cw = warp_id() - 1;
-    SmemTables t{s_ent_start, s_ent_dst, s_masks, p.null_counts ? s_nulls : nullptr, s_str_start};
+    SmemTables t{s_ent_start, s_ent_dst, s_masks, p.null_counts ? s_nulls : nullptr, s_str_start,
+                 p.hash_kind != SRJ_HASH_NONE ? s_hash : nullptr};
     WarpSched ws;
 #pragma unroll
     for (int k = 0; k < kNumClasses; ++k) ws.ustart[k] = (cw + NCW - (p.cls_ubase[k] % NCW)) % NCW;
     ws.vstart = (cw + NCW - (p.v_ubase % NCW)) % NCW;
+    {
+      const int nq = (p.ncols + 31) >> 5;
+      ws.vdg       = NCW / nq;
+      ws.vdq       = NCW - ws.vdg * nq;
+    }
     ws.sub    = lane / RPL;
     ws.lr     = lane - ws.sub * RPL;
     for (int it = 0;; ++it) {
@@ -701,6 +755,7 @@ size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols, int nstr)
   b += static_cast<size_t>(nentries) * 8 + static_cast<size_t>(ncols) * 8 + static_cast<size_t>((ncols + 3) & ~3) * 4;
   b += static_cast<size_t>((tl.tile_rows + 4) & ~3) * 4;
   b += static_cast<size_t>(nstr + 4) * 4;
+  b += sizeof(HashSpec) + 16;
   return (b + 127) & ~size_t{127};
 }
 
