@@ -271,7 +271,7 @@ def run_ours(args, wl, rank, world):
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "kernel": "srj::from_rows_kernel",
                 "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_row": bpr, "rows_per_launch": n,
-                "peak_source": peak_src}
+                "peak_source": peak_src, "this_box_copy_gbs": box_copy_gbs(torch) if rank == 0 else None}
     tr = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tr):
         try:
@@ -280,6 +280,30 @@ def run_ours(args, wl, rank, world):
             roofline["traffic_source"] = j.get("source")
         except Exception:
             pass
+
+    # ---- multi-GPU config: NCCL all-gather of the per-column chunks over NVLink (north_star) ---------------
+    # Each rank contributes the columns of its first n/world rows; every GPU ends with the n-row table.
+    allgather = None
+    if world > 1:
+        from srj_b200 import sharding
+        per = (n // world) // 32 * 32
+        chunks = [c.data[: per * SIZE[t]] for c, t in zip(outs, types)] + [c.mask[: per // 32] for c in outs]
+        gbytes = sum(ch.numel() * ch.element_size() for ch in chunks)
+        fulls = sharding.gather_fixed_columns(dist, chunks, world)          # warm-up (allocates)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for ch, full in zip(chunks, fulls):
+            dist.all_gather_into_tensor(full.view(-1), ch.contiguous().view(-1))
+        g1.record(stream)
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gms = float(tg[0])
+        allgather = {"rows_per_rank": per, "bytes_sent_per_gpu": gbytes, "bytes_received_per_gpu": gbytes * (world - 1),
+                     "ms": gms, "busbw_gbs": round(gbytes * (world - 1) / (gms * 1e-3) / 1e9, 1),
+                     "collectives": len(chunks), "note": "one all_gather_into_tensor per column and per mask (NCCL)"}
+        del fulls
 
     # ---- e2e: host rows -> host columns through the C-ABI host entry point --------------------------
     e2e = None
@@ -332,6 +356,8 @@ def run_ours(args, wl, rank, world):
                            "sharding": "contiguous row range per GPU, no data-path collective"},
                 "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": args.steps, "clocks": clocks}
+        if allgather:
+            line["allgather"] = allgather
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -501,64 +501,36 @@ __device__ __noinline__ void process_tile_slow(const FromRowsParams& p, const Sm
   process_tile<NCW, RPL, VAR, true, SAFE, ONEG>(p, t, ws, tv, cw);
 }
 
-template <int NCW, int RPL, bool VAR, bool ONEG>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __grid_constant__ FromRowsParams p)
+// The producer warp's loop lives in its own (out-of-line) function so that its long-lived 64-bit state does
+// not compete with the consumers' transpose loop for registers.  Everything it needs travels by value.
+struct ProducerArgs {
+  const uint8_t* rows;
+  const int32_t* row_offsets;
+  int64_t rows_bytes, num_rows, super_rows;
+  int32_t row_stride, tile_rows, stage_bytes, nstages, stage_span, soff_span;
+  uint8_t* payload0;
+  int32_t* soff0;
+  StageHdr* hdr0;
+  uint64_t* full;
+  uint64_t* empty;
+  int32_t* s_next_off;
+};
+
+template <bool VAR>
+__device__ __noinline__ void producer_loop(const ProducerArgs p)
 {
-  constexpr int kThreads = (NCW + 1) * 32;
-  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane       = lane_id();
   const int NS         = p.nstages;
-  const int stage_span = p.stage_bytes + kStageSlack;
-  uint8_t* payload0    = smem;
-  int32_t* soff0       = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(NS) * stage_span);
-  const int soff_span  = (p.tile_rows + 4) & ~3;  // ints per stage (tile_rows + 1, padded)
-  StageHdr* hdr0       = reinterpret_cast<StageHdr*>(soff0 + static_cast<size_t>(NS) * soff_span);
-  uint64_t* full       = reinterpret_cast<uint64_t*>(hdr0 + NS);
-  uint64_t* empty      = full + kMaxStages;
-  int32_t* s_ent_start = reinterpret_cast<int32_t*>(empty + kMaxStages);
-  uint8_t** s_ent_dst  = reinterpret_cast<uint8_t**>(s_ent_start + ((p.nentries + 1) & ~1));
-  uint32_t** s_masks   = reinterpret_cast<uint32_t**>(s_ent_dst + p.nentries);
-  int32_t* s_nulls     = reinterpret_cast<int32_t*>(s_masks + p.ncols);
-  int32_t* s_next_off  = s_nulls + ((p.ncols + 3) & ~3);  // producer scratch: offsets of the NEXT tile
-  int32_t* s_str_start = s_next_off + ((p.tile_rows + 4) & ~3);
-  HashSpec* s_hash     = reinterpret_cast<HashSpec*>(s_str_start + ((p.nstr + 3) & ~3));  // 16-byte aligned
-
-  const int tid = threadIdx.x;
-  for (int i = tid; i < p.nentries; i += kThreads) {
-    s_ent_start[i] = p.entries[i].start;
-    s_ent_dst[i]   = static_cast<uint8_t*>(p.ent_dst[i]);
-  }
-  for (int i = tid; i < p.ncols; i += kThreads) {
-    s_masks[i] = p.masks[i];
-    s_nulls[i] = 0;
-  }
-  for (int i = tid; i < p.nstr; i += kThreads) s_str_start[i] = p.string_start[i];
-  if (tid == 0 && p.hash_kind != SRJ_HASH_NONE) {
-    s_hash->kind            = p.hash_kind;
-    s_hash->nkeys           = p.hash_nkeys;
-    s_hash->validity_offset = p.validity_offset;
-    s_hash->seed            = p.hash_seed;
-    s_hash->out             = p.hash_out;
-    for (int k = 0; k < 16; ++k) {
-      s_hash->key_start[k] = p.key_start[k];
-      s_hash->key_type[k]  = p.key_type[k];
-      s_hash->key_col[k]   = p.key_col[k];
-    }
-  }
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NCW);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int lane = lane_id();
-  // the staged fast path needs 8-byte aligned rows
-  const bool base_ok = (reinterpret_cast<uintptr_t>(p.rows) & 7) == 0;
-
-  if (warp_id() == 0) {
-    // =================================== producer ===================================
+  const int stage_span = p.stage_span;
+  const int soff_span  = p.soff_span;
+  uint8_t* payload0    = p.payload0;
+  int32_t* soff0       = p.soff0;
+  StageHdr* hdr0       = p.hdr0;
+  uint64_t* full       = p.full;
+  uint64_t* empty      = p.empty;
+  int32_t* s_next_off  = p.s_next_off;
+  const bool base_ok   = (reinterpret_cast<uintptr_t>(p.rows) & 7) == 0;
+  {
     // Super-tiles (a few tiles of consecutive rows) are dealt round-robin to the CTAs, so at any moment
     // the whole grid streams through one contiguous window of the row buffer and of every column --
     // the access pattern of a plain copy kernel -- instead of 148 far-apart ranges.
@@ -690,6 +662,86 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
       r += rows;
       next_geometry();  // overlaps with the load just issued
     }
+  }
+}
+
+template <int NCW, int RPL, bool VAR, bool ONEG>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __grid_constant__ FromRowsParams p)
+{
+  constexpr int kThreads = (NCW + 1) * 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int NS         = p.nstages;
+  const int stage_span = p.stage_bytes + kStageSlack;
+  uint8_t* payload0    = smem;
+  int32_t* soff0       = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(NS) * stage_span);
+  const int soff_span  = (p.tile_rows + 4) & ~3;  // ints per stage (tile_rows + 1, padded)
+  StageHdr* hdr0       = reinterpret_cast<StageHdr*>(soff0 + static_cast<size_t>(NS) * soff_span);
+  uint64_t* full       = reinterpret_cast<uint64_t*>(hdr0 + NS);
+  uint64_t* empty      = full + kMaxStages;
+  int32_t* s_ent_start = reinterpret_cast<int32_t*>(empty + kMaxStages);
+  uint8_t** s_ent_dst  = reinterpret_cast<uint8_t**>(s_ent_start + ((p.nentries + 1) & ~1));
+  uint32_t** s_masks   = reinterpret_cast<uint32_t**>(s_ent_dst + p.nentries);
+  int32_t* s_nulls     = reinterpret_cast<int32_t*>(s_masks + p.ncols);
+  int32_t* s_next_off  = s_nulls + ((p.ncols + 3) & ~3);  // producer scratch: offsets of the NEXT tile
+  int32_t* s_str_start = s_next_off + ((p.tile_rows + 4) & ~3);
+  HashSpec* s_hash     = reinterpret_cast<HashSpec*>(s_str_start + ((p.nstr + 3) & ~3));  // 16-byte aligned
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.nentries; i += kThreads) {
+    s_ent_start[i] = p.entries[i].start;
+    s_ent_dst[i]   = static_cast<uint8_t*>(p.ent_dst[i]);
+  }
+  for (int i = tid; i < p.ncols; i += kThreads) {
+    s_masks[i] = p.masks[i];
+    s_nulls[i] = 0;
+  }
+  for (int i = tid; i < p.nstr; i += kThreads) s_str_start[i] = p.string_start[i];
+  if (tid == 0 && p.hash_kind != SRJ_HASH_NONE) {
+    s_hash->kind            = p.hash_kind;
+    s_hash->nkeys           = p.hash_nkeys;
+    s_hash->validity_offset = p.validity_offset;
+    s_hash->seed            = p.hash_seed;
+    s_hash->out             = p.hash_out;
+    for (int k = 0; k < 16; ++k) {
+      s_hash->key_start[k] = p.key_start[k];
+      s_hash->key_type[k]  = p.key_type[k];
+      s_hash->key_col[k]   = p.key_col[k];
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int lane = lane_id();
+  // the staged fast path needs 8-byte aligned rows
+  const bool base_ok = (reinterpret_cast<uintptr_t>(p.rows) & 7) == 0;
+
+  if (warp_id() == 0) {
+    // =================================== producer ===================================
+    ProducerArgs pa;
+    pa.rows        = p.rows;
+    pa.row_offsets = p.row_offsets;
+    pa.rows_bytes  = p.rows_bytes;
+    pa.num_rows    = p.num_rows;
+    pa.super_rows  = p.super_rows;
+    pa.row_stride  = p.row_stride;
+    pa.tile_rows   = p.tile_rows;
+    pa.stage_bytes = p.stage_bytes;
+    pa.nstages     = NS;
+    pa.stage_span  = stage_span;
+    pa.soff_span   = soff_span;
+    pa.payload0    = payload0;
+    pa.soff0       = soff0;
+    pa.hdr0        = hdr0;
+    pa.full        = full;
+    pa.empty       = empty;
+    pa.s_next_off  = s_next_off;
+    producer_loop<VAR>(pa);
   } else {
     // =================================== consumers ===================================
     const int cw = warp_id() - 1;
