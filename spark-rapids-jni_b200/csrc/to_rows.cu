@@ -45,6 +45,7 @@ struct ToRowsParams {
   const int32_t* string_cols;
   const int32_t* string_start;
   int32_t max_str_entries;  // capacity of the per-tile string tables (rows * nstr)
+  int32_t nbuf;             // 1: single stage buffer (more CTAs per SM), 2: double buffered
   int64_t offset_bias;      // added to the values written to out_offsets (tail launches of a batch)
 };
 
@@ -243,12 +244,19 @@ __device__ __forceinline__ void assemble_tile(const ToRowsParams& p, const TrTab
   }
 }
 
-__global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_constant__ ToRowsParams p)
+// SAFE tiles are rare: out of line, so their byte-wise code does not take registers from the fast path
+__device__ __noinline__ void assemble_tile_safe(const ToRowsParams& p, const TrTables& t, uint8_t* base, const int32_t* s_off,
+                                                int64_t stride, int64_t r, int rows, uint8_t* zero_base, int64_t zero_bytes)
+{
+  assemble_tile<true>(p, t, base, s_off, stride, r, rows, zero_base, zero_bytes);
+}
+
+__global__ void __launch_bounds__(kTrThreads, 4) to_rows_kernel(const __grid_constant__ ToRowsParams p)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   const int stage_span = p.stage_bytes + kTrSlack;
   uint8_t* stage0      = smem;
-  int32_t* s_off       = reinterpret_cast<int32_t*>(smem + 2 * static_cast<size_t>(stage_span));
+  int32_t* s_off       = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(p.nbuf) * stage_span);
   const int soff_span  = (p.tile_rows + 4) & ~3;
   TrHdr* hdr           = reinterpret_cast<TrHdr*>(s_off + soff_span);
   int32_t* s_ent_start = reinterpret_cast<int32_t*>(hdr + 1);
@@ -285,12 +293,15 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
 
   int64_t r = c0;
   for (int it = 0; r < c1; ++it) {
-    uint8_t* stage = stage0 + static_cast<size_t>(it & 1) * stage_span;
+    uint8_t* stage = stage0 + static_cast<size_t>(p.nbuf == 2 ? (it & 1) : 0) * stage_span;
     // ---- A: tile geometry (warp 0) -------------------------------------------------------------
-    if (tid == 0) tma_store_wait_read<1>();  // the store that last used this stage has drained
+    if (tid == 0) {  // the store that last used this stage has drained
+      if (p.nbuf == 2) tma_store_wait_read<1>();
+      else tma_store_wait_read<0>();
+    }
     if (warp_id() == 0) {
       int rows        = static_cast<int>(tmin<int64_t>(p.tile_rows, c1 - r));
-      const int64_t lo = row_off(r);
+      const int64_t lo = fixed ? row_off(r) : static_cast<int64_t>(p.out_offsets[r]);
       const int64_t base = lo - static_cast<int64_t>((reinterpret_cast<uintptr_t>(p.out_data) + lo) & 15);
       bool safe       = !base_ok;
       int64_t hi;
@@ -299,12 +310,13 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
         if (hi - lo > p.stage_bytes) safe = true;
         for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(p.offset_bias + lo + static_cast<int64_t>(i) * p.row_stride);
       } else {
+        // row offsets were written by batch_offsets_kernel: one coalesced read gives the whole tile geometry
         int fit = 0;
         for (int i0 = 0; i0 <= rows; i0 += 32) {
           const int i = i0 + lane;
           int64_t o   = 0;
           if (i <= rows) {
-            o        = row_off(r + i);
+            o        = p.out_offsets[r + i];
             s_off[i] = static_cast<int32_t>(o - base);
           }
           const bool ok = (i >= 1) && (i <= rows) && (round_up64(o - base, 16) <= p.stage_bytes + 16);
@@ -312,19 +324,20 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
         }
         if (fit < rows) fit &= ~7;
         if (p.max_str_entries < rows * p.nstr) fit = 0;
+        __syncwarp();
         if (fit == 0 || safe) {
           safe = true;
           rows = tmin(rows, 8);
           while (rows > 1 && rows * p.nstr > p.max_str_entries) --rows;
+          hi = static_cast<int64_t>(s_off[rows]) + base;
           __syncwarp();
-          for (int i = lane; i <= rows; i += 32) s_off[i] = static_cast<int32_t>(row_off(r + i) - lo);
+          for (int i = lane; i <= rows; i += 32) s_off[i] = static_cast<int32_t>(s_off[i] + base - lo);
         } else {
           rows = fit;
+          hi   = static_cast<int64_t>(s_off[rows]) + base;
         }
-        hi = row_off(r + rows);
-        for (int i = lane; i < rows; i += 32) p.out_offsets[r + i] = static_cast<int32_t>(p.offset_bias + row_off(r + i));
       }
-      if (r + rows == p.row_count && lane == 0) p.out_offsets[p.row_count] = static_cast<int32_t>(p.offset_bias + hi);
+      if (fixed && r + rows == p.row_count && lane == 0) p.out_offsets[p.row_count] = static_cast<int32_t>(p.offset_bias + hi);
       if (lane == 0) {
         hdr->r    = r;
         hdr->lo   = lo;
@@ -368,9 +381,9 @@ __global__ void __launch_bounds__(kTrThreads) to_rows_kernel(const __grid_consta
       }
     } else {
       if (fixed)
-        assemble_tile<true>(p, t, p.out_data + h.lo, nullptr, p.row_stride, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
+        assemble_tile_safe(p, t, p.out_data + h.lo, nullptr, p.row_stride, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
       else
-        assemble_tile<true>(p, t, p.out_data + h.lo, s_off, 0, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
+        assemble_tile_safe(p, t, p.out_data + h.lo, s_off, 0, h.r, h.rows, p.out_data + h.lo, h.hi - h.lo);
       __syncthreads();
     }
     r += h.rows;
@@ -728,6 +741,17 @@ __global__ void __launch_bounds__(kRsThreads) u64_scan_apply_kernel(uint64_t* v,
   }
 }
 
+// batch-relative LIST offsets of a batch: offsets[i] = cum[row_start + i - 1] - cum[row_start - 1]
+__global__ void __launch_bounds__(kRsThreads) batch_offsets_kernel(const uint64_t* __restrict__ cum, int64_t row_start,
+                                                                    int64_t row_count, int32_t* __restrict__ offsets)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kRsThreads + threadIdx.x;
+  if (i > row_count) return;
+  const uint64_t c0 = row_start > 0 ? cum[row_start - 1] : 0;
+  const int64_t a   = row_start + i;
+  offsets[i]        = static_cast<int32_t>(a == 0 ? 0 : cum[a - 1] - c0);
+}
+
 // d_cum_sizes: uint64[num_rows] followed by uint64[nchunks] scratch (see srj_to_rows_workspace_bytes)
 int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,
                      uint64_t* d_cum_sizes, cudaStream_t stream)
@@ -744,10 +768,10 @@ int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, 
   return SRJ_OK;
 }
 
-static size_t to_rows_smem_bytes(const srj_plan* plan, int tile_rows, int stage_bytes, int max_str_entries)
+static size_t to_rows_smem_bytes(const srj_plan* plan, int tile_rows, int stage_bytes, int max_str_entries, int nbuf)
 {
   const int nent = static_cast<int>(plan->tr_entries.size());
-  size_t b       = 2 * static_cast<size_t>(stage_bytes + kTrSlack);
+  size_t b       = static_cast<size_t>(nbuf) * static_cast<size_t>(stage_bytes + kTrSlack);
   b += static_cast<size_t>((tile_rows + 4) & ~3) * 4;
   b += sizeof(TrHdr);
   b += static_cast<size_t>(2 * nent + ((2 * nent) & 1)) * 4;
@@ -878,8 +902,16 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
   p.string_start = plan->d_string_start;
   p.offset_bias  = offset_bias;
 
-  // to_rows tiling: two 48 KB stages so that two CTAs share an SM (their barrier bubbles overlap)
-  const int stage_bytes = 48 * 1024;
+  // generic-kernel tiling.  The kernel is bound by the latency of its (synchronous) global reads, so it wants
+  // many resident CTAs rather than deep buffering: variable-width tables use ONE 40 KB stage per CTA
+  // (4-5 CTAs per SM); fixed-width tails keep two 48 KB stages.
+  const bool var        = plan->num_string_columns > 0;
+  static const int env_stage_kb = []() { const char* e = getenv("SRJ_TR_STAGE_KB"); return e ? atoi(e) : 0; }();
+  static const int env_nbuf     = []() { const char* e = getenv("SRJ_TR_NBUF"); return e ? atoi(e) : 0; }();
+  int stage_bytes       = (var ? 44 : 48) * 1024;
+  int nbuf              = var ? 1 : 2;
+  if (env_stage_kb > 0) stage_bytes = env_stage_kb * 1024;
+  if (env_nbuf > 0) nbuf = env_nbuf;
   int tile_rows         = (stage_bytes / plan->fixed_row_size) / 32 * 32;
   if (tile_rows > 512) tile_rows = 512;
   if (tile_rows < 32) tile_rows = (stage_bytes / plan->fixed_row_size) >= 16 ? 16 : 8;
@@ -891,6 +923,10 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
     if (max_str < p.nstr) max_str = p.nstr;  // at least one row (SAFE path walks row by row)
     if (max_str > 8192) return (set_error("to_rows: more than 8192 STRING columns is not supported"), SRJ_EUNSUPPORTED);
   }
+  p.nbuf            = nbuf;
+  if (d_cum_sizes)
+    batch_offsets_kernel<<<static_cast<unsigned>((row_count + 1 + kRsThreads - 1) / kRsThreads), kRsThreads, 0, stream>>>(
+      d_cum_sizes, row_start, row_count, out_offsets);
   p.tile_rows       = tile_rows;
   p.rpl             = tile_rows >= 32 ? 32 : tile_rows;
   p.stage_bytes     = stage_bytes;
@@ -901,11 +937,12 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int64_t T      = tile_rows;
   const int64_t ntiles = (row_count + T - 1) / T;
-  int64_t grid         = std::min<int64_t>(static_cast<int64_t>(nsm) * 2, ntiles);
+  const size_t smem    = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str, nbuf);
+  const int per_sm     = std::max<int>(1, std::min<int>(8, static_cast<int>((228 * 1024) / (smem + 1024))));
+  int64_t grid         = std::min<int64_t>(static_cast<int64_t>(nsm) * per_sm, ntiles);
   const int64_t per    = (ntiles + grid - 1) / grid;
   p.rows_per_cta       = per * T;
   grid                 = (row_count + p.rows_per_cta - 1) / p.rows_per_cta;
-  const size_t smem    = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str);
   SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   to_rows_kernel<<<static_cast<unsigned>(grid), kTrThreads, smem, stream>>>(p);
   SRJ_CUDA_TRY(cudaGetLastError());
