@@ -7,6 +7,7 @@
 // column chunks chained through the output column (the accumulator IS the next chunk's seed, which
 // is exactly the Spark chaining rule), so there is no hidden allocation at any width.
 #include <algorithm>
+#include <type_traits>
 #include "common.cuh"
 #include "hash_device.cuh"
 #include "kernels.hpp"
@@ -20,7 +21,8 @@ struct HashCol {
   const uint8_t* data;
   const uint32_t* mask;
   const int32_t* offsets;
-  int32_t type;
+  int16_t type;
+  int16_t kind;  // 0 = generic dispatch, 1 = plain 4-byte value, 2 = plain 8-byte value (hashed as raw bits)
   int32_t size;  // bytes per element (0 for STRING)
 };
 
@@ -56,60 +58,111 @@ __device__ __forceinline__ void load_fixed(const HashCol& c, int64_t r, uint64_t
   }
 }
 
+// Each thread hashes kRowsPerThread rows (strided by the block size, so every load stays coalesced): the
+// per-column dispatch is paid once per kRowsPerThread rows, the dependent multiply chains of the rows
+// overlap (ILP), and the NEXT column's values and mask words are fetched (unconditionally: fixed-width
+// reads never depend on validity) while the current column is hashed -- the memory-level parallelism a
+// one-row-per-thread loop (thrust::tabulate in the reference) lacks.
+constexpr int kRowsPerThread = 4;
+
+struct Fetched {
+  uint64_t v[kRowsPerThread];
+  uint64_t v2[kRowsPerThread];
+  bool ok[kRowsPerThread];
+};
+
+__device__ __forceinline__ void fetch_column(const HashCol& col, const int64_t (&r)[kRowsPerThread],
+                                             const bool (&live)[kRowsPerThread], Fetched& f)
+{
+  if (col.type == SRJ_STRING) {  // strings are read where they are hashed
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) f.ok[j] = live[j] && row_valid(col.mask, r[j]);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    f.v[j] = f.v2[j] = 0;
+    if (live[j]) {
+      if (col.kind == 1) f.v[j] = __ldg(reinterpret_cast<const uint32_t*>(col.data) + r[j]);
+      else if (col.kind == 2) f.v[j] = __ldg(reinterpret_cast<const unsigned long long*>(col.data) + r[j]);
+      else load_fixed(col, r[j], f.v[j], f.v2[j]);
+    }
+    f.ok[j] = live[j] && row_valid(col.mask, r[j]);
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kHashThreads) row_hash_kernel(const __grid_constant__ HashParams p)
 {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * kHashThreads + threadIdx.x;
-  if (r >= p.n) return;
-  if constexpr (KIND == SRJ_HASH_XXHASH64) {
-    uint64_t h = p.first ? static_cast<uint64_t>(p.seed) : reinterpret_cast<const uint64_t*>(p.out)[r];
-    for (int c = 0; c < p.ncols; ++c) {
-      const HashCol& col = p.cols[c];
-      if (!row_valid(col.mask, r)) continue;  // null keeps the accumulator (xxhash64.cu:352-353)
-      if (col.type == SRJ_STRING) {
-        const int32_t o0 = __ldg(col.offsets + r), o1 = __ldg(col.offsets + r + 1);
-        h = hash::xx_bytes(col.data + o0, o1 - o0, h);
-      } else {
-        uint64_t v, v2;
-        load_fixed(col, r, v, v2);
-        h = hash::xx_fixed(col.type, v, v2, h);
-      }
-    }
-    reinterpret_cast<uint64_t*>(p.out)[r] = h;
-  } else if constexpr (KIND == SRJ_HASH_MURMUR3_32) {
-    uint32_t h = p.first ? static_cast<uint32_t>(p.seed) : reinterpret_cast<const uint32_t*>(p.out)[r];
-    for (int c = 0; c < p.ncols; ++c) {
-      const HashCol& col = p.cols[c];
-      if (!row_valid(col.mask, r)) continue;  // murmur_hash.cu:111-117
-      if (col.type == SRJ_STRING) {
-        const int32_t o0 = __ldg(col.offsets + r), o1 = __ldg(col.offsets + r + 1);
-        h = hash::mm_bytes(col.data + o0, o1 - o0, h);
-      } else {
-        uint64_t v, v2;
-        load_fixed(col, r, v, v2);
-        h = hash::mm_fixed(col.type, v, v2, h);
-      }
-    }
-    reinterpret_cast<uint32_t*>(p.out)[r] = h;
-  } else {
-    uint32_t h = p.first ? 0u : reinterpret_cast<const uint32_t*>(p.out)[r];
-    for (int c = 0; c < p.ncols; ++c) {
-      const HashCol& col = p.cols[c];
-      uint32_t x         = 0;  // null -> 0 (hive_hash.cu:201-203)
-      if (row_valid(col.mask, r)) {
-        if (col.type == SRJ_STRING) {
-          const int32_t o0 = __ldg(col.offsets + r), o1 = __ldg(col.offsets + r + 1);
-          x = static_cast<uint32_t>(hash::hive_bytes(col.data + o0, o1 - o0));
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * (kHashThreads * kRowsPerThread) + threadIdx.x;
+  int64_t r[kRowsPerThread];
+  bool live[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    r[j]    = r0 + static_cast<int64_t>(j) * kHashThreads;
+    live[j] = r[j] < p.n;
+  }
+  if (!live[0]) return;
+  using acc_t = typename std::conditional<KIND == SRJ_HASH_XXHASH64, uint64_t, uint32_t>::type;
+  acc_t h[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    if (p.first || !live[j]) h[j] = KIND == SRJ_HASH_HIVE ? acc_t{0} : static_cast<acc_t>(p.seed);
+    else h[j] = reinterpret_cast<const acc_t*>(p.out)[r[j]];
+  }
+  Fetched cur, nxt;
+  fetch_column(p.cols[0], r, live, cur);
+  for (int c = 0; c < p.ncols; ++c) {
+    const HashCol col = p.cols[c];
+    if (c + 1 < p.ncols) fetch_column(p.cols[c + 1], r, live, nxt);  // in flight while this column is hashed
+    if (col.type == SRJ_STRING) {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if constexpr (KIND == SRJ_HASH_HIVE) {
+          uint32_t x = 0;  // null -> 0 (hive_hash.cu:201-203)
+          if (cur.ok[j]) {
+            const int32_t o0 = __ldg(col.offsets + r[j]), o1 = __ldg(col.offsets + r[j] + 1);
+            x                = static_cast<uint32_t>(hash::hive_bytes(col.data + o0, o1 - o0));
+          }
+          if (live[j]) h[j] = 31u * h[j] + x;
         } else {
-          uint64_t v, v2;
-          load_fixed(col, r, v, v2);
-          x = static_cast<uint32_t>(hash::hive_fixed(col.type, v));
+          if (!cur.ok[j]) continue;  // null keeps the accumulator (xxhash64.cu:352-353, murmur_hash.cu:111-117)
+          const int32_t o0 = __ldg(col.offsets + r[j]), o1 = __ldg(col.offsets + r[j] + 1);
+          if constexpr (KIND == SRJ_HASH_XXHASH64) h[j] = hash::xx_bytes(col.data + o0, o1 - o0, h[j]);
+          else h[j] = hash::mm_bytes(col.data + o0, o1 - o0, h[j]);
         }
       }
-      h = 31u * h + x;  // hive_hash.cu:179-191
+    } else {
+#pragma unroll
+      for (int j = 0; j < kRowsPerThread; ++j) {
+        if constexpr (KIND == SRJ_HASH_XXHASH64) {
+          if (cur.ok[j]) {
+            if (col.kind == 1) h[j] = hash::xx_u32(static_cast<uint32_t>(cur.v[j]), h[j]);
+            else if (col.kind == 2) h[j] = hash::xx_u64(cur.v[j], h[j]);
+            else h[j] = hash::xx_fixed(col.type, cur.v[j], cur.v2[j], h[j]);
+          }
+        } else if constexpr (KIND == SRJ_HASH_MURMUR3_32) {
+          if (cur.ok[j]) {
+            if (col.kind == 1) h[j] = hash::mm_u32(static_cast<uint32_t>(cur.v[j]), h[j]);
+            else if (col.kind == 2) h[j] = hash::mm_u64(cur.v[j], h[j]);
+            else h[j] = hash::mm_fixed(col.type, cur.v[j], cur.v2[j], h[j]);
+          }
+        } else {
+          uint32_t x = 0;
+          if (cur.ok[j]) {
+            if (col.kind == 1) x = static_cast<uint32_t>(cur.v[j]);                      // INT32 / DATE (hive_hash.cu:97-133)
+            else if (col.kind == 2) x = static_cast<uint32_t>((cur.v[j] >> 32) ^ cur.v[j]);  // INT64 (hive_hash.cu:44-47)
+            else x = static_cast<uint32_t>(hash::hive_fixed(col.type, cur.v[j]));
+          }
+          if (live[j]) h[j] = 31u * h[j] + x;  // hive_hash.cu:179-191
+        }
+      }
     }
-    reinterpret_cast<uint32_t*>(p.out)[r] = h;
+    cur = nxt;
   }
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j)
+    if (live[j]) reinterpret_cast<acc_t*>(p.out)[r[j]] = h[j];
 }
 
 static int elem_size(int32_t t)
@@ -139,7 +192,8 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
     if (kind == SRJ_HASH_HIVE && !hash::hive_supported(t)) { set_error("hive_hash: column %d has unsupported type id %d (hive_hash.cu:63-66)", c, t); return SRJ_EUNSUPPORTED; }
     if (cols[c].size != num_rows) { set_error("hash: column %d has %lld rows, expected %lld", c, (long long)cols[c].size, (long long)num_rows); return SRJ_EINVAL; }
   }
-  const unsigned grid = static_cast<unsigned>((num_rows + kHashThreads - 1) / kHashThreads);
+  const int64_t per_block = static_cast<int64_t>(kHashThreads) * kRowsPerThread;
+  const unsigned grid     = static_cast<unsigned>((num_rows + per_block - 1) / per_block);
   for (int c0 = 0; c0 < num_columns; c0 += kHashColsPerLaunch) {
     HashParams p{};
     p.ncols = std::min(kHashColsPerLaunch, num_columns - c0);
@@ -150,7 +204,17 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
     p.out   = out;
     for (int i = 0; i < p.ncols; ++i) {
       const srj_column& c = cols[c0 + i];
-      p.cols[i]           = HashCol{static_cast<const uint8_t*>(c.data), c.null_mask, c.offsets, c.type_id, elem_size(c.type_id)};
+      const int32_t t     = c.type_id;
+      int kind2           = 0;
+      if (kind == SRJ_HASH_HIVE) {
+        if (t == SRJ_INT32 || t == SRJ_TIMESTAMP_DAYS) kind2 = 1;
+        else if (t == SRJ_INT64) kind2 = 2;
+      } else {
+        if (t == SRJ_INT32 || t == SRJ_UINT32 || t == SRJ_TIMESTAMP_DAYS || t == SRJ_DURATION_DAYS) kind2 = 1;
+        else if (elem_size(t) == 8 && t != SRJ_FLOAT64) kind2 = 2;  // ints, timestamps, durations, DECIMAL64: raw 8 bytes
+      }
+      p.cols[i] = HashCol{static_cast<const uint8_t*>(c.data), c.null_mask, c.offsets, static_cast<int16_t>(t),
+                          static_cast<int16_t>(kind2), elem_size(t)};
     }
     if (kind == SRJ_HASH_XXHASH64)
       row_hash_kernel<SRJ_HASH_XXHASH64><<<grid, kHashThreads, 0, stream>>>(p);
