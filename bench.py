@@ -542,6 +542,67 @@ def run_c3(args, wl, rank, world):
                 "traffic": None, "kernel": "whole conversion of a batch (all kernels of the two C-ABI calls)",
                 "algorithmic_bytes_per_row": alg_step / rows_step, "rows_per_launch": nb, "peak_source": peak_src,
                 "ms_per_batch": ms_per_step / nbatches}
+    # ---- e2e through the public API with HOST buffers: pinned host rows -> device -> RowConversion.convertFromRows
+    # (incl. its size read-back) -> pinned host columns; a bounded number of batches, same batches as above ------
+    e2e = None
+    cpu = None
+    if not args.no_e2e and args.direction == "from_rows":
+        kb = min(pool, 4)
+        h_in, h_out = [], []
+        for i in range(kb):
+            rv = batches[i]["rows"]
+            h_in.append((rv.child.data.cpu().pin_memory(), rv.offsets.cpu().pin_memory()))
+            h_out.append([(torch.empty(c.data.numel(), dtype=torch.uint8, pin_memory=True),
+                           torch.empty(words, dtype=torch.int32, pin_memory=True),
+                           torch.empty(nb + 1, dtype=torch.int32, pin_memory=True) if c.dtype.type_id == STRING else None)
+                          for c in batches[i]["cols"]])
+        h2d = sum(a.numel() + 4 * b.numel() for a, b in h_in)
+        d2h = sum(sum(d.numel() + 4 * m.numel() + (4 * o.numel() if o is not None else 0) for d, m, o in hb) for hb in h_out)
+
+        def e2e_batch(i):
+            a, b = h_in[i]
+            dv = S.ColumnVector(S.DType.LIST, nb, None, None, b.cuda(non_blocking=True),
+                                S.ColumnVector(S.DType.INT8, a.numel(), a.cuda(non_blocking=True)))
+            tbl = S.RowConversion.convertFromRows(dv, dts)
+            for c, (d, m, o) in zip(tbl.columns, h_out[i]):
+                d.copy_(c.data, non_blocking=True)
+                m.copy_(c.mask, non_blocking=True)
+                if o is not None:
+                    o.copy_(c.offsets, non_blocking=True)
+        e2e_batch(0)
+        torch.cuda.synchronize()
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(kb):
+            e2e_batch(i)
+        torch.cuda.synchronize()
+        barrier()
+        e2e_s = time.perf_counter() - w0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * kb * nb / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": 1, "ms_per_step": float(te[0]) * 1e3,
+               "api": "srj_b200.RowConversion.convertFromRows on %d batches of %d rows, pinned host rows in / host columns out" % (kb, nb)}
+        if rank == 0:
+            from oracle import oracle as O
+            rvh, offh = h_in[0][0].numpy(), h_in[0][1].numpy()
+            nthreads = os.cpu_count()
+            hc = [O.HCol(t, np.empty(max(c.data.numel(), 1), np.uint8), np.empty(words, np.uint32),
+                         np.empty(nb + 1, np.int32) if t == STRING else None, 0, nb) for t, c in zip(types, batches[0]["cols"])]
+            O.from_rows_mt(rvh, offh, nb, hc, nthreads)
+            reps, tt_ = 0, 0.0
+            while tt_ < 10.0 and reps < 20:
+                t0_ = time.perf_counter()
+                O.from_rows_mt(rvh, offh, nb, hc, nthreads)
+                tt_ += time.perf_counter() - t0_
+                reps += 1
+            cpu = {"value": nb / (tt_ / reps), "unit": "rows/s", "cores": nthreads, "kind": "port",
+                   "sample": "one %d-row batch of the same workload x %d passes, %d OpenMP threads "
+                             "(oracle/srj_oracle.c orc_from_rows_mt: fixed fields + lengths, per-column scan, chars)" % (nb, reps, nthreads),
+                   "ms_per_pass": tt_ / reps * 1e3}
+        del h_in, h_out
+
     if rank == 0:
         print(json.dumps({"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -550,7 +611,7 @@ def run_c3(args, wl, rank, world):
                                      "batch_rows": nb, "batches_per_step": nbatches, "resident_pool_batches": pool,
                                      "avg_row_bytes": batches[0]["rows"].child.size / nb,
                                      "l2": "each batch touches ~%.1f GB >> 126 MB L2; pool of %d distinct batches" % (alg[0] / 1e9, pool)},
-                          "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": None, "e2e": None,
+                          "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                           "gpu_launches": args.steps * nbatches * kernels_per_batch, "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
