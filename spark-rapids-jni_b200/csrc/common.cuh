@@ -66,6 +66,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
                                           // (a __nanosleep here cost 4% on C2: slower wake-up)
 }
 
+// Waiter that backs off between probes: for issue-bound kernels whose consumer warps finish unevenly
+// (a spinning waiter steals issue slots from the warps still working).  Costs wake-up latency.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns)
+{
+  while (!mbar_try_wait(bar, parity)) { __nanosleep(ns); }
+}
+
 // TMA 1-D bulk load global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
     for (int it = 0;; ++it) {
       const int s        = it % NS;
       const uint32_t par = (it / NS) & 1;
-      mbar_wait(&full[s], par);
+      mbar_wait_backoff(&full[s], par, 256);
       const S2Hdr h = hdr0[s];
       if (h.rows == 0) break;
       const uint8_t* pay   = payload0 + static_cast<size_t>(s) * stage_span + kS2Front;
@@ -541,7 +541,24 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + lo));
               asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + lo), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
             } else {
-              for (int b = tmax(lo, a); b < tmin(hi, a + T); ++b) Dal[b] = stg[b];
+              // edge chunk: whole 4-byte words where they lie inside [a, a+T), single bytes at the two ends
+              // (the neighbouring bytes belong to other tiles / warps)
+              const int vlo = tmax(lo, a), vhi = tmin(hi, a + T);
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) {
+                const int wl = lo + 4 * w4, wh = wl + 4;
+                if (wl >= vlo && wh <= vhi) {
+                  uint32_t v;
+                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(stg_s + wl));
+                  asm volatile("st.global.u32 [%0], %1;" ::"l"(Dal + wl), "r"(v));
+                } else if (wh > vlo && wl < vhi) {
+                  for (int b = tmax(wl, vlo); b < tmin(wh, vhi); ++b) {
+                    uint32_t v;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + b));
+                    asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + b), "r"(v));
+                  }
+                }
+              }
             }
           }
           __syncwarp();
