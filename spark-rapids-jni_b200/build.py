@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "srj_b200", "libsrj_b200.so")
-SOURCES = ["capi.cu", "from_rows.cu", "to_rows.cu", "strings.cu", "hash.cu"]
+SOURCES = ["capi.cu", "from_rows.cu", "to_rows.cu", "to_rows_var.cu", "strings.cu", "hash.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", OUT] + objs
+    cmd = [NVCC, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-Xlinker", "--no-undefined", "-o", OUT] + objs
     subprocess.check_call(cmd)
     return OUT
 

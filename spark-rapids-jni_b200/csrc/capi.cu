@@ -439,7 +439,10 @@ int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t nu
                         reinterpret_cast<const int32_t* const*>(d + 2 * nc),
                         reinterpret_cast<const uint8_t* const*>(d + 2 * nc + nstr), batches[b].row_start,
                         batches[b].row_count, nstr ? static_cast<const uint64_t*>(workspace) : nullptr,
-                        batch_offsets[b], batch_data[b], batches[b].num_bytes, stream, tab.data());
+                        batch_offsets[b], batch_data[b], batches[b].num_bytes, stream, tab.data(),
+                        // the scan partials behind the cumulative sizes are dead after plan_batches: 4 bytes of
+                        // them carry the "fast kernel gave up" flag
+                        nstr ? reinterpret_cast<int32_t*>(const_cast<uint64_t*>(static_cast<const uint64_t*>(workspace)) + num_rows) : nullptr);
     if (rc != SRJ_OK) return rc;
   }
   return SRJ_OK;

@@ -32,7 +32,13 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
                    const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
                    int64_t row_count, const uint64_t* d_cum_sizes /* NULL for fixed */, int32_t* out_offsets,
                    uint8_t* out_data, int64_t out_bytes, cudaStream_t stream,
-                   const void* const* h_col_data /* host copy of the column pointers (alignment checks) */);
+                   const void* const* h_col_data /* host copy of the column pointers (alignment checks) */,
+                   int32_t* d_fail_flag /* 4 bytes of device scratch (variable-width tables), may be NULL */);
+// to_rows_var.cu: wide rows with STRING columns.  *launched = 0: table not eligible, nothing was launched.
+int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                       const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
+                       int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes,
+                       int32_t* d_fail_flag, cudaStream_t stream, const void* const* h_col_data, int* launched);
 
 // hash.cu
 int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out,

@@ -47,6 +47,7 @@ struct ToRowsParams {
   int32_t max_str_entries;  // capacity of the per-tile string tables (rows * nstr)
   int32_t nbuf;             // 1: single stage buffer (more CTAs per SM), 2: double buffered
   int64_t offset_bias;      // added to the values written to out_offsets (tail launches of a batch)
+  const int32_t* run_if;    // non-NULL: the launch is a fallback that only runs when *run_if != 0
 };
 
 struct TrHdr {
@@ -254,6 +255,7 @@ __device__ __noinline__ void assemble_tile_safe(const ToRowsParams& p, const TrT
 __global__ void __launch_bounds__(kTrThreads, 4) to_rows_kernel(const __grid_constant__ ToRowsParams p)
 {
   extern __shared__ __align__(128) uint8_t smem[];
+  if (p.run_if != nullptr && *p.run_if == 0) return;  // the fast kernel ahead of this launch handled the batch
   const int stage_span = p.stage_bytes + kTrSlack;
   uint8_t* stage0      = smem;
   int32_t* s_off       = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(p.nbuf) * stage_span);
@@ -784,7 +786,7 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
                                   const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars,
                                   int64_t row_start, int64_t row_count, const uint64_t* d_cum_sizes,
                                   int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes, int64_t offset_bias,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const int32_t* run_if = nullptr, bool write_offsets = true);
 
 // static unit schedule shared by the two directions (see from_rows.cu)
 static void t2_schedule(ToRows2Params& p)
@@ -808,9 +810,20 @@ static void t2_schedule(ToRows2Params& p)
 int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
                    const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
                    int64_t row_count, const uint64_t* d_cum_sizes, int32_t* out_offsets, uint8_t* out_data,
-                   int64_t out_bytes, cudaStream_t stream, const void* const* h_col_data)
+                   int64_t out_bytes, cudaStream_t stream, const void* const* h_col_data, int32_t* d_fail_flag)
 {
   if (row_count == 0) return SRJ_OK;
+  // ---- wide variable-width rows: to_rows3_kernel (to_rows_var.cu), generic kernel behind it as the fallback ----
+  if (plan->num_string_columns > 0 && d_cum_sizes != nullptr) {
+    batch_offsets_kernel<<<static_cast<unsigned>((row_count + 1 + kRsThreads - 1) / kRsThreads), kRsThreads, 0, stream>>>(
+      d_cum_sizes, row_start, row_count, out_offsets);
+    int launched = 0;
+    const int rc = launch_to_rows_var(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets,
+                                      out_data, out_bytes, d_fail_flag, stream, h_col_data, &launched);
+    if (rc != SRJ_OK) return rc;
+    return launch_to_rows_generic(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, d_cum_sizes,
+                                  out_offsets, out_data, out_bytes, 0, stream, launched ? d_fail_flag : nullptr, false);
+  }
   // ---- fast kernel: fixed-width tables, full tiles, 16-byte aligned buffers ------------------------
   const int S = plan->fixed_row_size;
   int D       = 0;
@@ -876,10 +889,11 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
                                   const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars,
                                   int64_t row_start, int64_t row_count, const uint64_t* d_cum_sizes,
                                   int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes, int64_t offset_bias,
-                                  cudaStream_t stream)
+                                  cudaStream_t stream, const int32_t* run_if, bool write_offsets)
 {
   if (row_count == 0) return SRJ_OK;
   ToRowsParams p{};
+  p.run_if          = run_if;
   p.col_data        = d_col_data;
   p.masks           = d_masks;
   p.str_offsets     = d_str_offsets;
@@ -924,7 +938,7 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
     if (max_str > 8192) return (set_error("to_rows: more than 8192 STRING columns is not supported"), SRJ_EUNSUPPORTED);
   }
   p.nbuf            = nbuf;
-  if (d_cum_sizes)
+  if (d_cum_sizes && write_offsets)
     batch_offsets_kernel<<<static_cast<unsigned>((row_count + 1 + kRsThreads - 1) / kRsThreads), kRsThreads, 0, stream>>>(
       d_cum_sizes, row_start, row_count, out_offsets);
   p.tile_rows       = tile_rows;

@@ -1,0 +1,432 @@
+// to_rows_var.cu -- columns -> JCUDF rows for tables with STRING columns and wide rows
+// (reference: copy_to_rows + copy_validity_to_rows + copy_strings_to_rows, RC:574-861).
+//
+// Two CTAs per SM, each owning one row-image buffer of ~105 KB.  A tile = the largest multiple of 8
+// rows (<= 32) whose bytes fit the buffer; lane = row everywhere, so every global read is a
+// contiguous piece of a column (values, offsets, chars of consecutive rows) and every shared-memory
+// write lands in the lane's own row image.  Per tile:
+//   1. geometry from the LIST offsets (already written by batch_offsets_kernel), every warp
+//      redundantly -- no header hand-off;
+//   2. string block sums: warp b sums the lengths of its block of STRING columns per row (these loads
+//      also pull the offsets into L1/L2 and prefetch the chars lines);
+//   3. wait for the previous TMA store to have read the buffer, zero it (padding bytes are 0);
+//   4. a dynamic work queue (shared-memory counter) of independent items writing disjoint bytes:
+//        string block : (offset, len) pairs + chars.  Chars of <= 32 bytes move as aligned 32-bit
+//                       words: up to 10 independent ld.global per lane, funnel-shifted to the
+//                       destination alignment, st.shared.u32 for whole words, st.shared.u8 at the
+//                       two ends; longer strings take a warp-cooperative byte copy;
+//        fixed batch  : 4 columns of one width class: 4 loads in flight, then 4 stores;
+//        validity     : lane = column loads the mask word(s) covering the tile, the 32x32 bit
+//                       butterfly turns them into 4 validity bytes per row;
+//   5. the finished tile -- ONE contiguous byte range of the output -- leaves with a single 1-D TMA
+//      bulk store; the other CTA of the SM assembles while this one drains.
+// A tile that cannot hold 8 rows raises *fail_flag; the generic kernel (to_rows.cu) launched right
+// behind redoes the batch when it sees the flag.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "kernels.hpp"
+#include "plan.hpp"
+
+namespace srj {
+
+constexpr int kT3Warps   = 12;
+constexpr int kT3Threads = kT3Warps * 32;
+constexpr int kT3MaxBlocks = 48;    // string blocks per row
+constexpr int kT3MaxItems  = 1024;
+
+struct ToRows3Params {
+  const void* const* col_data;
+  const uint32_t* const* masks;
+  const int32_t* const* str_offsets;
+  const uint8_t* const* str_chars;
+  int64_t row_start, row_count;
+  const int32_t* out_offsets;  // batch-relative LIST offsets, already written
+  uint8_t* out_data;
+  int32_t ncols, nstr, nfixed;
+  int32_t validity_offset, size_per_row;
+  int32_t stage_bytes;   // multiple of 16
+  int32_t super_rows;    // rows dealt to a CTA at a time (multiple of 8)
+  int32_t sb;            // STRING columns per block
+  int32_t nblocks;
+  int32_t class_begin[kNumClasses + 1];
+  const Entry* entries;
+  const int32_t* string_start;
+  int32_t* fail_flag;
+};
+
+enum : int { kItemString = 5, kItemValidity = 6 };
+__host__ __device__ inline int32_t t3_item(int kind, int begin, int count) { return kind | (begin << 3) | (count << 20); }
+
+__device__ __forceinline__ uint32_t t3_transpose32(uint32_t r, int lane)
+{
+  uint32_t m = 0x0000FFFFu;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, r, j);
+    if ((lane & j) == 0) {
+      const uint32_t t = ((r >> j) ^ other) & m;
+      r ^= t << j;
+    } else {
+      const uint32_t t = ((other >> j) ^ r) & m;
+      r ^= t;
+    }
+    m ^= m << (j >> 1);
+  }
+  return r;
+}
+
+__device__ __forceinline__ void t3_sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void t3_sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void t3_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void t3_sts_v2(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y)); }
+
+// 4 columns of element size W: loads first (independent), then the stores into the lane's row image
+template <int W>
+__device__ __forceinline__ void t3_fixed(const uint8_t* const* s_ent_ptr, const int32_t* s_ent_start, int begin, int count,
+                                         int64_t abs_row, bool act, uint32_t row_s)
+{
+  constexpr int NW = W >= 4 ? W / 4 : 1;
+  uint32_t v[4][NW];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < count && act) {
+      const uint8_t* src = s_ent_ptr[begin + j] + abs_row * W;
+      if constexpr (W == 1) v[j][0] = __ldcs(src);
+      else if constexpr (W == 2) v[j][0] = __ldcs(reinterpret_cast<const uint16_t*>(src));
+      else if constexpr (W == 4) v[j][0] = __ldcs(reinterpret_cast<const uint32_t*>(src));
+      else if constexpr (W == 8) { const uint2 t = __ldcs(reinterpret_cast<const uint2*>(src)); v[j][0] = t.x; v[j][1] = t.y; }
+      else { const uint4 t = __ldcs(reinterpret_cast<const uint4*>(src)); v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < count && act) {
+      const uint32_t a = row_s + static_cast<uint32_t>(s_ent_start[begin + j]);
+      if constexpr (W == 1) t3_sts_u8(a, v[j][0]);
+      else if constexpr (W == 2) t3_sts_u16(a, v[j][0]);
+      else if constexpr (W == 4) t3_sts_u32(a, v[j][0]);
+      else if constexpr (W == 8) t3_sts_v2(a, v[j][0], v[j][1]);
+      else { t3_sts_v2(a, v[j][0], v[j][1]); t3_sts_v2(a + 8, v[j][2], v[j][3]); }  // rows are 8-byte aligned only
+    }
+  }
+}
+
+// chars of one STRING column for the tile: lane's string = L bytes at global S -> shared address D
+__device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, int rows, int lane)
+{
+  const int maxL = __reduce_max_sync(0xffffffffu, L);
+  if (maxL == 0) return;
+  if (maxL <= 32) {
+    const int dsh      = static_cast<int>(D & 3u);
+    const int ssh      = static_cast<int>(S & 3u);
+    const int dlt      = ssh - dsh;  // source byte of dst word 0, relative to the aligned source word
+    const uintptr_t sp = (S - ssh) - (dlt < 0 ? 4 : 0);
+    const int sh       = (dlt < 0 ? 4 + dlt : dlt) * 8;
+    const int end      = dsh + L;          // one past the last dst byte, relative to dst word 0
+    const int kfull0   = dsh ? 1 : 0;
+    const int kfull1   = end >> 2;
+    const uint32_t w0s = D & ~3u;
+    const int Kmax     = (3 + maxL + 3) >> 2;  // warp-uniform bound on the words any lane touches (<= 9)
+    const uintptr_t Se = S + L;
+    uint32_t w[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      w[k]              = 0;
+      const uintptr_t a = sp + 4 * k;
+      // only words that overlap [S, S+L): an aligned word that holds one valid byte is inside the buffer's page
+      if (k <= Kmax && a < Se && a + 4 > S) w[k] = __ldg(reinterpret_cast<const uint32_t*>(a));
+    }
+    uint32_t first = 0, lastw = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (k < Kmax) {
+        const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+        if (k >= kfull0 && k < kfull1) t3_sts_u32(w0s + 4 * k, y);
+        if (k == 0) first = y;
+        if (k == kfull1) lastw = y;
+      }
+    }
+    if (L > 0) {
+      const int hh = dsh ? tmin(end, 4) : 0;  // head bytes [dsh, hh) of word 0
+#pragma unroll
+      for (int t = 1; t < 4; ++t)
+        if (t >= dsh && t < hh) t3_sts_u8(w0s + t, first >> (8 * t));
+      const int tt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;  // tail bytes [0, tt) of word kfull1
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+        if (t < tt) t3_sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
+    }
+  } else {
+    // long strings: the warp copies one row's string at a time, lane = byte
+    for (int i = 0; i < rows; ++i) {
+      const uintptr_t Si = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(S), i);
+      const uint32_t Di  = __shfl_sync(0xffffffffu, D, i);
+      const int Li       = __shfl_sync(0xffffffffu, L, i);
+      for (int j = lane; j < Li; j += 32) t3_sts_u8(Di + j, __ldg(reinterpret_cast<const uint8_t*>(Si + j)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_constant__ ToRows3Params p)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* image = smem;  // stage_bytes + 32
+  uint8_t* q     = smem + p.stage_bytes + 32;
+  const uint8_t** s_ent_ptr = reinterpret_cast<const uint8_t**>(q);  q += sizeof(void*) * p.nfixed;
+  const uint32_t** s_mask   = reinterpret_cast<const uint32_t**>(q); q += sizeof(void*) * p.ncols;
+  const int32_t** s_soff    = reinterpret_cast<const int32_t**>(q);  q += sizeof(void*) * p.nstr;
+  const uint8_t** s_chars   = reinterpret_cast<const uint8_t**>(q);  q += sizeof(void*) * p.nstr;
+  int32_t* s_ent_start      = reinterpret_cast<int32_t*>(q);         q += 4 * p.nfixed;
+  int32_t* s_sstart         = reinterpret_cast<int32_t*>(q);         q += 4 * p.nstr;
+  int32_t* s_bsum           = reinterpret_cast<int32_t*>(q);         q += 4 * 32 * p.nblocks;
+  int32_t* s_items          = reinterpret_cast<int32_t*>(q);
+  __shared__ int s_next, s_nitems;
+
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  const int w    = warp_id();
+  for (int i = tid; i < p.nfixed; i += kT3Threads) {
+    const Entry e  = p.entries[i];
+    s_ent_ptr[i]   = static_cast<const uint8_t*>(p.col_data[e.column]);
+    s_ent_start[i] = e.start;
+  }
+  for (int i = tid; i < p.ncols; i += kT3Threads) s_mask[i] = p.masks[i];
+  for (int i = tid; i < p.nstr; i += kT3Threads) {
+    s_soff[i]   = p.str_offsets[i];
+    s_chars[i]  = p.str_chars[i];
+    s_sstart[i] = p.string_start[i];
+  }
+  if (tid == 0) {
+    int n = 0;
+    for (int b = 0; b < p.nblocks; ++b) s_items[n++] = t3_item(kItemString, b, 0);
+    for (int k = kNumClasses - 1; k >= 0; --k)
+      for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += 4) s_items[n++] = t3_item(k, e, tmin(4, p.class_begin[k + 1] - e));
+    for (int g = 0; g * 32 < p.ncols; ++g) s_items[n++] = t3_item(kItemValidity, g, 0);
+    s_nitems = n;
+    s_next   = 0;
+  }
+  __syncthreads();
+  const int nitems       = s_nitems;
+  const uint32_t image_s = smem_u32(image);
+  const uintptr_t out_g  = reinterpret_cast<uintptr_t>(p.out_data);
+  const int nvb          = (p.ncols + 7) >> 3;
+
+  const int64_t nsuper = (p.row_count + p.super_rows - 1) / p.super_rows;
+  for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+    int64_t r          = st * p.super_rows;
+    const int64_t rend = tmin<int64_t>(p.row_count, r + p.super_rows);
+    while (r < rend) {
+      const int rem      = static_cast<int>(tmin<int64_t>(32, rend - r));
+      const int64_t abs0 = p.row_start + r;
+      // ---- 1. geometry -------------------------------------------------------------------------------
+      int64_t oa = 0, ob = 0;
+      if (lane < rem) {
+        oa = p.out_offsets[r + lane];
+        ob = p.out_offsets[r + lane + 1];
+      }
+      // ---- 2. string block sums (+ prefetch of the chars) -----------------------------------------------
+      for (int b = w; b < p.nblocks; b += kT3Warps) {
+        const int s0 = b * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
+        int32_t sum = 0;
+        for (int sA = s0; sA < s1; sA += 4) {
+          int32_t o0[4], o1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o0[j] = o1[j] = 0;
+            if (sA + j < s1 && lane < rem) {
+              const int32_t* so = s_soff[sA + j] + abs0 + lane;
+              o0[j]             = __ldg(so);
+              o1[j]             = __ldg(so + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (sA + j < s1 && lane < rem) {
+              sum += o1[j] - o0[j];
+              if (o1[j] > o0[j]) asm volatile("prefetch.global.L2 [%0];" ::"l"(s_chars[sA + j] + o0[j]));
+            }
+          }
+        }
+        s_bsum[b * 32 + lane] = sum;
+      }
+      const int64_t lo      = __shfl_sync(0xffffffffu, oa, 0);
+      const int skew        = static_cast<int>((out_g + lo) & 15);
+      const int my_off      = static_cast<int>(oa - lo) + skew;
+      const int my_end      = static_cast<int>(ob - lo) + skew;
+      const bool fits       = lane < rem && my_end <= p.stage_bytes;
+      int rows              = __popc(__ballot_sync(0xffffffffu, fits));
+      if (rows < rem) rows &= ~7;
+      if (rows == 0) {  // cannot hold 8 rows: the generic kernel redoes the batch
+        if (tid == 0) { atomicExch(p.fail_flag, 1); tma_store_wait_all<0>(); }
+        return;
+      }
+      const int hi_rel = __shfl_sync(0xffffffffu, my_end, rows - 1);
+      const bool act   = lane < rows;
+      const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
+      // ---- 3. buffer free -> zero fill -----------------------------------------------------------------
+      if (tid == 0) { tma_store_wait_read<0>(); s_next = 0; }
+      __syncthreads();
+      {
+        const int n = (hi_rel + 15) >> 4;
+        for (int i = tid; i < n; i += kT3Threads)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(image_s + 16u * i), "r"(0u));
+      }
+      __syncthreads();
+      // ---- 4. work queue ---------------------------------------------------------------------------------
+      for (;;) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&s_next, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= nitems) break;
+        const int32_t item = s_items[it];
+        const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
+        if (kind == kItemString) {
+          const int s0 = begin * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
+          int32_t run = p.size_per_row;  // RC:838
+          for (int b = 0; b < begin; ++b) run += s_bsum[b * 32 + lane];
+          for (int s = s0; s < s1; ++s) {
+            int32_t o0 = 0, L = 0;
+            if (act) {
+              const int32_t* so = s_soff[s] + abs0 + lane;
+              o0                = __ldg(so);
+              L                 = tmax(__ldg(so + 1) - o0, 0);
+              const uint32_t pa = row_s + static_cast<uint32_t>(s_sstart[s]);
+              t3_sts_u32(pa, static_cast<uint32_t>(run));  // RC:848
+              t3_sts_u32(pa + 4, static_cast<uint32_t>(L));  // RC:849
+            }
+            t3_copy_chars(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0), row_s + static_cast<uint32_t>(run), L, rows, lane);
+            run += L;
+          }
+        } else if (kind == kItemValidity) {
+          const int c      = begin * 32 + lane;
+          uint32_t bits    = 0;
+          if (c < p.ncols) {
+            const uint32_t* m = s_mask[c];
+            if (m == nullptr) {
+              bits = 0xffffffffu;
+            } else {
+              const int64_t wi  = abs0 >> 5;
+              const int shb     = static_cast<int>(abs0 & 31);
+              const uint32_t w0 = __ldg(m + wi);
+              uint32_t w1       = 0;
+              if (shb != 0 && ((abs0 + rows - 1) >> 5) > wi) w1 = __ldg(m + wi + 1);
+              bits = __funnelshift_r(w0, w1, shb);
+            }
+          }
+          const uint32_t t = t3_transpose32(bits, lane);  // lane = row: bit j = column begin*32 + j
+          if (act) {
+            const uint32_t a = row_s + static_cast<uint32_t>(p.validity_offset + begin * 4);
+            const int nb     = tmin(4, nvb - begin * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nb) t3_sts_u8(a + k, t >> (8 * k));
+          }
+        } else {
+          const int64_t ar = abs0 + lane;
+          switch (kind) {
+            case 4: t3_fixed<16>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 3: t3_fixed<8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 2: t3_fixed<4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 1: t3_fixed<2>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            default: t3_fixed<1>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+          }
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
+      __syncthreads();
+      // ---- 5. write out ------------------------------------------------------------------------------------
+      if (tid == 0) {
+        const uintptr_t g_lo = out_g + lo;
+        const uintptr_t g_hi = g_lo + (hi_rel - skew);
+        const uintptr_t fl   = g_lo - skew;  // global address of image byte 0
+        const uintptr_t t_lo = (g_lo + 15) & ~uintptr_t{15};
+        const uintptr_t t_hi = g_hi & ~uintptr_t{15};
+        uintptr_t h_end      = tmin(t_lo, g_hi);
+        uintptr_t t_beg      = tmax(t_hi, h_end);
+        if (t_hi > t_lo) {
+          tma_store_1d(reinterpret_cast<void*>(t_lo), image + (t_lo - fl), static_cast<uint32_t>(t_hi - t_lo));
+        } else {
+          h_end = g_hi;
+          t_beg = g_hi;
+        }
+        tma_store_commit();
+        for (uintptr_t a = g_lo; a < h_end; a += 8)
+          *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(image + (a - fl));
+        for (uintptr_t a = t_beg; a < g_hi; a += 8)
+          *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(image + (a - fl));
+      }
+      r += rows;
+    }
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+}
+
+// Returns SRJ_OK and sets *launched when the kernel was launched (the caller then launches the generic kernel
+// guarded by d_fail_flag); *launched = 0 means the table is not eligible.
+int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                       const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
+                       int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes,
+                       int32_t* d_fail_flag, cudaStream_t stream, const void* const* h_col_data, int* launched)
+{
+  *launched = 0;
+  const int nstr = plan->num_string_columns;
+  if (nstr == 0 || row_count == 0 || !d_fail_flag || !h_col_data) return SRJ_OK;
+  if (getenv("SRJ_TR_GENERIC")) return SRJ_OK;
+  const bool force = getenv("SRJ_TR_VAR_FORCE") != nullptr;
+  if ((reinterpret_cast<uintptr_t>(out_data) & 7) != 0) return SRJ_OK;
+  for (const Entry& e : plan->tr_entries)
+    if (reinterpret_cast<uintptr_t>(h_col_data[e.column]) & static_cast<uintptr_t>(plan->col_size[e.column] - 1)) return SRJ_OK;
+
+  ToRows3Params p{};
+  p.nfixed  = static_cast<int32_t>(plan->tr_entries.size());
+  p.ncols   = plan->num_columns;
+  p.nstr    = nstr;
+  p.sb      = std::max(4, (nstr + kT3MaxBlocks - 1) / kT3MaxBlocks);
+  p.nblocks = (nstr + p.sb - 1) / p.sb;
+  int nitems = p.nblocks + (p.ncols + 31) / 32;
+  for (int k = 0; k < kNumClasses; ++k) nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + 3) / 4;
+  if (nitems > kT3MaxItems) return SRJ_OK;
+  const size_t tables = sizeof(void*) * (static_cast<size_t>(p.nfixed) + p.ncols + 2 * static_cast<size_t>(nstr)) +
+                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + nitems) + 32 + 128;
+  const int64_t budget = 232448 / 2 - 1024 - 64;  // two CTAs per SM
+  int64_t stage        = (budget - static_cast<int64_t>(tables)) / 16 * 16;
+  if (stage < 32 * 1024 || stage < 8ll * (plan->fixed_row_size + 64)) return SRJ_OK;
+  const int64_t avg_row = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
+  int fit               = static_cast<int>(std::min<int64_t>(32, stage / avg_row / 8 * 8));
+  if (!force && (fit < 8 || stage / avg_row >= 64)) return SRJ_OK;  // narrow rows: multi-group tiles of the generic kernel
+  if (fit < 8) fit = 8;
+
+  p.col_data        = d_col_data;
+  p.masks           = d_masks;
+  p.str_offsets     = d_str_offsets;
+  p.str_chars       = d_str_chars;
+  p.row_start       = row_start;
+  p.row_count       = row_count;
+  p.out_offsets     = out_offsets;
+  p.out_data        = out_data;
+  p.validity_offset = plan->validity_offset;
+  p.size_per_row    = plan->size_per_row;
+  p.stage_bytes     = static_cast<int32_t>(stage);
+  p.super_rows      = fit * 8;
+  for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->tr_class_begin[k];
+  p.entries      = plan->d_tr_entries;
+  p.string_start = plan->d_string_start;
+  p.fail_flag    = d_fail_flag;
+
+  int dev = 0, nsm = 0;
+  SRJ_CUDA_TRY(cudaGetDevice(&dev));
+  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t nsuper = (row_count + p.super_rows - 1) / p.super_rows;
+  const int64_t grid   = std::min<int64_t>(2ll * nsm, nsuper);
+  const size_t smem    = static_cast<size_t>(stage) + 32 + tables;
+  SRJ_CUDA_TRY(cudaMemsetAsync(d_fail_flag, 0, sizeof(int32_t), stream));
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 / 2 - 1024));
+  to_rows3_kernel<<<static_cast<unsigned>(grid), kT3Threads, smem, stream>>>(p);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  *launched = 1;
+  return SRJ_OK;
+}
+
+}  // namespace srj
