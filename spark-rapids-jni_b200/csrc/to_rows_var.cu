@@ -31,8 +31,6 @@
 
 namespace srj {
 
-constexpr int kT3Warps   = 12;
-constexpr int kT3Threads = kT3Warps * 32;
 constexpr int kT3MaxBlocks = 48;    // string blocks per row
 constexpr int kT3MaxItems  = 1024;
 
@@ -50,6 +48,8 @@ struct ToRows3Params {
   int32_t super_rows;    // rows dealt to a CTA at a time (multiple of 8)
   int32_t sb;            // STRING columns per block
   int32_t nblocks;
+  int32_t pf;            // L2 prefetch of column pieces: 0 off, 1 next tile, 2 this tile (at the top)
+  int32_t nitems;        // work items per tile (string blocks + fixed batches + validity groups)
   int32_t class_begin[kNumClasses + 1];
   const Entry* entries;
   const int32_t* string_start;
@@ -119,44 +119,52 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
   const int maxL = __reduce_max_sync(0xffffffffu, L);
   if (maxL == 0) return;
   if (maxL <= 32) {
+    // dst words k = 0.. start at the aligned address D - dsh; dst word k = source bytes [4k - dsh, 4k - dsh + 4) of
+    // the string = funnel(w[k], w[k+1]) of the aligned source words w[k] at sp + 4k, sp = S - pre.
     const int dsh      = static_cast<int>(D & 3u);
     const int ssh      = static_cast<int>(S & 3u);
-    const int dlt      = ssh - dsh;  // source byte of dst word 0, relative to the aligned source word
-    const uintptr_t sp = (S - ssh) - (dlt < 0 ? 4 : 0);
-    const int sh       = (dlt < 0 ? 4 + dlt : dlt) * 8;
-    const int end      = dsh + L;          // one past the last dst byte, relative to dst word 0
-    const int kfull0   = dsh ? 1 : 0;
-    const int kfull1   = end >> 2;
-    const uint32_t w0s = D & ~3u;
-    const int Kmax     = (3 + maxL + 3) >> 2;  // warp-uniform bound on the words any lane touches (<= 9)
-    const uintptr_t Se = S + L;
+    const int dlt      = ssh - dsh;
+    const int pre      = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
+    const uintptr_t sp = S - pre;
+    const int sh       = (dlt & 3) * 8;
+    const int end      = dsh + L;            // one past the last dst byte, relative to dst word 0
+    const int kfull1   = end >> 2;           // full dst words: [dsh ? 1 : 0, kfull1)
+    const uint32_t w0s = D - dsh;
+    const int lim      = L > 0 ? L + pre : 0;  // source word k overlaps the string iff 4k < lim (and k > 0 or pre < 4)
+    const int Kmax     = (maxL + 6) >> 2;    // warp-uniform bound on kfull1 (<= 9)
+    // edge bytes straight from the source (independent of the word pipeline): the first nh bytes when the
+    // destination starts inside a word, the last nt bytes when it ends inside one
+    const int nh = dsh ? tmin(L, 4 - dsh) : 0;
+    const int nt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
+    const uint8_t* Sb = reinterpret_cast<const uint8_t*>(S);
+    const uint8_t* St = Sb + (L - nt);
+    uint32_t hb[3], tb[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      hb[t] = tb[t] = 0;
+      if (t < nh) hb[t] = __ldg(Sb + t);
+      if (t < nt) tb[t] = __ldg(St + t);
+    }
     uint32_t w[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-      w[k]              = 0;
-      const uintptr_t a = sp + 4 * k;
+      w[k] = 0;
       // only words that overlap [S, S+L): an aligned word that holds one valid byte is inside the buffer's page
-      if (k <= Kmax && a < Se && a + 4 > S) w[k] = __ldg(reinterpret_cast<const uint32_t*>(a));
+      const bool need = k == 0 ? (lim > 0 && pre < 4) : (4 * k < lim);
+      if (need) w[k] = __ldg(reinterpret_cast<const uint32_t*>(sp + 4 * k));
     }
-    uint32_t first = 0, lastw = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      if (t < nh) t3_sts_u8(D + t, hb[t]);
+      if (t < nt) t3_sts_u8(D + (L - nt) + t, tb[t]);
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       if (k < Kmax) {
         const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
-        if (k >= kfull0 && k < kfull1) t3_sts_u32(w0s + 4 * k, y);
-        if (k == 0) first = y;
-        if (k == kfull1) lastw = y;
+        const bool full  = k == 0 ? (dsh == 0 && kfull1 > 0) : (k < kfull1);
+        if (full) t3_sts_u32(w0s + 4 * k, y);
       }
-    }
-    if (L > 0) {
-      const int hh = dsh ? tmin(end, 4) : 0;  // head bytes [dsh, hh) of word 0
-#pragma unroll
-      for (int t = 1; t < 4; ++t)
-        if (t >= dsh && t < hh) t3_sts_u8(w0s + t, first >> (8 * t));
-      const int tt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;  // tail bytes [0, tt) of word kfull1
-#pragma unroll
-      for (int t = 0; t < 3; ++t)
-        if (t < tt) t3_sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
     }
   } else {
     // long strings: the warp copies one row's string at a time, lane = byte
@@ -169,8 +177,10 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
   }
 }
 
-__global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_constant__ ToRows3Params p)
+template <int kT3Warps, int kCtasPerSm>
+__global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(const __grid_constant__ ToRows3Params p)
 {
+  constexpr int kT3Threads = kT3Warps * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* image = smem;  // stage_bytes + 32
   uint8_t* q     = smem + p.stage_bytes + 32;
@@ -181,7 +191,8 @@ __global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_co
   int32_t* s_ent_start      = reinterpret_cast<int32_t*>(q);         q += 4 * p.nfixed;
   int32_t* s_sstart         = reinterpret_cast<int32_t*>(q);         q += 4 * p.nstr;
   int32_t* s_bsum           = reinterpret_cast<int32_t*>(q);         q += 4 * 32 * p.nblocks;
-  int32_t* s_items          = reinterpret_cast<int32_t*>(q);
+  int32_t* s_items          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;
+  uint8_t* s_ent_w          = q;  // element size of each fixed-width entry
   __shared__ int s_next, s_nitems;
 
   const int tid  = threadIdx.x;
@@ -191,6 +202,9 @@ __global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_co
     const Entry e  = p.entries[i];
     s_ent_ptr[i]   = static_cast<const uint8_t*>(p.col_data[e.column]);
     s_ent_start[i] = e.start;
+    int k = 0;
+    while (i >= p.class_begin[k + 1]) ++k;
+    s_ent_w[i] = static_cast<uint8_t>(1 << k);
   }
   for (int i = tid; i < p.ncols; i += kT3Threads) s_mask[i] = p.masks[i];
   for (int i = tid; i < p.nstr; i += kT3Threads) {
@@ -263,15 +277,47 @@ __global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_co
         return;
       }
       const int hi_rel = __shfl_sync(0xffffffffu, my_end, rows - 1);
+      // ---- L2 prefetch of column pieces (values, offsets, mask words): fire and forget ----------------------------
+      if (p.pf) {
+        int64_t nr = r;
+        if (p.pf == 1) {
+          nr = r + rows;
+          if (nr >= rend) nr = (st + gridDim.x) * p.super_rows;
+        }
+        if (nr + 64 <= p.row_count) {  // stay inside every buffer
+          const int64_t an = p.row_start + nr;
+          for (int i = tid; i < p.nfixed; i += kT3Threads) {
+            const int W      = s_ent_w[i];
+            const uint8_t* a = s_ent_ptr[i] + an * W;
+            for (int off = 0; off <= 32 * W; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
+          }
+          if (p.pf == 1)
+            for (int i = tid; i < p.nstr; i += kT3Threads) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(s_soff[i] + an));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(s_soff[i] + an + 32));
+            }
+          for (int i = tid; i < p.ncols; i += kT3Threads)
+            if (s_mask[i]) asm volatile("prefetch.global.L2 [%0];" ::"l"(s_mask[i] + (an >> 5)));
+        }
+      }
       const bool act   = lane < rows;
       const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
       // ---- 3. buffer free -> zero fill -----------------------------------------------------------------
       if (tid == 0) { tma_store_wait_read<0>(); s_next = 0; }
       __syncthreads();
+      if (w == kT3Warps - 1) {  // block sums -> exclusive prefix per row (published by the barrier below)
+        int32_t acc = p.size_per_row;  // RC:838: chars start right behind the fixed section
+        for (int b = 0; b < p.nblocks; ++b) {
+          const int32_t v       = s_bsum[b * 32 + lane];
+          s_bsum[b * 32 + lane] = acc;
+          acc += v;
+        }
+      }
       {
-        const int n = (hi_rel + 15) >> 4;
-        for (int i = tid; i < n; i += kT3Threads)
-          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(image_s + 16u * i), "r"(0u));
+        const uint32_t ze = image_s + static_cast<uint32_t>(hi_rel);
+#pragma unroll 4
+        for (uint32_t a = image_s + 16u * tid; a < ze; a += 16u * kT3Threads)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u));
       }
       __syncthreads();
       // ---- 4. work queue ---------------------------------------------------------------------------------
@@ -284,8 +330,7 @@ __global__ void __launch_bounds__(kT3Threads, 2) to_rows3_kernel(const __grid_co
         const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
         if (kind == kItemString) {
           const int s0 = begin * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
-          int32_t run = p.size_per_row;  // RC:838
-          for (int b = 0; b < begin; ++b) run += s_bsum[b * 32 + lane];
+          int32_t run = s_bsum[begin * 32 + lane];
           for (int s = s0; s < s1; ++s) {
             int32_t o0 = 0, L = 0;
             if (act) {
@@ -383,14 +428,21 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.nfixed  = static_cast<int32_t>(plan->tr_entries.size());
   p.ncols   = plan->num_columns;
   p.nstr    = nstr;
-  p.sb      = std::max(4, (nstr + kT3MaxBlocks - 1) / kT3MaxBlocks);
+  const int env_sb = getenv("SRJ_T3_SB") ? atoi(getenv("SRJ_T3_SB")) : 0;  // tuning knobs (development)
+  const int env_su = getenv("SRJ_T3_SUPER") ? atoi(getenv("SRJ_T3_SUPER")) : 0;
+  const int env_w  = getenv("SRJ_T3_WARPS") ? atoi(getenv("SRJ_T3_WARPS")) : 0;
+  const int nwarps = env_w == 12 ? 12 : 24;
+  const int cps    = nwarps == 24 ? 1 : 2;  // CTAs per SM
+  p.sb      = std::max(env_sb > 0 ? env_sb : (cps == 1 ? 4 : 8), (nstr + kT3MaxBlocks - 1) / kT3MaxBlocks);
   p.nblocks = (nstr + p.sb - 1) / p.sb;
   int nitems = p.nblocks + (p.ncols + 31) / 32;
   for (int k = 0; k < kNumClasses; ++k) nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + 3) / 4;
   if (nitems > kT3MaxItems) return SRJ_OK;
+  p.nitems = nitems;
   const size_t tables = sizeof(void*) * (static_cast<size_t>(p.nfixed) + p.ncols + 2 * static_cast<size_t>(nstr)) +
-                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + nitems) + 32 + 128;
-  const int64_t budget = 232448 / 2 - 1024 - 64;  // two CTAs per SM
+                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + nitems) +
+                        ((static_cast<size_t>(p.nfixed) + 15) & ~size_t{15}) + 32 + 128;
+  const int64_t budget = 232448 / cps - 1024 - 64;
   int64_t stage        = (budget - static_cast<int64_t>(tables)) / 16 * 16;
   if (stage < 32 * 1024 || stage < 8ll * (plan->fixed_row_size + 64)) return SRJ_OK;
   const int64_t avg_row = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
@@ -409,21 +461,27 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.validity_offset = plan->validity_offset;
   p.size_per_row    = plan->size_per_row;
   p.stage_bytes     = static_cast<int32_t>(stage);
-  p.super_rows      = fit * 8;
+  p.super_rows      = fit * (env_su > 0 ? env_su : (cps == 1 ? 2 : 8));
   for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->tr_class_begin[k];
   p.entries      = plan->d_tr_entries;
   p.string_start = plan->d_string_start;
   p.fail_flag    = d_fail_flag;
+  p.pf           = getenv("SRJ_T3_PF") ? atoi(getenv("SRJ_T3_PF")) : 0;
 
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int64_t nsuper = (row_count + p.super_rows - 1) / p.super_rows;
-  const int64_t grid   = std::min<int64_t>(2ll * nsm, nsuper);
+  const int64_t grid   = std::min<int64_t>(static_cast<int64_t>(cps) * nsm, nsuper);
   const size_t smem    = static_cast<size_t>(stage) + 32 + tables;
   SRJ_CUDA_TRY(cudaMemsetAsync(d_fail_flag, 0, sizeof(int32_t), stream));
-  SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 / 2 - 1024));
-  to_rows3_kernel<<<static_cast<unsigned>(grid), kT3Threads, smem, stream>>>(p);
+  if (cps == 1) {
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows3_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    to_rows3_kernel<24, 1><<<static_cast<unsigned>(grid), 24 * 32, smem, stream>>>(p);
+  } else {
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows3_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 / 2 - 1024));
+    to_rows3_kernel<12, 2><<<static_cast<unsigned>(grid), 12 * 32, smem, stream>>>(p);
+  }
   SRJ_CUDA_TRY(cudaGetLastError());
   *launched = 1;
   return SRJ_OK;
