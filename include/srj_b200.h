@@ -130,6 +130,9 @@ SRJ_API int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* col
  * Step 2 (async): fill each batch's LIST offsets child (int32[row_count + 1]) and INT8 data child
  * (num_bytes).  Fuses copy_to_rows + copy_validity_to_rows + copy_strings_to_rows
  * (RC:574-688, 706-798, 816-861).  Padding bytes are written as zeros (undefined in the reference).
+ * `workspace` is the buffer step 1 filled: its cumulative row sizes are only read, the scratch
+ * words behind them (scan partials, dead after step 1) carry a 4-byte device flag of the fast
+ * variable-width kernel -- so two step-2 calls must not share one workspace concurrently.
  */
 SRJ_API int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t num_rows,
                                 const void* workspace, const srj_row_batch* batches,

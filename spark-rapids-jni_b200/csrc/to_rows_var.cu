@@ -33,6 +33,16 @@ namespace srj {
 
 constexpr int kT3MaxBlocks = 48;    // string blocks per row
 constexpr int kT3MaxItems  = 1024;
+#ifndef T3_STATIC
+#define T3_STATIC 1
+#endif
+#ifndef T3_U8
+#define T3_U8 0
+#endif
+#ifndef T3_HOIST
+#define T3_HOIST 1
+#endif
+constexpr int kHoist       = T3_HOIST;     // STRING columns whose offsets are fetched together
 
 struct ToRows3Params {
   const void* const* col_data;
@@ -48,7 +58,6 @@ struct ToRows3Params {
   int32_t super_rows;    // rows dealt to a CTA at a time (multiple of 8)
   int32_t sb;            // STRING columns per block
   int32_t nblocks;
-  int32_t pf;            // L2 prefetch of column pieces: 0 off, 1 next tile, 2 this tile (at the top)
   int32_t nitems;        // work items per tile (string blocks + fixed batches + validity groups)
   int32_t class_begin[kNumClasses + 1];
   const Entry* entries;
@@ -82,15 +91,15 @@ __device__ __forceinline__ void t3_sts_u16(uint32_t a, uint32_t v) { asm volatil
 __device__ __forceinline__ void t3_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void t3_sts_v2(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y)); }
 
-// 4 columns of element size W: loads first (independent), then the stores into the lane's row image
-template <int W>
+// U columns of element size W: loads first (independent), then the stores into the lane's row image
+template <int W, int U>
 __device__ __forceinline__ void t3_fixed(const uint8_t* const* s_ent_ptr, const int32_t* s_ent_start, int begin, int count,
                                          int64_t abs_row, bool act, uint32_t row_s)
 {
   constexpr int NW = W >= 4 ? W / 4 : 1;
-  uint32_t v[4][NW];
+  uint32_t v[U][NW];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < U; ++j) {
     if (j < count && act) {
       const uint8_t* src = s_ent_ptr[begin + j] + abs_row * W;
       if constexpr (W == 1) v[j][0] = __ldcs(src);
@@ -101,7 +110,7 @@ __device__ __forceinline__ void t3_fixed(const uint8_t* const* s_ent_ptr, const 
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < U; ++j) {
     if (j < count && act) {
       const uint32_t a = row_s + static_cast<uint32_t>(s_ent_start[begin + j]);
       if constexpr (W == 1) t3_sts_u8(a, v[j][0]);
@@ -191,9 +200,11 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   int32_t* s_ent_start      = reinterpret_cast<int32_t*>(q);         q += 4 * p.nfixed;
   int32_t* s_sstart         = reinterpret_cast<int32_t*>(q);         q += 4 * p.nstr;
   int32_t* s_bsum           = reinterpret_cast<int32_t*>(q);         q += 4 * 32 * p.nblocks;
-  int32_t* s_items          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;
-  uint8_t* s_ent_w          = q;  // element size of each fixed-width entry
-  __shared__ int s_next, s_nitems;
+  int32_t* s_items          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // build order
+  int32_t* s_list           = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // grouped by owning warp
+  uint8_t* s_owner          = q;
+  __shared__ int s_nitems, s_next;
+  __shared__ int s_wbeg[kT3Warps + 1];
 
   const int tid  = threadIdx.x;
   const int lane = lane_id();
@@ -202,9 +213,6 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     const Entry e  = p.entries[i];
     s_ent_ptr[i]   = static_cast<const uint8_t*>(p.col_data[e.column]);
     s_ent_start[i] = e.start;
-    int k = 0;
-    while (i >= p.class_begin[k + 1]) ++k;
-    s_ent_w[i] = static_cast<uint8_t>(1 << k);
   }
   for (int i = tid; i < p.ncols; i += kT3Threads) s_mask[i] = p.masks[i];
   for (int i = tid; i < p.nstr; i += kT3Threads) {
@@ -216,30 +224,60 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     int n = 0;
     for (int b = 0; b < p.nblocks; ++b) s_items[n++] = t3_item(kItemString, b, 0);
     for (int k = kNumClasses - 1; k >= 0; --k)
-      for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += 4) s_items[n++] = t3_item(k, e, tmin(4, p.class_begin[k + 1] - e));
+    {
+      const int U = (k >= 3 || !T3_U8) ? 4 : 8;
+      for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += U) s_items[n++] = t3_item(k, e, tmin(U, p.class_begin[k + 1] - e));
+    }
     for (int g = 0; g * 32 < p.ncols; ++g) s_items[n++] = t3_item(kItemValidity, g, 0);
     s_nitems = n;
-    s_next   = 0;
   }
   __syncthreads();
-  const int nitems       = s_nitems;
+  // static schedule: items (heaviest first) go to the least-loaded warp; every warp then walks its own list
+  // (no atomics in the tile loop).  Costs are in units of ~one dependent memory round trip.
+  if (w == 0) {
+    const int n = s_nitems;
+    int load    = lane < kT3Warps ? 0 : (1 << 25);
+    for (int i = 0; i < n; ++i) {
+      const int32_t item = s_items[i];
+      const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
+      const int cost = kind == kItemString ? 10 * tmin(p.sb, p.nstr - begin * p.sb) : kind == kItemValidity ? 6 : 4 + count;
+      const int sel  = static_cast<int>(__reduce_min_sync(0xffffffffu, static_cast<unsigned>((load << 5) | lane)) & 31u);
+      if (lane == sel) load += cost;
+      if (lane == 0) s_owner[i] = static_cast<uint8_t>(sel);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int pos = 0;
+      for (int ww = 0; ww < kT3Warps; ++ww) {
+        s_wbeg[ww] = pos;
+        for (int i = 0; i < n; ++i)
+          if (s_owner[i] == ww) s_list[pos++] = s_items[i];
+      }
+      s_wbeg[kT3Warps] = pos;
+    }
+  }
+  __syncthreads();
+  const int my_beg = s_wbeg[w], my_end_item = s_wbeg[w + 1];
   const uint32_t image_s = smem_u32(image);
   const uintptr_t out_g  = reinterpret_cast<uintptr_t>(p.out_data);
   const int nvb          = (p.ncols + 7) >> 3;
 
   const int64_t nsuper = (p.row_count + p.super_rows - 1) / p.super_rows;
-  for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
-    int64_t r          = st * p.super_rows;
-    const int64_t rend = tmin<int64_t>(p.row_count, r + p.super_rows);
-    while (r < rend) {
+  // tiles walk super-tiles (dealt round-robin to the CTAs); the LIST offsets of the NEXT tile are fetched while
+  // the current one is assembled, so the geometry never waits on memory
+  int64_t st = blockIdx.x;
+  if (st >= nsuper) return;
+  int64_t r    = st * p.super_rows;
+  int64_t rend = tmin<int64_t>(p.row_count, r + p.super_rows);
+  int32_t oa = 0, ob = 0;
+  if (lane < tmin<int64_t>(32, rend - r)) {
+    oa = p.out_offsets[r + lane];
+    ob = p.out_offsets[r + lane + 1];
+  }
+  {
+    for (;;) {
       const int rem      = static_cast<int>(tmin<int64_t>(32, rend - r));
       const int64_t abs0 = p.row_start + r;
-      // ---- 1. geometry -------------------------------------------------------------------------------
-      int64_t oa = 0, ob = 0;
-      if (lane < rem) {
-        oa = p.out_offsets[r + lane];
-        ob = p.out_offsets[r + lane + 1];
-      }
       // ---- 2. string block sums (+ prefetch of the chars) -----------------------------------------------
       for (int b = w; b < p.nblocks; b += kT3Warps) {
         const int s0 = b * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
@@ -265,10 +303,10 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         }
         s_bsum[b * 32 + lane] = sum;
       }
-      const int64_t lo      = __shfl_sync(0xffffffffu, oa, 0);
+      const int64_t lo      = static_cast<uint32_t>(__shfl_sync(0xffffffffu, oa, 0));
       const int skew        = static_cast<int>((out_g + lo) & 15);
-      const int my_off      = static_cast<int>(oa - lo) + skew;
-      const int my_end      = static_cast<int>(ob - lo) + skew;
+      const int my_off      = static_cast<int>(static_cast<uint32_t>(oa) - static_cast<uint32_t>(lo)) + skew;
+      const int my_end      = static_cast<int>(static_cast<uint32_t>(ob) - static_cast<uint32_t>(lo)) + skew;
       const bool fits       = lane < rem && my_end <= p.stage_bytes;
       int rows              = __popc(__ballot_sync(0xffffffffu, fits));
       if (rows < rem) rows &= ~7;
@@ -277,28 +315,18 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         return;
       }
       const int hi_rel = __shfl_sync(0xffffffffu, my_end, rows - 1);
-      // ---- L2 prefetch of column pieces (values, offsets, mask words): fire and forget ----------------------------
-      if (p.pf) {
-        int64_t nr = r;
-        if (p.pf == 1) {
-          nr = r + rows;
-          if (nr >= rend) nr = (st + gridDim.x) * p.super_rows;
-        }
-        if (nr + 64 <= p.row_count) {  // stay inside every buffer
-          const int64_t an = p.row_start + nr;
-          for (int i = tid; i < p.nfixed; i += kT3Threads) {
-            const int W      = s_ent_w[i];
-            const uint8_t* a = s_ent_ptr[i] + an * W;
-            for (int off = 0; off <= 32 * W; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
-          }
-          if (p.pf == 1)
-            for (int i = tid; i < p.nstr; i += kT3Threads) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(s_soff[i] + an));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(s_soff[i] + an + 32));
-            }
-          for (int i = tid; i < p.ncols; i += kT3Threads)
-            if (s_mask[i]) asm volatile("prefetch.global.L2 [%0];" ::"l"(s_mask[i] + (an >> 5)));
-        }
+      // next tile: position + its LIST offsets (consumed at the bottom of the loop)
+      int64_t nr = r + rows, nst = st, nrend = rend;
+      if (nr >= rend) {
+        nst   = st + gridDim.x;
+        nr    = nst * p.super_rows;
+        nrend = tmin<int64_t>(p.row_count, nr + p.super_rows);
+      }
+      const bool more = nst < nsuper;
+      int32_t na = 0, nb = 0;
+      if (more && lane < tmin<int64_t>(32, nrend - nr)) {
+        na = p.out_offsets[nr + lane];
+        nb = p.out_offsets[nr + lane + 1];
       }
       const bool act   = lane < rows;
       const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
@@ -320,29 +348,46 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
           asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u));
       }
       __syncthreads();
-      // ---- 4. work queue ---------------------------------------------------------------------------------
+      // ---- 4. this warp's items ----------------------------------------------------------------------------
+#if T3_STATIC
+      for (int qi = my_beg; qi < my_end_item; ++qi) {
+        const int32_t item = s_list[qi];
+#else
       for (;;) {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(&s_next, 1);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= nitems) break;
-        const int32_t item = s_items[it];
+        int qi = 0;
+        if (lane == 0) qi = atomicAdd(&s_next, 1);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= s_nitems) break;
+        const int32_t item = s_items[qi];
+#endif
         const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
         if (kind == kItemString) {
           const int s0 = begin * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
           int32_t run = s_bsum[begin * 32 + lane];
-          for (int s = s0; s < s1; ++s) {
-            int32_t o0 = 0, L = 0;
-            if (act) {
-              const int32_t* so = s_soff[s] + abs0 + lane;
-              o0                = __ldg(so);
-              L                 = tmax(__ldg(so + 1) - o0, 0);
-              const uint32_t pa = row_s + static_cast<uint32_t>(s_sstart[s]);
-              t3_sts_u32(pa, static_cast<uint32_t>(run));  // RC:848
-              t3_sts_u32(pa + 4, static_cast<uint32_t>(L));  // RC:849
+          for (int sA = s0; sA < s1; sA += kHoist) {
+            int32_t o0[kHoist], Ls[kHoist];
+#pragma unroll
+            for (int j = 0; j < kHoist; ++j) {  // the offsets of kHoist columns first (L1 / L2 hits: step 2 touched them)
+              o0[j] = Ls[j] = 0;
+              if (sA + j < s1 && act) {
+                const int32_t* so = s_soff[sA + j] + abs0 + lane;
+                o0[j]             = __ldg(so);
+                Ls[j]             = tmax(__ldg(so + 1) - o0[j], 0);
+              }
             }
-            t3_copy_chars(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0), row_s + static_cast<uint32_t>(run), L, rows, lane);
-            run += L;
+#pragma unroll
+            for (int j = 0; j < kHoist; ++j) {
+              if (sA + j < s1) {
+                const int s = sA + j;
+                if (act) {
+                  const uint32_t pa = row_s + static_cast<uint32_t>(s_sstart[s]);
+                  t3_sts_u32(pa, static_cast<uint32_t>(run));        // RC:848
+                  t3_sts_u32(pa + 4, static_cast<uint32_t>(Ls[j]));  // RC:849
+                }
+                t3_copy_chars(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0[j]), row_s + static_cast<uint32_t>(run), Ls[j], rows, lane);
+                run += Ls[j];
+              }
+            }
           }
         } else if (kind == kItemValidity) {
           const int c      = begin * 32 + lane;
@@ -371,11 +416,11 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         } else {
           const int64_t ar = abs0 + lane;
           switch (kind) {
-            case 4: t3_fixed<16>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 3: t3_fixed<8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 2: t3_fixed<4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 1: t3_fixed<2>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            default: t3_fixed<1>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 4: t3_fixed<16, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 3: t3_fixed<8, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 2: t3_fixed<4, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 1: t3_fixed<2, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            default: t3_fixed<1, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
           }
         }
       }
@@ -402,7 +447,8 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         for (uintptr_t a = t_beg; a < g_hi; a += 8)
           *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(image + (a - fl));
       }
-      r += rows;
+      if (!more) break;
+      st = nst; r = nr; rend = nrend; oa = na; ob = nb;
     }
   }
   if (tid == 0) tma_store_wait_all<0>();
@@ -436,12 +482,15 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.sb      = std::max(env_sb > 0 ? env_sb : (cps == 1 ? 4 : 8), (nstr + kT3MaxBlocks - 1) / kT3MaxBlocks);
   p.nblocks = (nstr + p.sb - 1) / p.sb;
   int nitems = p.nblocks + (p.ncols + 31) / 32;
-  for (int k = 0; k < kNumClasses; ++k) nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + 3) / 4;
+  for (int k = 0; k < kNumClasses; ++k) {
+    const int U = (k >= 3 || !T3_U8) ? 4 : 8;
+    nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + U - 1) / U;
+  }
   if (nitems > kT3MaxItems) return SRJ_OK;
   p.nitems = nitems;
   const size_t tables = sizeof(void*) * (static_cast<size_t>(p.nfixed) + p.ncols + 2 * static_cast<size_t>(nstr)) +
-                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + nitems) +
-                        ((static_cast<size_t>(p.nfixed) + 15) & ~size_t{15}) + 32 + 128;
+                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + 2 * static_cast<size_t>(nitems)) +
+                        ((static_cast<size_t>(nitems) + 15) & ~size_t{15}) + 32 + 128;
   const int64_t budget = 232448 / cps - 1024 - 64;
   int64_t stage        = (budget - static_cast<int64_t>(tables)) / 16 * 16;
   if (stage < 32 * 1024 || stage < 8ll * (plan->fixed_row_size + 64)) return SRJ_OK;
@@ -466,7 +515,6 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.entries      = plan->d_tr_entries;
   p.string_start = plan->d_string_start;
   p.fail_flag    = d_fail_flag;
-  p.pf           = getenv("SRJ_T3_PF") ? atoi(getenv("SRJ_T3_PF")) : 0;
 
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrj_b200.so")
+LIB_PATH = os.environ.get("SRJ_B200_LIB") or os.path.join(_HERE, "libsrj_b200.so")  # env: development variants only
 
 SRJ_OK, SRJ_EINVAL, SRJ_EUNSUPPORTED, SRJ_EOVERFLOW, SRJ_ECUDA, SRJ_ENOMEM = 0, -1, -2, -3, -4, -5
 HASH_NONE, HASH_XXHASH64, HASH_MURMUR3_32, HASH_HIVE = 0, 1, 2, 3
