@@ -158,6 +158,20 @@ __device__ __forceinline__ uint64_t load_key(const uint8_t* p, int sz)
   }
 }
 
+// 4 / 8: the key is hashed as the 4- / 8-byte value stored in the row (xxhash64.cu / murmur_hash.cuh element
+// hashers for 32- and 64-bit integers, dates, timestamps, durations, DECIMAL64); 0: needs widening or normalising
+__device__ __forceinline__ int plain_key_bytes(int32_t t)
+{
+  switch (t) {
+    case SRJ_INT32: case SRJ_UINT32: case SRJ_TIMESTAMP_DAYS: case SRJ_DURATION_DAYS: return 4;
+    case SRJ_INT64: case SRJ_UINT64: case SRJ_TIMESTAMP_SECONDS: case SRJ_TIMESTAMP_MILLISECONDS:
+    case SRJ_TIMESTAMP_MICROSECONDS: case SRJ_TIMESTAMP_NANOSECONDS: case SRJ_DURATION_SECONDS:
+    case SRJ_DURATION_MILLISECONDS: case SRJ_DURATION_MICROSECONDS: case SRJ_DURATION_NANOSECONDS:
+    case SRJ_DECIMAL64: return 8;
+    default: return 0;
+  }
+}
+
 __device__ __forceinline__ int key_size(int32_t t)
 {
   switch (t) {
@@ -173,7 +187,8 @@ __device__ __forceinline__ int key_size(int32_t t)
 // Fused-hash parameters, copied to shared memory once per CTA: the out-of-line hash code must not reach
 // into the kernel parameter struct through a generic pointer (each access becomes a global-path load).
 struct HashSpec {
-  int32_t kind, nkeys, validity_offset, pad;
+  int32_t kind, nkeys, validity_offset;
+  int32_t plain;  // 1: every key is a 4- or 8-byte integer-like value (hashed as is): two-chains path
   int32_t key_start[16];
   int32_t key_type[16];
   int32_t key_col[16];
@@ -406,6 +421,47 @@ __device__ __noinline__ void hash_tile(const HashSpec* hs, const uint8_t* base, 
   // groups are dealt to the warps starting at a different warp every tile: consumers only meet at the
   // stage barriers (up to two tiles apart), so the extra group a warp gets on one tile is absorbed.
   const int rot = static_cast<int>((r0 / tmax(rows, 1)) % NCW);
+  if (!SAFE && hs->plain) {
+    // Plain keys: a warp hashes TWO of its row groups at once -- two independent multiply chains per lane --
+    // (the element hash is a serial dependency chain; one chain per warp leaves the integer pipe idle).
+    const bool xx = kind == SRJ_HASH_XXHASH64;
+    for (int g = (cw + NCW - rot) % NCW; g < ng32; g += 2 * NCW) {
+      const int rowA = g * 32 + lane, rowB = rowA + NCW * 32;
+      const bool inA = rowA < rows, inB = rowB < rows;
+      const uint8_t* rpA = row_ptr<VAR>(tv, inA ? rowA : 0);
+      const uint8_t* rpB = row_ptr<VAR>(tv, inB ? rowB : 0);
+      uint64_t hA = static_cast<uint64_t>(hs->seed), hB = hA;
+      for (int k = 0; k < nkeys; ++k) {
+        const int c       = hs->key_col[k];
+        const int st      = hs->key_start[k];
+        const bool four   = plain_key_bytes(hs->key_type[k]) == 4;
+        const bool validA = (rpA[voff + (c >> 3)] >> (c & 7)) & 1u;
+        const bool validB = (rpB[voff + (c >> 3)] >> (c & 7)) & 1u;
+        uint64_t tA, tB;
+        if (four) {
+          const uint32_t vA = *reinterpret_cast<const uint32_t*>(rpA + st);
+          const uint32_t vB = *reinterpret_cast<const uint32_t*>(rpB + st);
+          if (xx) { tA = hash::xx_u32(vA, hA); tB = hash::xx_u32(vB, hB); }
+          else { tA = hash::mm_u32(vA, static_cast<uint32_t>(hA)); tB = hash::mm_u32(vB, static_cast<uint32_t>(hB)); }
+        } else {
+          const uint64_t vA = load_key<false>(rpA + st, 8);
+          const uint64_t vB = load_key<false>(rpB + st, 8);
+          if (xx) { tA = hash::xx_u64(vA, hA); tB = hash::xx_u64(vB, hB); }
+          else { tA = hash::mm_u64(vA, static_cast<uint32_t>(hA)); tB = hash::mm_u64(vB, static_cast<uint32_t>(hB)); }
+        }
+        hA = validA ? tA : hA;  // a null keeps the accumulator (Spark)
+        hB = validB ? tB : hB;
+      }
+      if (xx) {
+        if (inA) reinterpret_cast<uint64_t*>(hs->out)[r0 + rowA] = hA;
+        if (inB) reinterpret_cast<uint64_t*>(hs->out)[r0 + rowB] = hB;
+      } else {
+        if (inA) reinterpret_cast<uint32_t*>(hs->out)[r0 + rowA] = static_cast<uint32_t>(hA);
+        if (inB) reinterpret_cast<uint32_t*>(hs->out)[r0 + rowB] = static_cast<uint32_t>(hB);
+      }
+    }
+    return;
+  }
   for (int g = (cw + NCW - rot) % NCW; g < ng32; g += NCW) {
     const int row = g * 32 + lane;
     if (row >= rows) continue;
@@ -702,6 +758,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_kernel(const __gr
     s_hash->validity_offset = p.validity_offset;
     s_hash->seed            = p.hash_seed;
     s_hash->out             = p.hash_out;
+    int plain               = p.hash_kind == SRJ_HASH_XXHASH64 || p.hash_kind == SRJ_HASH_MURMUR3_32;
+    for (int k = 0; k < p.hash_nkeys; ++k) plain &= plain_key_bytes(p.key_type[k]) != 0;
+    s_hash->plain = plain;
     for (int k = 0; k < 16; ++k) {
       s_hash->key_start[k] = p.key_start[k];
       s_hash->key_type[k]  = p.key_type[k];

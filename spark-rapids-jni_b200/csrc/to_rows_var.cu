@@ -1,8 +1,8 @@
 // to_rows_var.cu -- columns -> JCUDF rows for tables with STRING columns and wide rows
 // (reference: copy_to_rows + copy_validity_to_rows + copy_strings_to_rows, RC:574-861).
 //
-// Two CTAs per SM, each owning one row-image buffer of ~105 KB.  A tile = the largest multiple of 8
-// rows (<= 32) whose bytes fit the buffer; lane = row everywhere, so every global read is a
+// One CTA of 24 warps per SM owning a ~200 KB row-image buffer (variant: two CTAs of 12 warps with
+// ~105 KB each).  A tile = as many rows (<= 32, a multiple of 8 unless the super-tile ends) as fit; lane = row everywhere, so every global read is a
 // contiguous piece of a column (values, offsets, chars of consecutive rows) and every shared-memory
 // write lands in the lane's own row image.  Per tile:
 //   1. geometry from the LIST offsets (already written by batch_offsets_kernel), every warp
@@ -10,7 +10,8 @@
 //   2. string block sums: warp b sums the lengths of its block of STRING columns per row (these loads
 //      also pull the offsets into L1/L2 and prefetch the chars lines);
 //   3. wait for the previous TMA store to have read the buffer, zero it (padding bytes are 0);
-//   4. a dynamic work queue (shared-memory counter) of independent items writing disjoint bytes:
+//   4. independent work items writing disjoint bytes, dealt to the warps once per launch by a
+//      longest-processing-time rule (no atomics in the tile loop):
 //        string block : (offset, len) pairs + chars.  Chars of <= 32 bytes move as aligned 32-bit
 //                       words: up to 10 independent ld.global per lane, funnel-shifted to the
 //                       destination alignment, st.shared.u32 for whole words, st.shared.u8 at the
@@ -19,7 +20,7 @@
 //        validity     : lane = column loads the mask word(s) covering the tile, the 32x32 bit
 //                       butterfly turns them into 4 validity bytes per row;
 //   5. the finished tile -- ONE contiguous byte range of the output -- leaves with a single 1-D TMA
-//      bulk store; the other CTA of the SM assembles while this one drains.
+//      bulk store.
 // A tile that cannot hold 8 rows raises *fail_flag; the generic kernel (to_rows.cu) launched right
 // behind redoes the batch when it sees the flag.
 #include <algorithm>
@@ -38,6 +39,12 @@ constexpr int kT3MaxItems  = 1024;
 #endif
 #ifndef T3_U8
 #define T3_U8 0
+#endif
+#ifndef T3_CPF
+#define T3_CPF 1
+#endif
+#ifndef T3_CPASYNC
+#define T3_CPASYNC 1
 #endif
 #ifndef T3_HOIST
 #define T3_HOIST 1
@@ -90,6 +97,29 @@ __device__ __forceinline__ void t3_sts_u8(uint32_t a, uint32_t v) { asm volatile
 __device__ __forceinline__ void t3_sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void t3_sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 __device__ __forceinline__ void t3_sts_v2(uint32_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y)); }
+
+// U columns of element size W (>= 4) straight from the column into the lane's row image with cp.async (LDGSTS):
+// no register staging and no scoreboard wait -- the warp only issues; completion is collected once per tile
+// (cp.async.wait_all before the TMA store).  16-byte fields go as two 8-byte copies (rows are 8-byte aligned only).
+template <int W, int U>
+__device__ __forceinline__ void t3_fixed_async(const uint8_t* const* s_ent_ptr, const int32_t* s_ent_start, int begin, int count,
+                                               int64_t abs_row, bool act, uint32_t row_s)
+{
+  static_assert(W >= 4, "cp.async moves 4, 8 or 16 bytes");
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    if (j < count && act) {
+      const uint8_t* src = s_ent_ptr[begin + j] + abs_row * W;
+      const uint32_t a   = row_s + static_cast<uint32_t>(s_ent_start[begin + j]);
+      if constexpr (W == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(src) : "memory");
+      else if constexpr (W == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(src) : "memory");
+      else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(src) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a + 8), "l"(src + 8) : "memory");
+      }
+    }
+  }
+}
 
 // U columns of element size W: loads first (independent), then the stores into the lane's row image
 template <int W, int U>
@@ -225,7 +255,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     for (int b = 0; b < p.nblocks; ++b) s_items[n++] = t3_item(kItemString, b, 0);
     for (int k = kNumClasses - 1; k >= 0; --k)
     {
-      const int U = (k >= 3 || !T3_U8) ? 4 : 8;
+      const int U = T3_CPASYNC ? 8 : ((k >= 3 || !T3_U8) ? 4 : 8);
       for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += U) s_items[n++] = t3_item(k, e, tmin(U, p.class_begin[k + 1] - e));
     }
     for (int g = 0; g * 32 < p.ncols; ++g) s_items[n++] = t3_item(kItemValidity, g, 0);
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     for (int i = 0; i < n; ++i) {
       const int32_t item = s_items[i];
       const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
-      const int cost = kind == kItemString ? 10 * tmin(p.sb, p.nstr - begin * p.sb) : kind == kItemValidity ? 6 : 4 + count;
+      const int cost = kind == kItemString ? 10 * tmin(p.sb, p.nstr - begin * p.sb) : kind == kItemValidity ? 6 : (T3_CPASYNC && kind >= 2 ? 3 : 4 + count);
       const int sel  = static_cast<int>(__reduce_min_sync(0xffffffffu, static_cast<unsigned>((load << 5) | lane)) & 31u);
       if (lane == sel) load += cost;
       if (lane == 0) s_owner[i] = static_cast<uint8_t>(sel);
@@ -263,21 +293,20 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   const int nvb          = (p.ncols + 7) >> 3;
 
   const int64_t nsuper = (p.row_count + p.super_rows - 1) / p.super_rows;
-  // tiles walk super-tiles (dealt round-robin to the CTAs); the LIST offsets of the NEXT tile are fetched while
-  // the current one is assembled, so the geometry never waits on memory
-  int64_t st = blockIdx.x;
-  if (st >= nsuper) return;
-  int64_t r    = st * p.super_rows;
-  int64_t rend = tmin<int64_t>(p.row_count, r + p.super_rows);
-  int32_t oa = 0, ob = 0;
-  if (lane < tmin<int64_t>(32, rend - r)) {
-    oa = p.out_offsets[r + lane];
-    ob = p.out_offsets[r + lane + 1];
-  }
-  {
-    for (;;) {
+  for (int64_t st = blockIdx.x; st < nsuper; st += gridDim.x) {
+    int64_t r          = st * p.super_rows;
+    const int64_t rend = tmin<int64_t>(p.row_count, r + p.super_rows);
+    while (r < rend) {
       const int rem      = static_cast<int>(tmin<int64_t>(32, rend - r));
       const int64_t abs0 = p.row_start + r;
+      // ---- 1. geometry: every warp reads the tile's LIST offsets itself (no header hand-off).  Fetching the next
+      // tile's offsets a tile ahead was measured slower (the early loads pin a scoreboard the tile's other
+      // memory operations then wait on) ----------------------------------------------------------------------------
+      int32_t oa = 0, ob = 0;
+      if (lane < rem) {
+        oa = p.out_offsets[r + lane];
+        ob = p.out_offsets[r + lane + 1];
+      }
       // ---- 2. string block sums (+ prefetch of the chars) -----------------------------------------------
       for (int b = w; b < p.nblocks; b += kT3Warps) {
         const int s0 = b * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
@@ -297,7 +326,9 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
           for (int j = 0; j < 4; ++j) {
             if (sA + j < s1 && lane < rem) {
               sum += o1[j] - o0[j];
+#if T3_CPF
               if (o1[j] > o0[j]) asm volatile("prefetch.global.L2 [%0];" ::"l"(s_chars[sA + j] + o0[j]));
+#endif
             }
           }
         }
@@ -315,19 +346,6 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         return;
       }
       const int hi_rel = __shfl_sync(0xffffffffu, my_end, rows - 1);
-      // next tile: position + its LIST offsets (consumed at the bottom of the loop)
-      int64_t nr = r + rows, nst = st, nrend = rend;
-      if (nr >= rend) {
-        nst   = st + gridDim.x;
-        nr    = nst * p.super_rows;
-        nrend = tmin<int64_t>(p.row_count, nr + p.super_rows);
-      }
-      const bool more = nst < nsuper;
-      int32_t na = 0, nb = 0;
-      if (more && lane < tmin<int64_t>(32, nrend - nr)) {
-        na = p.out_offsets[nr + lane];
-        nb = p.out_offsets[nr + lane + 1];
-      }
       const bool act   = lane < rows;
       const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
       // ---- 3. buffer free -> zero fill -----------------------------------------------------------------
@@ -416,14 +434,23 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         } else {
           const int64_t ar = abs0 + lane;
           switch (kind) {
+#if T3_CPASYNC
+            case 4: t3_fixed_async<16, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 3: t3_fixed_async<8, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 2: t3_fixed_async<4, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            case 1: t3_fixed<2, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+            default: t3_fixed<1, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+#else
             case 4: t3_fixed<16, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 3: t3_fixed<8, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 2: t3_fixed<4, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 1: t3_fixed<2, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             default: t3_fixed<1, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
+#endif
           }
         }
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's cp.async copies have landed
       fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA store
       __syncthreads();
       // ---- 5. write out ------------------------------------------------------------------------------------
@@ -447,8 +474,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         for (uintptr_t a = t_beg; a < g_hi; a += 8)
           *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(image + (a - fl));
       }
-      if (!more) break;
-      st = nst; r = nr; rend = nrend; oa = na; ob = nb;
+      r += rows;
     }
   }
   if (tid == 0) tma_store_wait_all<0>();
@@ -483,7 +509,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.nblocks = (nstr + p.sb - 1) / p.sb;
   int nitems = p.nblocks + (p.ncols + 31) / 32;
   for (int k = 0; k < kNumClasses; ++k) {
-    const int U = (k >= 3 || !T3_U8) ? 4 : 8;
+    const int U = T3_CPASYNC ? 8 : ((k >= 3 || !T3_U8) ? 4 : 8);
     nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + U - 1) / U;
   }
   if (nitems > kT3MaxItems) return SRJ_OK;
