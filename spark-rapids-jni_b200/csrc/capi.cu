@@ -583,7 +583,11 @@ int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int6
   if (h_null_counts) std::fill(h_null_counts, h_null_counts + nc, 0);
   if (num_rows == 0) return SRJ_OK;
   const int64_t S = plan->fixed_row_size;
-  if (chunk_rows <= 0) chunk_rows = std::max<int64_t>(32 * 1024, (256ll << 20) / S);  // ~256 MB of rows per chunk
+  if (chunk_rows <= 0) {
+    const char* e     = getenv("SRJ_HOST_CHUNK_MB");  // tuning knob (development)
+    const int64_t cmb = e ? std::max(1, atoi(e)) : 256;
+    chunk_rows        = std::max<int64_t>(32 * 1024, (cmb << 20) / S);  // ~256 MB of rows per chunk
+  }
   const int64_t T = plan->tiling.tile_rows >= 32 ? plan->tiling.tile_rows : 32;
   chunk_rows      = (chunk_rows + T - 1) / T * T;
   chunk_rows      = std::min<int64_t>(chunk_rows, (num_rows + T - 1) / T * T);

@@ -40,9 +40,6 @@ constexpr int kT3MaxItems  = 1024;
 #ifndef T3_U8
 #define T3_U8 0
 #endif
-#ifndef T3_CPF
-#define T3_CPF 1
-#endif
 #ifndef T3_CPASYNC
 #define T3_CPASYNC 1
 #endif
@@ -65,6 +62,7 @@ struct ToRows3Params {
   int32_t super_rows;    // rows dealt to a CTA at a time (multiple of 8)
   int32_t sb;            // STRING columns per block
   int32_t nblocks;
+  int32_t slot_bytes;    // chars staging bytes per STRING column (multiple of 16), 0 = no staging
   int32_t nitems;        // work items per tile (string blocks + fixed batches + validity groups)
   int32_t class_begin[kNumClasses + 1];
   const Entry* entries;
@@ -152,8 +150,28 @@ __device__ __forceinline__ void t3_fixed(const uint8_t* const* s_ent_ptr, const 
   }
 }
 
-// chars of one STRING column for the tile: lane's string = L bytes at global S -> shared address D
-__device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, int rows, int lane)
+// source-space loads of the chars copy: global (read-only path) or shared (the staging slots)
+template <bool SMEM>
+__device__ __forceinline__ uint32_t t3_ld_u32(uint64_t a)
+{
+  uint32_t v;
+  if constexpr (SMEM) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(a)));
+  else v = __ldg(reinterpret_cast<const uint32_t*>(a));
+  return v;
+}
+template <bool SMEM>
+__device__ __forceinline__ uint32_t t3_ld_u8(uint64_t a)
+{
+  uint32_t v;
+  if constexpr (SMEM) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(a)));
+  else v = __ldg(reinterpret_cast<const uint8_t*>(a));
+  return v;
+}
+
+// chars of one STRING column for the tile: lane's string = L bytes at source address S (global, or shared when
+// the tile's chars were staged) -> shared address D
+template <bool SMEM>
+__device__ __forceinline__ void t3_copy_chars(uint64_t S, uint32_t D, int L, int rows, int lane)
 {
   const int maxL = __reduce_max_sync(0xffffffffu, L);
   if (maxL == 0) return;
@@ -164,7 +182,7 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
     const int ssh      = static_cast<int>(S & 3u);
     const int dlt      = ssh - dsh;
     const int pre      = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
-    const uintptr_t sp = S - pre;
+    const uint64_t sp  = S - pre;
     const int sh       = (dlt & 3) * 8;
     const int end      = dsh + L;            // one past the last dst byte, relative to dst word 0
     const int kfull1   = end >> 2;           // full dst words: [dsh ? 1 : 0, kfull1)
@@ -175,14 +193,13 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
     // destination starts inside a word, the last nt bytes when it ends inside one
     const int nh = dsh ? tmin(L, 4 - dsh) : 0;
     const int nt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
-    const uint8_t* Sb = reinterpret_cast<const uint8_t*>(S);
-    const uint8_t* St = Sb + (L - nt);
+    const uint64_t St = S + (L - nt);
     uint32_t hb[3], tb[3];
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
       hb[t] = tb[t] = 0;
-      if (t < nh) hb[t] = __ldg(Sb + t);
-      if (t < nt) tb[t] = __ldg(St + t);
+      if (t < nh) hb[t] = t3_ld_u8<SMEM>(S + t);
+      if (t < nt) tb[t] = t3_ld_u8<SMEM>(St + t);
     }
     uint32_t w[10];
 #pragma unroll
@@ -190,7 +207,7 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
       w[k] = 0;
       // only words that overlap [S, S+L): an aligned word that holds one valid byte is inside the buffer's page
       const bool need = k == 0 ? (lim > 0 && pre < 4) : (4 * k < lim);
-      if (need) w[k] = __ldg(reinterpret_cast<const uint32_t*>(sp + 4 * k));
+      if (need) w[k] = t3_ld_u32<SMEM>(sp + 4 * k);
     }
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
@@ -208,10 +225,10 @@ __device__ __forceinline__ void t3_copy_chars(uintptr_t S, uint32_t D, int L, in
   } else {
     // long strings: the warp copies one row's string at a time, lane = byte
     for (int i = 0; i < rows; ++i) {
-      const uintptr_t Si = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(S), i);
-      const uint32_t Di  = __shfl_sync(0xffffffffu, D, i);
-      const int Li       = __shfl_sync(0xffffffffu, L, i);
-      for (int j = lane; j < Li; j += 32) t3_sts_u8(Di + j, __ldg(reinterpret_cast<const uint8_t*>(Si + j)));
+      const uint64_t Si = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(S), i);
+      const uint32_t Di = __shfl_sync(0xffffffffu, D, i);
+      const int Li      = __shfl_sync(0xffffffffu, L, i);
+      for (int j = lane; j < Li; j += 32) t3_sts_u8(Di + j, t3_ld_u8<SMEM>(Si + j));
     }
   }
 }
@@ -222,7 +239,8 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   constexpr int kT3Threads = kT3Warps * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* image = smem;  // stage_bytes + 32
-  uint8_t* q     = smem + p.stage_bytes + 32;
+  uint8_t* stg   = smem + p.stage_bytes + 32;  // nstr * slot_bytes: the tile's chars, one 16-byte aligned slice per column
+  uint8_t* q     = stg + static_cast<size_t>(p.nstr) * p.slot_bytes;
   const uint8_t** s_ent_ptr = reinterpret_cast<const uint8_t**>(q);  q += sizeof(void*) * p.nfixed;
   const uint32_t** s_mask   = reinterpret_cast<const uint32_t**>(q); q += sizeof(void*) * p.ncols;
   const int32_t** s_soff    = reinterpret_cast<const int32_t**>(q);  q += sizeof(void*) * p.nstr;
@@ -230,10 +248,12 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   int32_t* s_ent_start      = reinterpret_cast<int32_t*>(q);         q += 4 * p.nfixed;
   int32_t* s_sstart         = reinterpret_cast<int32_t*>(q);         q += 4 * p.nstr;
   int32_t* s_bsum           = reinterpret_cast<int32_t*>(q);         q += 4 * 32 * p.nblocks;
+  int32_t* s_delta          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nstr;     // staged address of chars offset 0
   int32_t* s_items          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // build order
   int32_t* s_list           = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // grouped by owning warp
   uint8_t* s_owner          = q;
   __shared__ int s_nitems, s_next;
+  __shared__ int s_direct[2];  // per tile parity: 1 = some column's slice did not fit its slot, read the chars from global
   __shared__ int s_wbeg[kT3Warps + 1];
 
   const int tid  = threadIdx.x;
@@ -259,7 +279,9 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
       for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += U) s_items[n++] = t3_item(k, e, tmin(U, p.class_begin[k + 1] - e));
     }
     for (int g = 0; g * 32 < p.ncols; ++g) s_items[n++] = t3_item(kItemValidity, g, 0);
-    s_nitems = n;
+    s_nitems    = n;
+    s_direct[0] = 0;
+    s_direct[1] = 0;
   }
   __syncthreads();
   // static schedule: items (heaviest first) go to the least-loaded warp; every warp then walks its own list
@@ -289,6 +311,9 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   __syncthreads();
   const int my_beg = s_wbeg[w], my_end_item = s_wbeg[w + 1];
   const uint32_t image_s = smem_u32(image);
+  const uint32_t stg_s   = smem_u32(stg);
+  int tile_par           = 0;
+
   const uintptr_t out_g  = reinterpret_cast<uintptr_t>(p.out_data);
   const int nvb          = (p.ncols + 7) >> 3;
 
@@ -307,7 +332,8 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         oa = p.out_offsets[r + lane];
         ob = p.out_offsets[r + lane + 1];
       }
-      // ---- 2. string block sums (+ prefetch of the chars) -----------------------------------------------
+      // ---- 2. string block sums + staging of the tile's chars ---------------------------------------------
+      bool direct = p.slot_bytes == 0;
       for (int b = w; b < p.nblocks; b += kT3Warps) {
         const int s0 = b * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
         int32_t sum = 0;
@@ -324,16 +350,36 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (sA + j < s1 && lane < rem) {
+            if (sA + j < s1) {  // warp-uniform
+              const int sj = sA + j;
               sum += o1[j] - o0[j];
-#if T3_CPF
-              if (o1[j] > o0[j]) asm volatile("prefetch.global.L2 [%0];" ::"l"(s_chars[sA + j] + o0[j]));
-#endif
+              if (p.slot_bytes > 0) {
+                // stage the column's chars for rows [abs0, abs0 + rem): ONE contiguous global range, copied by
+                // 16-byte cp.async (no registers, no scoreboard) into the column's slot; only granules that hold
+                // at least one valid byte are read
+                const int32_t first = __shfl_sync(0xffffffffu, o0[j], 0);
+                const int32_t last  = __shfl_sync(0xffffffffu, o1[j], rem - 1);
+                if (last > first) {
+                  const uintptr_t cb = reinterpret_cast<uintptr_t>(s_chars[sj]);
+                  const uintptr_t g0 = (cb + static_cast<uint32_t>(first)) & ~uintptr_t{15};
+                  const uintptr_t g1 = (cb + static_cast<uint32_t>(last) + 15) & ~uintptr_t{15};
+                  const int64_t span = static_cast<int64_t>(g1 - g0);
+                  if (span > p.slot_bytes) {
+                    direct = true;
+                  } else {
+                    const uint32_t slot_s = stg_s + static_cast<uint32_t>(sj) * static_cast<uint32_t>(p.slot_bytes);
+                    for (int c = lane * 16; c < static_cast<int>(span); c += 512)
+                      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_s + c), "l"(g0 + c) : "memory");
+                    if (lane == 0) s_delta[sj] = static_cast<int32_t>(slot_s) - static_cast<int32_t>(static_cast<int64_t>(g0) - static_cast<int64_t>(cb));
+                  }
+                }
+              }
             }
           }
         }
         s_bsum[b * 32 + lane] = sum;
       }
+      if (direct && lane == 0) s_direct[tile_par] = 1;
       const int64_t lo      = static_cast<uint32_t>(__shfl_sync(0xffffffffu, oa, 0));
       const int skew        = static_cast<int>((out_g + lo) & 15);
       const int my_off      = static_cast<int>(static_cast<uint32_t>(oa) - static_cast<uint32_t>(lo)) + skew;
@@ -349,7 +395,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
       const bool act   = lane < rows;
       const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
       // ---- 3. buffer free -> zero fill -----------------------------------------------------------------
-      if (tid == 0) { tma_store_wait_read<0>(); s_next = 0; }
+      if (tid == 0) { tma_store_wait_read<0>(); s_next = 0; s_direct[tile_par ^ 1] = 0; }
       __syncthreads();
       if (w == kT3Warps - 1) {  // block sums -> exclusive prefix per row (published by the barrier below)
         int32_t acc = p.size_per_row;  // RC:838: chars start right behind the fixed section
@@ -365,7 +411,9 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         for (uint32_t a = image_s + 16u * tid; a < ze; a += 16u * kT3Threads)
           asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u));
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's slice of the chars staging has landed
       __syncthreads();
+      const bool tile_direct = s_direct[tile_par] != 0;
       // ---- 4. this warp's items ----------------------------------------------------------------------------
 #if T3_STATIC
       for (int qi = my_beg; qi < my_end_item; ++qi) {
@@ -402,7 +450,10 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
                   t3_sts_u32(pa, static_cast<uint32_t>(run));        // RC:848
                   t3_sts_u32(pa + 4, static_cast<uint32_t>(Ls[j]));  // RC:849
                 }
-                t3_copy_chars(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0[j]), row_s + static_cast<uint32_t>(run), Ls[j], rows, lane);
+                if (tile_direct)
+                  t3_copy_chars<false>(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0[j]), row_s + static_cast<uint32_t>(run), Ls[j], rows, lane);
+                else
+                  t3_copy_chars<true>(static_cast<uint32_t>(s_delta[s] + o0[j]), row_s + static_cast<uint32_t>(run), Ls[j], rows, lane);
                 run += Ls[j];
               }
             }
@@ -475,6 +526,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
           *reinterpret_cast<uint2*>(a) = *reinterpret_cast<const uint2*>(image + (a - fl));
       }
       r += rows;
+      tile_par ^= 1;
     }
   }
   if (tid == 0) tma_store_wait_all<0>();
@@ -515,10 +567,14 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   if (nitems > kT3MaxItems) return SRJ_OK;
   p.nitems = nitems;
   const size_t tables = sizeof(void*) * (static_cast<size_t>(p.nfixed) + p.ncols + 2 * static_cast<size_t>(nstr)) +
-                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + 2 * static_cast<size_t>(nitems)) +
+                        4 * (static_cast<size_t>(p.nfixed) + nstr + 32 * static_cast<size_t>(p.nblocks) + nstr + 2 * static_cast<size_t>(nitems)) +
                         ((static_cast<size_t>(nitems) + 15) & ~size_t{15}) + 32 + 128;
   const int64_t budget = 232448 / cps - 1024 - 64;
-  int64_t stage        = (budget - static_cast<int64_t>(tables)) / 16 * 16;
+  // chars staging: a quarter of the budget at most, 1 KB per STRING column at most
+  int64_t slot = std::min<int64_t>((budget - static_cast<int64_t>(tables)) / 4, 1024ll * nstr) / nstr / 16 * 16;
+  if (slot < 128 || getenv("SRJ_T3_NOSTAGE")) slot = 0;
+  p.slot_bytes         = static_cast<int32_t>(slot);
+  int64_t stage        = (budget - static_cast<int64_t>(tables) - slot * nstr) / 16 * 16;
   if (stage < 32 * 1024 || stage < 8ll * (plan->fixed_row_size + 64)) return SRJ_OK;
   const int64_t avg_row = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
   int fit               = static_cast<int>(std::min<int64_t>(32, stage / avg_row / 8 * 8));
@@ -547,7 +603,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int64_t nsuper = (row_count + p.super_rows - 1) / p.super_rows;
   const int64_t grid   = std::min<int64_t>(static_cast<int64_t>(cps) * nsm, nsuper);
-  const size_t smem    = static_cast<size_t>(stage) + 32 + tables;
+  const size_t smem    = static_cast<size_t>(stage) + 32 + static_cast<size_t>(slot) * nstr + tables;
   SRJ_CUDA_TRY(cudaMemsetAsync(d_fail_flag, 0, sizeof(int32_t), stream));
   if (cps == 1) {
     SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows3_kernel<24, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
