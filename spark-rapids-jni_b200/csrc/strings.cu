@@ -278,6 +278,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
@@ -491,74 +497,83 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
           // everything below addresses shared memory through 32-bit shared-space addresses (explicit
           // ld.shared / st.shared: the generic pointers above would compile to LD/ST + 64-bit math)
           const int a         = static_cast<int>(reinterpret_cast<uintptr_t>(D) & 15);
-          const int d         = a + pe;
+          const int d         = a + pe;                 // staging byte of this lane's string
           const int dsh       = d & 3;
           const uint32_t srcs = pay_s + static_cast<uint32_t>(rowsm_lane + run_before);
           const int ssh       = static_cast<int>(srcs & 3u);
-          const int dlt       = ssh - dsh;  // source byte offset of dst word 0, relative to the aligned source word
-          const uint32_t sp   = (srcs - ssh) + (dlt < 0 ? -4 : 0);
-          const int sh        = (dlt < 0 ? 4 + dlt : dlt) * 8;
+          const int dlt       = ssh - dsh;
+          const int pre       = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
+          const uint32_t sp   = srcs - pre;
+          const int sh        = (dlt & 3) * 8;
           const int end       = dsh + L;                 // one past the last staging byte, relative to word w0
-          const int kfull0    = dsh ? 1 : 0;             // first full word
-          const int kfull1    = end >> 2;                // one past the last full word
-          const uint32_t w0s  = stg_s + static_cast<uint32_t>(d & ~3);
-          const int Kmax      = (3 + maxL + 3) >> 2;     // warp-uniform bound on the words any lane touches
+          const int kfull1    = end >> 2;                // full words: [dsh ? 1 : 0, kfull1)
+          const uint32_t ds   = stg_s + static_cast<uint32_t>(d);
+          const uint32_t w0s  = ds - dsh;
+          const int lim       = L > 0 ? L + pre : 0;     // source word k overlaps the string iff 4k < lim
+          const int Kmax      = (maxL + 6) >> 2;         // warp-uniform bound on kfull1 (<= 9)
+          // edge bytes straight from the source: the first nh bytes when the string starts inside a staging word,
+          // the last nt bytes when it ends inside one
+          const int nh = dsh ? tmin(L, 4 - dsh) : 0;
+          const int nt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
+          uint32_t hb[3], tb[3];
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            hb[t] = tb[t] = 0;
+            if (t < nh) hb[t] = lds_u8(srcs + t);
+            if (t < nt) tb[t] = lds_u8(srcs + (L - nt) + t);
+          }
           // all source words first (independent loads), then shift + store
           uint32_t w[10];
 #pragma unroll
           for (int k = 0; k < 10; ++k) {
             w[k] = 0;
-            if (k <= Kmax && 4 * (k - 1) < end) w[k] = lds_u32(sp + 4 * k);
+            const bool need = k == 0 ? (lim > 0 && pre < 4) : (4 * k < lim);
+            if (need) w[k] = lds_u32(sp + 4 * k);
           }
-          uint32_t first = 0, lastw = 0;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            if (t < nh) sts_u8(ds + t, hb[t]);
+            if (t < nt) sts_u8(ds + (L - nt) + t, tb[t]);
+          }
 #pragma unroll
           for (int k = 0; k < 9; ++k) {
             if (k < Kmax) {
               const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
-              if (k >= kfull0 && k < kfull1) sts_u32(w0s + 4 * k, y);
-              if (k == 0) first = y;
-              if (k == kfull1) lastw = y;
+              const bool full  = k == 0 ? (dsh == 0 && kfull1 > 0) : (k < kfull1);
+              if (full) sts_u32(w0s + 4 * k, y);
             }
           }
-          if (L > 0) {
-            // head bytes [dsh, min(4, end)) of word 0 and tail bytes [0, end & 3) of word kfull1
-            const int hh = dsh ? tmin(end, 4) : 0;
-#pragma unroll
-            for (int t = 1; t < 4; ++t)
-              if (t >= dsh && t < hh) sts_u8(w0s + t, first >> (8 * t));
-            const int tt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
-#pragma unroll
-            for (int t = 0; t < 3; ++t)
-              if (t < tt) sts_u8(w0s + 4 * kfull1 + t, lastw >> (8 * t));
-          }
           __syncwarp();
+          // flush: whole 16-byte chunks inside [a, a+T) with one ld.shared.v4 / st.global.v4 per lane; the bytes of
+          // the two partial chunks at the ends (their neighbours belong to other tiles / warps) one per lane:
+          // lanes 0-15 the head chunk, lanes 16-31 the tail chunk
           uint8_t* Dal      = D - a;  // 16-byte aligned
-          const int nchunks = (a + T + 15) >> 4;
-          for (int c = lane; c < nchunks; c += 32) {
-            const int lo = c * 16, hi = lo + 16;
-            if (lo >= a && hi <= a + T) {
-              uint32_t v0, v1, v2, v3;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + lo));
-              asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + lo), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+          const int aT      = a + T;
+          const int c_first = (a + 15) >> 4;  // first whole chunk
+          const int c_end   = aT >> 4;        // one past the last whole chunk
+          for (int c = c_first + lane; c < c_end; c += 32) {
+            uint32_t v0, v1, v2, v3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
+            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+          }
+          {
+            // head chunk = chunk 0 when a > 0; tail chunk = chunk c_end when aT is not a multiple of 16.  When
+            // both are the same chunk (c_end == 0) the head lanes cover all of [a, aT).
+            const int hl = lane & 15;
+            int bpos;
+            bool ok;
+            if (lane < 16) {
+              bpos = hl;                                   // head chunk bytes [a, min(16, aT))
+              ok   = hl >= a && hl < tmin(16, aT) && a > 0;
+              if (a == 0 && c_end == 0) ok = hl < aT;      // a single partial chunk starting at an aligned byte
             } else {
-              // edge chunk: whole 4-byte words where they lie inside [a, a+T), single bytes at the two ends
-              // (the neighbouring bytes belong to other tiles / warps)
-              const int vlo = tmax(lo, a), vhi = tmin(hi, a + T);
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) {
-                const int wl = lo + 4 * w4, wh = wl + 4;
-                if (wl >= vlo && wh <= vhi) {
-                  uint32_t v;
-                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(stg_s + wl));
-                  asm volatile("st.global.u32 [%0], %1;" ::"l"(Dal + wl), "r"(v));
-                } else if (wh > vlo && wl < vhi) {
-                  for (int b = tmax(wl, vlo); b < tmin(wh, vhi); ++b) {
-                    uint32_t v;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + b));
-                    asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + b), "r"(v));
-                  }
-                }
-              }
+              bpos = 16 * c_end + hl;                      // tail chunk bytes [16 * c_end, aT)
+              ok   = c_end > 0 && bpos < aT;
+            }
+            if (ok) {
+              uint32_t v;
+              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + bpos));
+              asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + bpos), "r"(v));
             }
           }
           __syncwarp();
