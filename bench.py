@@ -60,6 +60,52 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def gpu_local_cpus(torch, index: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        return cpus or None
+    except Exception:
+        return None
+
+
+class NumaBind:
+    """Run the host side of the end-to-end leg on the GPU's NUMA node (what `numactl --cpunodebind` does for a
+    Spark executor pinned to its GPU): pinned buffers are first-touched there and the PCIe copies do not cross
+    the socket interconnect.  Restores the original affinity on exit (the CPU baseline uses every core)."""
+
+    def __init__(self, torch, index: int):
+        self.cpus = gpu_local_cpus(torch, index) if not os.environ.get("SRJ_BENCH_NO_NUMA") else None
+        self.prev = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.prev = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus & self.prev or self.prev)
+            except Exception:
+                self.prev = None
+        return self
+
+    def __exit__(self, *a):
+        if self.prev:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            except Exception:
+                pass
+        return False
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -309,38 +355,41 @@ def run_ours(args, wl, rank, world):
     e2e = None
     cpu = None
     if not args.no_e2e:
-        h_rows = torch.empty(n * row_size, dtype=torch.uint8, pin_memory=True)
-        h_rows.copy_(rows)
-        torch.cuda.synchronize()
-        h_cols = []
-        harr = (N.SrjColumn * len(types))()
-        for i, t in enumerate(types):
-            d = torch.empty(n * SIZE[t], dtype=torch.uint8, pin_memory=True)
-            m = torch.empty(words, dtype=torch.int32, pin_memory=True)
-            h_cols.append((d, m))
-            harr[i].type_id, harr[i].scale, harr[i].size = t, 0, n
-            harr[i].data, harr[i].null_mask, harr[i].offsets = d.data_ptr(), m.data_ptr(), None
-        h_nulls = np.zeros(len(types), np.int64)
-        h2d = n * row_size
-        d2h = sum(n * SIZE[t] + words * 4 for t in types) + 8 * len(types)
+        numa = NumaBind(torch, torch.cuda.current_device())
+        with numa:
+            h_rows = torch.empty(n * row_size, dtype=torch.uint8, pin_memory=True)
+            h_rows.copy_(rows)
+            torch.cuda.synchronize()
+            h_cols = []
+            harr = (N.SrjColumn * len(types))()
+            for i, t in enumerate(types):
+                d = torch.empty(n * SIZE[t], dtype=torch.uint8, pin_memory=True)
+                m = torch.empty(words, dtype=torch.int32, pin_memory=True)
+                h_cols.append((d, m))
+                harr[i].type_id, harr[i].scale, harr[i].size = t, 0, n
+                harr[i].data, harr[i].null_mask, harr[i].offsets = d.data_ptr(), m.data_ptr(), None
+            h_nulls = np.zeros(len(types), np.int64)
+            h2d = n * row_size
+            d2h = sum(n * SIZE[t] + words * 4 for t in types) + 8 * len(types)
 
-        def e2e_step():
-            N.check(lib.srj_convert_from_rows_host(plan.handle, h_rows.data_ptr(), n, harr, h_nulls.ctypes.data, 0))
+            def e2e_step():
+                N.check(lib.srj_convert_from_rows_host(plan.handle, h_rows.data_ptr(), n, harr, h_nulls.ctypes.data, 0))
 
-        e2e_step()                                   # warm-up (also validates)
-        assert torch.equal(h_cols[3][0], outs[3].data.cpu()), "bench e2e: host result differs from device result"
-        barrier()
-        ksteps = max(1, min(args.steps, 3))
-        w0 = time.perf_counter()
-        for _ in range(ksteps):
-            e2e_step()                               # synchronises internally (result is in host memory)
-        barrier()
-        e2e_s = (time.perf_counter() - w0) / ksteps
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": ksteps, "ms_per_step": float(te[0]) * 1e3, "api": "srj_convert_from_rows_host (pinned host buffers)"}
+            e2e_step()                                   # warm-up (also validates)
+            assert torch.equal(h_cols[3][0], outs[3].data.cpu()), "bench e2e: host result differs from device result"
+            barrier()
+            ksteps = max(1, min(args.steps, 3))
+            w0 = time.perf_counter()
+            for _ in range(ksteps):
+                e2e_step()                               # synchronises internally (result is in host memory)
+            barrier()
+            e2e_s = (time.perf_counter() - w0) / ksteps
+            te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "steps": ksteps, "ms_per_step": float(te[0]) * 1e3, "api": "srj_convert_from_rows_host (pinned host buffers)",
+                   "host_numa_bound": bool(numa.prev)}
         if rank == 0:
             cpu = cpu_baseline(types, row_size, h_rows.numpy(), min(n, args.cpu_sample_rows), bpr)
         del h_rows, h_cols
