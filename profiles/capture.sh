@@ -15,6 +15,7 @@ SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:
 SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:strings2_kernel -c 1 -o $O/prof_strings2_c3_$R python bench.py --workload c3 --rows 1000000 --no-e2e --steps 1 > /dev/null 2>&1
 SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:from_rows_kernel -c 1 -o $O/prof_from_rows_c4_$R python bench.py --workload c4 --rows 40000000 --no-e2e --steps 1 > /dev/null 2>&1
 $P --set full --import-source on -k regex:to_rows2_kernel -s 4 -c 1 -o $O/prof_to_rows2_c2_$R python profiles/time_to_rows.py c2 20000000 > /dev/null 2>&1
-SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:to_rows_kernel -c 1 -o $O/prof_to_rows_c3_$R python bench.py --workload c3 --direction to_rows --rows 1000000 --no-e2e --steps 1 > /dev/null 2>&1
+SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:to_rows3_kernel -c 1 -o $O/prof_to_rows3_c3_$R python bench.py --workload c3 --direction to_rows --rows 1000000 --no-e2e --steps 1 > /dev/null 2>&1
+SRJ_TR_GENERIC=1 SRJ_CUPROF=1 $P --profile-from-start off --set full --import-source on -k regex:to_rows_kernel -c 1 -o $O/prof_to_rows_generic_c3_$R python bench.py --workload c3 --direction to_rows --rows 1000000 --no-e2e --steps 1 > /dev/null 2>&1
 $P --set full --import-source on -k regex:row_hash -s 2 -c 1 -o $O/prof_hash_xx_$R python profiles/time_hash.py 100000000 > /dev/null 2>&1
 ls -la $O | tail -20
