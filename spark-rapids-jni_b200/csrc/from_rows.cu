@@ -499,8 +499,9 @@ __device__ __noinline__ void hash_tile(const HashSpec* hs, const uint8_t* base, 
 // Variable-width tables: does every row place its strings where convert_to_rows would (chars of the
 // STRING columns back to back, in column order, from byte size_per_row -- RC:838-858)?  Phase 2's fast
 // path relies on it; a mismatch only flips a status bit that routes phase 2 to the generic gather.
-// A warp takes a row, lane = STRING column: a row is canonical iff the first pair starts at size_per_row
-// and every pair starts where its left neighbour ends -- one shuffle per 32 columns, no scan.
+// A row is canonical iff the first pair starts at size_per_row and every pair starts where its left neighbour
+// ends: a purely local test.  lane = row; the (row group, block of STRING columns) items are dealt to the consumer
+// warps, each lane walking its block's pairs once -- ~5 instructions per string, the same cost for 1 or 64 columns.
 template <int NCW, bool SAFE>
 __device__ __noinline__ void canonical_check_tile(const uint8_t* base, const int32_t* s_off, int rows, int cw,
                                                   const int32_t* s_string_start, int nstr, int size_per_row,
@@ -509,24 +510,30 @@ __device__ __noinline__ void canonical_check_tile(const uint8_t* base, const int
   TileView tv;
   tv.base  = base;
   tv.s_off = s_off;
-  const int lane = lane_id();
-  bool bad       = false;
-  for (int row = cw; row < rows; row += NCW) {
-    const uint8_t* rp = row_ptr<true>(tv, row);
-    uint32_t expect   = static_cast<uint32_t>(size_per_row);
-    for (int s0 = 0; s0 < nstr; s0 += 32) {
-      const int s = s0 + lane;
-      uint32_t so = 0, ln = 0;
-      if (s < nstr) {
-        const uint8_t* pp = rp + s_string_start[s];
-        so                = static_cast<uint32_t>(load_key<SAFE>(pp, 4));
-        ln                = static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
+  const int lane    = lane_id();
+  const int ngroups = (rows + 31) >> 5;
+  const int nblk    = tmin(nstr, NCW);
+  const int nitems  = ngroups * nblk;
+  bool bad          = false;
+  for (int item = cw; item < nitems; item += NCW) {
+    const int g   = item / nblk;
+    const int b   = item - g * nblk;
+    const int s0  = (b * nstr) / nblk, s1 = ((b + 1) * nstr) / nblk;
+    const int row = g * 32 + lane;
+    if (row < rows) {
+      const uint8_t* rp = row_ptr<true>(tv, row);
+      uint32_t expect   = static_cast<uint32_t>(size_per_row);
+      if (s0 > 0) {
+        const uint8_t* pp = rp + s_string_start[s0 - 1];
+        expect            = static_cast<uint32_t>(load_key<SAFE>(pp, 4)) + static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
       }
-      const uint32_t end = so + ln;
-      uint32_t prev_end  = __shfl_up_sync(0xffffffffu, end, 1);
-      if (lane == 0) prev_end = expect;
-      if (s < nstr) bad |= so != prev_end;
-      expect = __shfl_sync(0xffffffffu, end, tmin(31, nstr - s0 - 1));
+      for (int s = s0; s < s1; ++s) {
+        const uint8_t* pp = rp + s_string_start[s];
+        const uint32_t so = static_cast<uint32_t>(load_key<SAFE>(pp, 4));
+        const uint32_t ln = static_cast<uint32_t>(load_key<SAFE>(pp + 4, 4));
+        bad |= so != expect;
+        expect = so + ln;
+      }
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(status, 1ull);

@@ -3,6 +3,7 @@
 //       per-column thrust::exclusive_scan + .element() sync loop of the reference (RC:2375-2395);
 //   (2) chars gather: replaces copy_strings_from_rows (RC:1110-1150).
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.hpp"
 #include "plan.hpp"
@@ -169,12 +170,17 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
   // runs only when phase 1 flagged non-canonical rows (or no status word was passed)
   if (status && !(*status & 1)) return;
   const int lane = lane_id();
-  const int w    = warp_id();
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // one task = (32-row tile, STRING column); tasks are dealt to the warps of the whole grid, so every warp is busy
+  // whatever the number of STRING columns (tables with 1-3 strings are the common case)
+  const int64_t ntasks = ntiles * nstr;
+  const int64_t wstep  = static_cast<int64_t>(gridDim.x) * kStrWarps;
+  for (int64_t task = static_cast<int64_t>(blockIdx.x) * kStrWarps + warp_id(); task < ntasks; task += wstep) {
+    const int64_t tile = task / nstr;
+    const int s        = static_cast<int>(task - tile * nstr);
     const int64_t r    = tile * 32 + lane;
     const bool active  = r < num_rows;
     const int64_t rsta = active ? (row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride) : 0;
-    for (int s = w; s < nstr; s += kStrWarps) {
+    {
       uint32_t so = 0, len = 0;
       int32_t d0 = 0;
       if (active) {
@@ -237,6 +243,7 @@ constexpr int kS2Front      = 16;   // slack before the payload (word reads may 
 constexpr int kS2Back       = 48;   // slack after it (word reads may run past a string)
 constexpr int kS2Slice      = 36;   // ints per offsets slice: rows + 1 <= 33, padded to 16-byte chunks
 constexpr int kS2StageLine  = 16 + 1024 + 32;  // per-warp staging line
+constexpr int kS2MinCols    = 16;   // fewer STRING columns: the generic task-parallel kernel
 constexpr int kS2MaxCols    = 160;  // offsets slices must fit shared memory
 
 struct S2Hdr {
@@ -623,7 +630,12 @@ int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const in
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const bool fast = d_status != nullptr && nstr <= kS2MaxCols;
+  // strings2 splits the STRING columns of a 32-row tile over its 19 consumer warps: it needs many columns to fill
+  // them.  Tables with few STRING columns take the task-parallel generic kernel (which follows the stored offsets,
+  // so it serves canonical and non-canonical rows alike).
+  const char* e_min  = getenv("SRJ_S2_MINCOLS");  // tuning knob (development)
+  const int min_cols = e_min ? atoi(e_min) : kS2MinCols;
+  const bool fast    = d_status != nullptr && nstr <= kS2MaxCols && nstr >= min_cols;
   if (fast) {
     S2Params p{};
     p.rows         = rows;
