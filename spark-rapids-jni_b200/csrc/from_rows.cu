@@ -621,21 +621,33 @@ __device__ __noinline__ void producer_loop(const ProducerArgs p)
         g_hi = (r + rows) * static_cast<int64_t>(p.row_stride);
         if (g_hi - g_lo > p.stage_bytes) safe = true;
       } else {
-        // load off[r .. r+rows] (coalesced) and pick the largest multiple-of-8 row count that fits
-        const int64_t a0   = p.row_offsets[r];
+        // load off[r .. r+rows] (coalesced) and pick the largest multiple-of-8 row count that fits.  All the loads
+        // are issued before the first use: one memory round trip per tile, not one per 32 rows (a 512-row tile of
+        // a narrow table spent 10 us here, 7x the time its consumers need).
+        constexpr int kMaxChunks = 17;  // tile_rows <= 512 -> rows + 1 <= 513 offsets
+        rows = tmin(rows, 512);
+        int32_t ov[kMaxChunks];
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+          const int i = k * 32 + lane;
+          ov[k]       = (i <= rows) ? p.row_offsets[r + i] : 0;
+        }
+        const int64_t a0   = static_cast<uint32_t>(__shfl_sync(0xffffffffu, ov[0], 0));
         const int64_t base = a0 - static_cast<int64_t>((reinterpret_cast<uintptr_t>(p.rows) + a0) & 15);
         int fit            = 0;
         bool misaligned    = (a0 & 7) != 0;
-        for (int i0 = 0; i0 <= rows; i0 += 32) {
-          const int i = i0 + lane;
-          int64_t o   = 0;
-          if (i <= rows) {
-            o             = p.row_offsets[r + i];
-            s_next_off[i] = static_cast<int32_t>(o - base);
-            if (i < rows && (o & 7)) misaligned = true;
+#pragma unroll
+        for (int k = 0; k < kMaxChunks; ++k) {
+          if (k * 32 <= rows) {  // warp-uniform
+            const int i     = k * 32 + lane;
+            const int64_t o = static_cast<uint32_t>(ov[k]);
+            if (i <= rows) {
+              s_next_off[i] = static_cast<int32_t>(o - base);
+              if (i < rows && (o & 7)) misaligned = true;
+            }
+            const bool ok = (i >= 1) && (i <= rows) && (round_up64(o - base, 16) <= p.stage_bytes + 16);
+            fit += __popc(__ballot_sync(0xffffffffu, ok));
           }
-          const bool ok = (i >= 1) && (i <= rows) && (round_up64(o - base, 16) <= p.stage_bytes + 16);
-          fit += __popc(__ballot_sync(0xffffffffu, ok));
         }
         misaligned = __any_sync(0xffffffffu, misaligned);
         if (fit < rows) fit &= ~7;
@@ -649,7 +661,8 @@ __device__ __noinline__ void producer_loop(const ProducerArgs p)
           rows = fit;
         }
         g_lo = a0;
-        g_hi = p.row_offsets[r + rows];
+        __syncwarp();
+        g_hi = safe ? static_cast<int64_t>(s_next_off[rows]) : base + s_next_off[rows];
       }
       g_rows = rows;
       g_safe = safe;

@@ -192,54 +192,47 @@ __device__ __forceinline__ void assemble_tile(const ToRowsParams& p, const TrTab
   if (p.nstr > 0) {
     const int nstr = p.nstr;
     const int nent = rows * nstr;
-    // S1: (src offset, len) of every (row, string column); lanes run over rows => coalesced offsets
+    // The per-tile string tables are laid out [string column][row] (index = s * rows + row): consecutive threads
+    // touch consecutive words in every step.
+    // S1: (src offset, len) of every (row, string column); threads run over rows => coalesced offsets
     for (int idx = tid; idx < nent; idx += kTrThreads) {
       const int s           = idx / rows;
       const int row         = idx - s * rows;
       const int32_t* so     = p.str_offsets[s] + abs0 + row;
       const int32_t o0      = __ldg(so);
       const int32_t o1      = __ldg(so + 1);
-      t.str_src[row * nstr + s] = o0;
-      t.str_len[row * nstr + s] = o1 - o0;
+      t.str_src[idx]        = o0;
+      t.str_len[idx]        = o1 - o0;
     }
     __syncthreads();
-    // S2: warp per row: running offset across the row's string columns, pairs into the row image
-    for (int row = w; row < rows; row += kTrWarps) {
+    // S2: thread per row: running offset across the row's string columns (RC:838-858), pairs into the row image.
+    // (A warp per row with a 32-lane scan cost 66 warp instructions per ROW whatever the number of columns.)
+    for (int row = tid; row < rows; row += kTrThreads) {
       uint32_t run = static_cast<uint32_t>(p.size_per_row);  // RC:838
       uint8_t* rp  = rowptr(row);
-      for (int s0 = 0; s0 < nstr; s0 += 32) {
-        const int s        = s0 + lane;
-        const uint32_t len = s < nstr ? static_cast<uint32_t>(t.str_len[row * nstr + s]) : 0u;
-        uint32_t x         = len;
+      for (int s = 0; s < nstr; ++s) {
+        const int e        = s * rows + row;
+        const uint32_t len = static_cast<uint32_t>(t.str_len[e]);
+        t.str_dst[e]       = static_cast<int32_t>(run);
+        uint8_t* pp        = rp + p.string_start[s];
+        if constexpr (SAFE) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-          if (lane >= o) x += y;
+          for (int i = 0; i < 4; ++i) { pp[i] = static_cast<uint8_t>(run >> (8 * i)); pp[4 + i] = static_cast<uint8_t>(len >> (8 * i)); }
+        } else {
+          reinterpret_cast<uint32_t*>(pp)[0] = run;  // RC:848
+          reinterpret_cast<uint32_t*>(pp)[1] = len;  // RC:849
         }
-        const uint32_t off = run + x - len;
-        if (s < nstr) {
-          t.str_dst[row * nstr + s] = static_cast<int32_t>(off);
-          uint8_t* pp               = rp + p.string_start[s];
-          if constexpr (SAFE) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { pp[i] = static_cast<uint8_t>(off >> (8 * i)); pp[4 + i] = static_cast<uint8_t>(len >> (8 * i)); }
-          } else {
-            reinterpret_cast<uint32_t*>(pp)[0] = off;  // RC:848
-            reinterpret_cast<uint32_t*>(pp)[1] = len;  // RC:849
-          }
-        }
-        run += __shfl_sync(0xffffffffu, x, 31);
+        run += len;
       }
     }
     __syncthreads();
-    // S3: chars.  Thread per (row, string): adjacent lanes read adjacent strings of one column.
+    // S3: chars.  Thread per (row, string): adjacent threads read adjacent strings of one column.
     for (int idx = tid; idx < nent; idx += kTrThreads) {
       const int s        = idx / rows;
       const int row      = idx - s * rows;
-      const int e        = row * nstr + s;
-      const int32_t len  = t.str_len[e];
-      const uint8_t* src = p.str_chars[s] + t.str_src[e];
-      uint8_t* dst       = rowptr(row) + static_cast<uint32_t>(t.str_dst[e]);
+      const int32_t len  = t.str_len[idx];
+      const uint8_t* src = p.str_chars[s] + t.str_src[idx];
+      uint8_t* dst       = rowptr(row) + static_cast<uint32_t>(t.str_dst[idx]);
       for (int32_t i = 0; i < len; ++i) dst[i] = __ldg(src + i);
     }
   }
