@@ -160,7 +160,108 @@ int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_strin
 // destination range -- with lane = destination byte, locating the source row by a shuffle search.
 // Destination stores are fully coalesced; source reads stay inside 2-3 sectors per instruction.
 // --------------------------------------------------------------------------------------------------
+
+// ---- shared-memory helpers of the chars gathers (32-bit shared-space addresses) ----------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+// A warp's staging line holds the T chars of one (32-row tile, column) at the byte positions [a, a + T), a = the
+// destination's offset inside its 16-byte granule.  Flush: whole 16-byte chunks with one ld.shared.v4 /
+// st.global.v4 per lane; the bytes of the two partial chunks at the ends (their neighbours belong to other tiles /
+// warps) one per lane: lanes 0-15 the head chunk, lanes 16-31 the tail chunk.
+__device__ __forceinline__ void flush_staging_line(uint32_t stg_s, uint8_t* D, int a, int T, int lane)
+{
+  uint8_t* Dal      = D - a;  // 16-byte aligned
+  const int aT      = a + T;
+  const int c_first = (a + 15) >> 4;  // first whole chunk
+  const int c_end   = aT >> 4;        // one past the last whole chunk
+  for (int c = c_first + lane; c < c_end; c += 32) {
+    uint32_t v0, v1, v2, v3;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+  }
+  // head chunk = chunk 0 when a > 0; tail chunk = chunk c_end when aT is not a multiple of 16.  When both are the
+  // same chunk (c_end == 0) the head lanes cover all of [a, aT).
+  const int hl = lane & 15;
+  int bpos;
+  bool ok;
+  if (lane < 16) {
+    bpos = hl;                                   // head chunk bytes [a, min(16, aT))
+    ok   = hl >= a && hl < tmin(16, aT) && a > 0;
+    if (a == 0 && c_end == 0) ok = hl < aT;      // a single partial chunk starting at an aligned byte
+  } else {
+    bpos = 16 * c_end + hl;                      // tail chunk bytes [16 * c_end, aT)
+    ok   = c_end > 0 && bpos < aT;
+  }
+  if (ok) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + bpos));
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + bpos), "r"(v));
+  }
+}
+
+// lane's string = L bytes at GLOBAL address S -> staging byte ds (shared address).  Aligned 32-bit source words
+// (only words that overlap the string are read), funnel shift to the staging alignment, st.shared.u32 for whole
+// words; the <= 3 edge bytes at each end come straight from the source.  maxL (<= 32) is the warp's longest string.
+__device__ __forceinline__ void copy_global_to_staging(uint64_t S, uint32_t ds, int L, int maxL)
+{
+  const int dsh      = static_cast<int>(ds & 3u);
+  const int ssh      = static_cast<int>(S & 3u);
+  const int dlt      = ssh - dsh;
+  const int pre      = ssh + (dlt < 0 ? 4 : 0);
+  const uint64_t sp  = S - pre;
+  const int sh       = (dlt & 3) * 8;
+  const int end      = dsh + L;
+  const int kfull1   = end >> 2;
+  const uint32_t w0s = ds - dsh;
+  const int lim      = L > 0 ? L + pre : 0;
+  const int Kmax     = (maxL + 6) >> 2;
+  const int nh       = dsh ? tmin(L, 4 - dsh) : 0;
+  const int nt       = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
+  const uint8_t* Sb  = reinterpret_cast<const uint8_t*>(S);
+  uint32_t hb[3], tb[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    hb[t] = tb[t] = 0;
+    if (t < nh) hb[t] = __ldg(Sb + t);
+    if (t < nt) tb[t] = __ldg(Sb + (L - nt) + t);
+  }
+  uint32_t w[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    w[k]            = 0;
+    const bool need = k == 0 ? (lim > 0 && pre < 4) : (4 * k < lim);
+    if (need) w[k] = __ldg(reinterpret_cast<const uint32_t*>(sp + 4 * k));
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t < nh) sts_u8(ds + t, hb[t]);
+    if (t < nt) sts_u8(ds + (L - nt) + t, tb[t]);
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (k < Kmax) {
+      const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+      const bool full  = k == 0 ? (dsh == 0 && kfull1 > 0) : (k < kfull1);
+      if (full) sts_u32(w0s + 4 * k, y);
+    }
+  }
+}
+
 constexpr int kStrWarps = 8;
+constexpr int kStrLine  = 16 + 1024 + 32;  // per-warp staging line
 
 __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
   const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets, int64_t row_stride, int64_t num_rows,
@@ -169,7 +270,9 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
 {
   // runs only when phase 1 flagged non-canonical rows (or no status word was passed)
   if (status && !(*status & 1)) return;
-  const int lane = lane_id();
+  __shared__ __align__(16) uint8_t s_line[kStrWarps * kStrLine];
+  const int lane       = lane_id();
+  const uint32_t stg_s = smem_u32(s_line + warp_id() * kStrLine);
   // one task = (32-row tile, STRING column); tasks are dealt to the warps of the whole grid, so every warp is busy
   // whatever the number of STRING columns (tables with 1-3 strings are the common case)
   const int64_t ntasks = ntiles * nstr;
@@ -201,6 +304,19 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
       const uint32_t total = __shfl_sync(0xffffffffu, pe + len, last);
       const int64_t srcoff = rsta + so;
       uint8_t* dst         = chars[s] + dbase;
+      const int maxL       = __reduce_max_sync(0xffffffffu, active ? static_cast<int>(tmin<uint32_t>(len, 1u << 20)) : 0);
+      if (total == 0) continue;
+      if (maxL <= 32 && total <= 1024) {
+        // short strings (the common case): lane = row copies its string into the warp's staging line, laid out
+        // like the destination, and the line leaves with 16-byte stores
+        const int a = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);
+        copy_global_to_staging(reinterpret_cast<uint64_t>(rows) + static_cast<uint64_t>(srcoff), stg_s + static_cast<uint32_t>(a) + pe,
+                               active ? static_cast<int>(len) : 0, maxL);
+        __syncwarp();
+        flush_staging_line(stg_s, dst, a, static_cast<int>(total), lane);
+        __syncwarp();
+        continue;
+      }
       const uint32_t bound = (total + 31u) & ~31u;  // all lanes take part in the shuffles
       for (uint32_t p = lane; p < bound; p += 32) {
         int j = 0;
@@ -243,7 +359,7 @@ constexpr int kS2Front      = 16;   // slack before the payload (word reads may 
 constexpr int kS2Back       = 48;   // slack after it (word reads may run past a string)
 constexpr int kS2Slice      = 36;   // ints per offsets slice: rows + 1 <= 33, padded to 16-byte chunks
 constexpr int kS2StageLine  = 16 + 1024 + 32;  // per-warp staging line
-constexpr int kS2MinCols    = 16;   // fewer STRING columns: the generic task-parallel kernel
+constexpr int kS2MinCols    = 32;   // fewer STRING columns: the generic task-parallel kernel
 constexpr int kS2MaxCols    = 160;  // offsets slices must fit shared memory
 
 struct S2Hdr {
@@ -279,20 +395,6 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_constant__ S2Params p)
 {
@@ -551,38 +653,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
             }
           }
           __syncwarp();
-          // flush: whole 16-byte chunks inside [a, a+T) with one ld.shared.v4 / st.global.v4 per lane; the bytes of
-          // the two partial chunks at the ends (their neighbours belong to other tiles / warps) one per lane:
-          // lanes 0-15 the head chunk, lanes 16-31 the tail chunk
-          uint8_t* Dal      = D - a;  // 16-byte aligned
-          const int aT      = a + T;
-          const int c_first = (a + 15) >> 4;  // first whole chunk
-          const int c_end   = aT >> 4;        // one past the last whole chunk
-          for (int c = c_first + lane; c < c_end; c += 32) {
-            uint32_t v0, v1, v2, v3;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
-            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
-          }
-          {
-            // head chunk = chunk 0 when a > 0; tail chunk = chunk c_end when aT is not a multiple of 16.  When
-            // both are the same chunk (c_end == 0) the head lanes cover all of [a, aT).
-            const int hl = lane & 15;
-            int bpos;
-            bool ok;
-            if (lane < 16) {
-              bpos = hl;                                   // head chunk bytes [a, min(16, aT))
-              ok   = hl >= a && hl < tmin(16, aT) && a > 0;
-              if (a == 0 && c_end == 0) ok = hl < aT;      // a single partial chunk starting at an aligned byte
-            } else {
-              bpos = 16 * c_end + hl;                      // tail chunk bytes [16 * c_end, aT)
-              ok   = c_end > 0 && bpos < aT;
-            }
-            if (ok) {
-              uint32_t v;
-              asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + bpos));
-              asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + bpos), "r"(v));
-            }
-          }
+          flush_staging_line(stg_s, D, a, T, lane);
           __syncwarp();
         } else {
           // ---- slow: long strings / SAFE tiles: lane = destination byte, source row by shuffle search ----
