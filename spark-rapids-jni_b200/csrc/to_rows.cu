@@ -405,6 +405,13 @@ __global__ void __launch_bounds__(kTrThreads, 4) to_rows_kernel(const __grid_con
 constexpr int kT2Consumers = 11;
 constexpr int kT2Threads   = (kT2Consumers + 1) * 32;
 constexpr int kT2MaxStages = 3;
+constexpr int kT2Super     = 4;  // consecutive tiles a CTA takes before the round-robin moves on (longer contiguous
+                                 // pieces per column and per CTA: see the from_rows super-tiles)
+__device__ __forceinline__ int64_t t2_first_tile() { return static_cast<int64_t>(blockIdx.x) * kT2Super; }
+__device__ __forceinline__ int64_t t2_next_tile(int64_t tile)
+{
+  return ((tile + 1) % kT2Super) ? tile + 1 : tile + 1 + static_cast<int64_t>(gridDim.x - 1) * kT2Super;
+}
 
 struct ToRows2Params {
   const void* const* col_data;
@@ -539,7 +546,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) to_rows2_kernel(const __grid_co
   if (warp_id() == 0) {
     // =================================== producer ===================================
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = t2_first_tile(); tile < p.num_tiles; tile = t2_next_tile(tile), ++it) {
       const int s        = it % NS;
       const uint32_t par = ((it / NS) & 1) ^ 1;
       if (lane == 0) {
@@ -566,7 +573,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) to_rows2_kernel(const __grid_co
     const int ng32   = p.R >> 5;
     const int vitems = nq * ng32;
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = t2_first_tile(); tile < p.num_tiles; tile = t2_next_tile(tile), ++it) {
       const int s        = it % NS;
       const uint32_t par = (it / NS) & 1;
       const int b        = it & 1;
@@ -862,7 +869,7 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
     int dev = 0, nsm = 0;
     SRJ_CUDA_TRY(cudaGetDevice(&dev));
     SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    const int64_t grid = std::min<int64_t>(nsm, p.num_tiles);
+    const int64_t grid = std::min<int64_t>(nsm, (p.num_tiles + kT2Super - 1) / kT2Super);
     size_t smem        = static_cast<size_t>(NS) * R * D + 2 * static_cast<size_t>(R) * S + 2 * kT2MaxStages * 8;
     smem += static_cast<size_t>(p.nentries) * (4 + 4 + 8 + 4) + 8 + static_cast<size_t>(p.ncols) * 8 + 64;
     smem = (smem + 127) & ~size_t{127};
