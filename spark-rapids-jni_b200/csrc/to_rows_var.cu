@@ -532,6 +532,217 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   if (tid == 0) tma_store_wait_all<0>();
 }
 
+
+// ==================================================================================================
+// Narrow rows with STRING columns (a few hundred bytes per row -- the common Spark shape): every warp owns a private
+// row-image buffer and converts 32-row tiles on its own: no CTA barrier anywhere in the tile loop.
+//   lane = row: LIST offsets -> geometry; zero the image; fixed-width fields by cp.async (4/8/16 B) or LDG/STS
+//   (1/2 B); validity by the 32x32 bit butterfly; per STRING column the (offset, len) pair and the chars (aligned
+//   32-bit words from global, funnel-shifted, see t3_copy_chars); then the warp flushes its image -- ONE contiguous
+//   byte range of the output -- with 16-byte coalesced stores.
+// A tile whose rows do not fit the warp's buffer raises *fail_flag (generic kernel redoes the batch).
+// ==================================================================================================
+constexpr int kTwWarps = 24;
+constexpr bool kWarpKernelDefault = false;  // flipped once the GPU parity tests have run on it
+
+struct ToRowsWParams {
+  const void* const* col_data;
+  const uint32_t* const* masks;
+  const int32_t* const* str_offsets;
+  const uint8_t* const* str_chars;
+  int64_t row_start, row_count;
+  const int32_t* out_offsets;
+  uint8_t* out_data;
+  int32_t ncols, nstr, nfixed;
+  int32_t validity_offset, size_per_row;
+  int32_t wbuf_bytes;  // per-warp image bytes (multiple of 16)
+  int32_t class_begin[kNumClasses + 1];
+  const Entry* entries;
+  const int32_t* string_start;
+  int32_t* fail_flag;
+};
+
+__global__ void __launch_bounds__(kTwWarps * 32, 1) to_rows_w_kernel(const __grid_constant__ ToRowsWParams p)
+{
+  constexpr int kThreads = kTwWarps * 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* q = smem + static_cast<size_t>(kTwWarps) * (p.wbuf_bytes + 32);
+  const uint8_t** s_ent_ptr = reinterpret_cast<const uint8_t**>(q);  q += sizeof(void*) * p.nfixed;
+  const uint32_t** s_mask   = reinterpret_cast<const uint32_t**>(q); q += sizeof(void*) * p.ncols;
+  const int32_t** s_soff    = reinterpret_cast<const int32_t**>(q);  q += sizeof(void*) * p.nstr;
+  const uint8_t** s_chars   = reinterpret_cast<const uint8_t**>(q);  q += sizeof(void*) * p.nstr;
+  int32_t* s_ent_start      = reinterpret_cast<int32_t*>(q);         q += 4 * p.nfixed;
+  int32_t* s_sstart         = reinterpret_cast<int32_t*>(q);
+
+  const int tid  = threadIdx.x;
+  const int lane = lane_id();
+  const int w    = warp_id();
+  for (int i = tid; i < p.nfixed; i += kThreads) {
+    const Entry e  = p.entries[i];
+    s_ent_ptr[i]   = static_cast<const uint8_t*>(p.col_data[e.column]);
+    s_ent_start[i] = e.start;
+  }
+  for (int i = tid; i < p.ncols; i += kThreads) s_mask[i] = p.masks[i];
+  for (int i = tid; i < p.nstr; i += kThreads) {
+    s_soff[i]   = p.str_offsets[i];
+    s_chars[i]  = p.str_chars[i];
+    s_sstart[i] = p.string_start[i];
+  }
+  __syncthreads();
+  uint8_t* image         = smem + static_cast<size_t>(w) * (p.wbuf_bytes + 32);
+  const uint32_t image_s = smem_u32(image);
+  const uintptr_t out_g  = reinterpret_cast<uintptr_t>(p.out_data);
+  const int nvb          = (p.ncols + 7) >> 3;
+  const int ngv          = (p.ncols + 31) >> 5;
+
+  // 32-row groups are dealt to the warps of the grid; a group takes one or more tiles (rows that fit the buffer)
+  const int64_t ngroups = (p.row_count + 31) >> 5;
+  const int64_t gstep   = static_cast<int64_t>(gridDim.x) * kTwWarps;
+  for (int64_t grp = static_cast<int64_t>(blockIdx.x) * kTwWarps + w; grp < ngroups; grp += gstep) {
+    int64_t r          = grp * 32;
+    const int64_t rend = tmin<int64_t>(p.row_count, r + 32);
+    while (r < rend) {
+      const int rem      = static_cast<int>(rend - r);
+      const int64_t abs0 = p.row_start + r;
+      int32_t oa = 0, ob = 0;
+      if (lane < rem) {
+        oa = p.out_offsets[r + lane];
+        ob = p.out_offsets[r + lane + 1];
+      }
+      const int64_t lo = static_cast<uint32_t>(__shfl_sync(0xffffffffu, oa, 0));
+      const int skew   = static_cast<int>((out_g + lo) & 15);
+      const int my_off = static_cast<int>(static_cast<uint32_t>(oa) - static_cast<uint32_t>(lo)) + skew;
+      const int my_end = static_cast<int>(static_cast<uint32_t>(ob) - static_cast<uint32_t>(lo)) + skew;
+      const bool fits  = lane < rem && my_end <= p.wbuf_bytes;
+      int rows         = __popc(__ballot_sync(0xffffffffu, fits));
+      if (rows == 0) {  // a row larger than the warp's buffer: the generic kernel redoes the batch
+        if (lane == 0) atomicExch(p.fail_flag, 1);
+        return;
+      }
+      const int hi_rel     = __shfl_sync(0xffffffffu, my_end, rows - 1);
+      const bool act       = lane < rows;
+      const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
+      // ---- zero fill (padding bytes are 0) ------------------------------------------------------------
+      for (uint32_t a = image_s + 16u * lane; a < image_s + static_cast<uint32_t>(hi_rel); a += 512u)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u));
+      __syncwarp();
+      // ---- fixed-width fields -------------------------------------------------------------------------
+      const int64_t ar = abs0 + lane;
+      for (int e = p.class_begin[4]; e < p.class_begin[5]; e += 8) t3_fixed_async<16, 8>(s_ent_ptr, s_ent_start, e, tmin(8, p.class_begin[5] - e), ar, act, row_s);
+      for (int e = p.class_begin[3]; e < p.class_begin[4]; e += 8) t3_fixed_async<8, 8>(s_ent_ptr, s_ent_start, e, tmin(8, p.class_begin[4] - e), ar, act, row_s);
+      for (int e = p.class_begin[2]; e < p.class_begin[3]; e += 8) t3_fixed_async<4, 8>(s_ent_ptr, s_ent_start, e, tmin(8, p.class_begin[3] - e), ar, act, row_s);
+      for (int e = p.class_begin[1]; e < p.class_begin[2]; e += 4) t3_fixed<2, 4>(s_ent_ptr, s_ent_start, e, tmin(4, p.class_begin[2] - e), ar, act, row_s);
+      for (int e = p.class_begin[0]; e < p.class_begin[1]; e += 4) t3_fixed<1, 4>(s_ent_ptr, s_ent_start, e, tmin(4, p.class_begin[1] - e), ar, act, row_s);
+      // ---- validity -----------------------------------------------------------------------------------
+      for (int g = 0; g < ngv; ++g) {
+        const int c   = g * 32 + lane;
+        uint32_t bits = 0;
+        if (c < p.ncols) {
+          const uint32_t* m = s_mask[c];
+          if (m == nullptr) {
+            bits = 0xffffffffu;
+          } else {
+            const int64_t wi  = abs0 >> 5;
+            const int shb     = static_cast<int>(abs0 & 31);
+            const uint32_t w0 = __ldg(m + wi);
+            uint32_t w1       = 0;
+            if (shb != 0 && ((abs0 + rows - 1) >> 5) > wi) w1 = __ldg(m + wi + 1);
+            bits = __funnelshift_r(w0, w1, shb);
+          }
+        }
+        const uint32_t t = t3_transpose32(bits, lane);  // lane = row: bit j = column g*32 + j
+        if (act) {
+          const uint32_t a = row_s + static_cast<uint32_t>(p.validity_offset + g * 4);
+          const int nb     = tmin(4, nvb - g * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < nb) t3_sts_u8(a + k, t >> (8 * k));
+        }
+      }
+      // ---- strings: pairs + chars (RC:838-858) ---------------------------------------------------------
+      int32_t run = p.size_per_row;
+      for (int s = 0; s < p.nstr; ++s) {
+        int32_t o0 = 0, L = 0;
+        if (act) {
+          const int32_t* so = s_soff[s] + abs0 + lane;
+          o0                = __ldg(so);
+          L                 = tmax(__ldg(so + 1) - o0, 0);
+          const uint32_t pa = row_s + static_cast<uint32_t>(s_sstart[s]);
+          t3_sts_u32(pa, static_cast<uint32_t>(run));
+          t3_sts_u32(pa + 4, static_cast<uint32_t>(L));
+        }
+        t3_copy_chars<false>(reinterpret_cast<uintptr_t>(s_chars[s]) + static_cast<uint32_t>(o0), row_s + static_cast<uint32_t>(run), L, rows, lane);
+        run += L;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+      // ---- flush: the image is one contiguous byte range of the output ------------------------------------
+      {
+        const uintptr_t g_lo = out_g + lo;
+        const uintptr_t g_hi = g_lo + (hi_rel - skew);
+        const uintptr_t fl   = g_lo - skew;  // global address of image byte 0 (16-byte aligned)
+        const uintptr_t t_lo = (g_lo + 15) & ~uintptr_t{15};
+        const uintptr_t t_hi = tmax(g_hi & ~uintptr_t{15}, t_lo);
+        for (uintptr_t a = t_lo + 16u * lane; a < t_hi; a += 512) {
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(image_s + static_cast<uint32_t>(a - fl)));
+          asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+        }
+        // rows are 8-byte aligned: at most one 8-byte piece before the first and after the last 16-byte chunk
+        if (lane == 0 && g_lo < tmin(t_lo, g_hi)) *reinterpret_cast<uint2*>(g_lo) = *reinterpret_cast<const uint2*>(image + (g_lo - fl));
+        if (lane == 1 && t_hi < g_hi && t_hi >= t_lo && g_hi > t_lo) *reinterpret_cast<uint2*>(t_hi) = *reinterpret_cast<const uint2*>(image + (t_hi - fl));
+      }
+      __syncwarp();  // the image is reused by the next tile
+      r += rows;
+    }
+  }
+}
+
+static int launch_to_rows_warp(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
+                               const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
+                               int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t avg_row,
+                               int32_t* d_fail_flag, cudaStream_t stream, int* launched)
+{
+  const int nstr = plan->num_string_columns;
+  ToRowsWParams p{};
+  p.nfixed = static_cast<int32_t>(plan->tr_entries.size());
+  p.ncols  = plan->num_columns;
+  p.nstr   = nstr;
+  const size_t tables = sizeof(void*) * (static_cast<size_t>(p.nfixed) + p.ncols + 2 * static_cast<size_t>(nstr)) +
+                        4 * (static_cast<size_t>(p.nfixed) + nstr) + 128;
+  const int64_t budget = 232448 - 1024 - 64 - static_cast<int64_t>(tables);
+  const int64_t wbuf   = (budget / kTwWarps - 32) / 16 * 16;
+  // want >= 16 rows per tile on average (half the lanes busy), and at least one maximal fixed section
+  if (wbuf < 1024 || wbuf < plan->fixed_row_size + 64 || avg_row * 16 > wbuf) return SRJ_OK;
+  p.col_data        = d_col_data;
+  p.masks           = d_masks;
+  p.str_offsets     = d_str_offsets;
+  p.str_chars       = d_str_chars;
+  p.row_start       = row_start;
+  p.row_count       = row_count;
+  p.out_offsets     = out_offsets;
+  p.out_data        = out_data;
+  p.validity_offset = plan->validity_offset;
+  p.size_per_row    = plan->size_per_row;
+  p.wbuf_bytes      = static_cast<int32_t>(wbuf);
+  for (int k = 0; k <= kNumClasses; ++k) p.class_begin[k] = plan->tr_class_begin[k];
+  p.entries      = plan->d_tr_entries;
+  p.string_start = plan->d_string_start;
+  p.fail_flag    = d_fail_flag;
+  int dev = 0, nsm = 0;
+  SRJ_CUDA_TRY(cudaGetDevice(&dev));
+  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t ngroups = (row_count + 31) / 32;
+  const int64_t grid    = std::min<int64_t>(nsm, (ngroups + kTwWarps - 1) / kTwWarps);
+  const size_t smem     = static_cast<size_t>(kTwWarps) * (wbuf + 32) + tables;
+  SRJ_CUDA_TRY(cudaMemsetAsync(d_fail_flag, 0, sizeof(int32_t), stream));
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(to_rows_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+  to_rows_w_kernel<<<static_cast<unsigned>(grid), kTwWarps * 32, smem, stream>>>(p);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  *launched = 1;
+  return SRJ_OK;
+}
+
 // Returns SRJ_OK and sets *launched when the kernel was launched (the caller then launches the generic kernel
 // guarded by d_fail_flag); *launched = 0 means the table is not eligible.
 int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
@@ -548,6 +759,15 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   for (const Entry& e : plan->tr_entries)
     if (reinterpret_cast<uintptr_t>(h_col_data[e.column]) & static_cast<uintptr_t>(plan->col_size[e.column] - 1)) return SRJ_OK;
 
+  {
+    // narrow rows: warp-private tiles (to_rows_w_kernel); wide rows: CTA tiles (to_rows3_kernel) below
+    const int64_t avg = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
+    if (!force && !getenv("SRJ_TR_NOWARP") && kWarpKernelDefault) {
+      const int rc = launch_to_rows_warp(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets,
+                                         out_data, avg, d_fail_flag, stream, launched);
+      if (rc != SRJ_OK || *launched) return rc;
+    }
+  }
   ToRows3Params p{};
   p.nfixed  = static_cast<int32_t>(plan->tr_entries.size());
   p.ncols   = plan->num_columns;

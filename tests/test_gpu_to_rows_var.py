@@ -100,3 +100,27 @@ def test_medium_rows_use_partial_tiles(force_var):
         cols.append(O.strings_col(vals))
     cols.append(O.HCol(O.INT64, rng.integers(0, 2**62, n).astype(np.int64).view(np.uint8), None, None, 0, n))
     _check(cols)
+
+
+# ---- narrow rows: the warp-private kernel (to_rows_w_kernel) is picked by the launcher's own rule -------------------
+@pytest.mark.parametrize("nrows", [1, 31, 32, 33, 1000, 50_003])
+@pytest.mark.parametrize("name", ["simple_string", "double_string", "mixed", "c3_small", "all_widths"])
+def test_narrow_rows_pick_the_warp_kernel(name, nrows):
+    _check(random_table(SCHEMAS[name], nrows, seed=nrows + 7))
+
+
+def test_narrow_rows_without_masks_and_long_strings():
+    types = [O.INT32, O.STRING, O.INT64, O.STRING, O.INT8]
+    _check(random_table(types, 4001, seed=3, null_frac=0.0))
+    _check(random_table(types, 4001, seed=4, max_str=200))     # > 32 bytes: warp-cooperative copy
+
+
+def test_narrow_table_with_one_huge_row_falls_back():
+    """Average row is small (warp kernel chosen) but one row exceeds a warp's buffer: flag -> generic kernel."""
+    rng = np.random.default_rng(8)
+    n = 3000
+    vals = [bytes(rng.integers(32, 127, int(rng.integers(0, 20)), dtype=np.uint8)) for _ in range(n)]
+    vals[1777] = bytes(rng.integers(32, 127, 40_000, dtype=np.uint8))
+    c0 = O.strings_col(vals)
+    c1 = O.HCol(O.INT64, rng.integers(0, 2**62, n).astype(np.int64).view(np.uint8), None, None, 0, n)
+    _check([c1, c0])
