@@ -762,7 +762,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   {
     // narrow rows: warp-private tiles (to_rows_w_kernel); wide rows: CTA tiles (to_rows3_kernel) below
     const int64_t avg = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
-    if (!force && !getenv("SRJ_TR_NOWARP") && kWarpKernelDefault) {
+    if (!force && !getenv("SRJ_TR_NOWARP") && (kWarpKernelDefault || getenv("SRJ_TR_WARP"))) {
       const int rc = launch_to_rows_warp(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets,
                                          out_data, avg, d_fail_flag, stream, launched);
       if (rc != SRJ_OK || *launched) return rc;
