@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
 // A tile whose rows do not fit the warp's buffer raises *fail_flag (generic kernel redoes the batch).
 // ==================================================================================================
 constexpr int kTwWarps = 24;
-constexpr bool kWarpKernelDefault = false;  // flipped once the GPU parity tests have run on it
+constexpr bool kWarpKernelDefault = true;  // SRJ_TR_NOWARP=1 switches it off (development)
 
 struct ToRowsWParams {
   const void* const* col_data;
