@@ -609,6 +609,19 @@ __global__ void __launch_bounds__(kTwWarps * 32, 1) to_rows_w_kernel(const __gri
         oa = p.out_offsets[r + lane];
         ob = p.out_offsets[r + lane + 1];
       }
+      // the offsets of the first STRING columns are fetched with the geometry: their latency hides behind the zero
+      // fill, the cp.async issue and the validity transpose instead of heading the chars chain
+      constexpr int kPre = 4;
+      int32_t po0[kPre], pL[kPre];
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        po0[j] = pL[j] = 0;
+        if (j < p.nstr && lane < rem) {
+          const int32_t* so = s_soff[j] + abs0 + lane;
+          po0[j]            = __ldg(so);
+          pL[j]             = __ldg(so + 1);
+        }
+      }
       const int64_t lo = static_cast<uint32_t>(__shfl_sync(0xffffffffu, oa, 0));
       const int skew   = static_cast<int>((out_g + lo) & 15);
       const int my_off = static_cast<int>(static_cast<uint32_t>(oa) - static_cast<uint32_t>(lo)) + skew;
@@ -661,7 +674,21 @@ __global__ void __launch_bounds__(kTwWarps * 32, 1) to_rows_w_kernel(const __gri
       }
       // ---- strings: pairs + chars (RC:838-858) ---------------------------------------------------------
       int32_t run = p.size_per_row;
-      for (int s = 0; s < p.nstr; ++s) {
+#pragma unroll
+      for (int j = 0; j < kPre; ++j) {
+        if (j < p.nstr) {
+          const int32_t o0 = po0[j];
+          const int32_t L  = act ? tmax(pL[j] - o0, 0) : 0;
+          if (act) {
+            const uint32_t pa = row_s + static_cast<uint32_t>(s_sstart[j]);
+            t3_sts_u32(pa, static_cast<uint32_t>(run));
+            t3_sts_u32(pa + 4, static_cast<uint32_t>(L));
+          }
+          t3_copy_chars<false>(reinterpret_cast<uintptr_t>(s_chars[j]) + static_cast<uint32_t>(o0), row_s + static_cast<uint32_t>(run), L, rows, lane);
+          run += L;
+        }
+      }
+      for (int s = kPre; s < p.nstr; ++s) {
         int32_t o0 = 0, L = 0;
         if (act) {
           const int32_t* so = s_soff[s] + abs0 + lane;
