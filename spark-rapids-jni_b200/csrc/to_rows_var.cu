@@ -1,28 +1,31 @@
-// to_rows_var.cu -- columns -> JCUDF rows for tables with STRING columns and wide rows
+// to_rows_var.cu -- columns -> JCUDF rows for tables with STRING columns
 // (reference: copy_to_rows + copy_validity_to_rows + copy_strings_to_rows, RC:574-861).
 //
-// One CTA of 24 warps per SM owning a ~200 KB row-image buffer (variant: two CTAs of 12 warps with
-// ~105 KB each).  A tile = as many rows (<= 32, a multiple of 8 unless the super-tile ends) as fit; lane = row everywhere, so every global read is a
-// contiguous piece of a column (values, offsets, chars of consecutive rows) and every shared-memory
-// write lands in the lane's own row image.  Per tile:
-//   1. geometry from the LIST offsets (already written by batch_offsets_kernel), every warp
-//      redundantly -- no header hand-off;
-//   2. string block sums: warp b sums the lengths of its block of STRING columns per row (these loads
-//      also pull the offsets into L1/L2 and prefetch the chars lines);
-//   3. wait for the previous TMA store to have read the buffer, zero it (padding bytes are 0);
+// Two kernels, both lane = row (every global read is a contiguous piece of a column -- values, offsets, chars of
+// consecutive rows -- and every shared-memory write lands in the lane's own row image):
+//
+// to_rows3_kernel (wide rows, >= ~3 KB: the C3 shape).  One CTA of 24 warps per SM owning a ~150-200 KB row-image
+// buffer (variant: two CTAs of 12 warps).  A tile = as many rows (<= 32) as fit.  Per tile:
+//   1. geometry from the LIST offsets (already written by batch_offsets_kernel), every warp redundantly;
+//   2. string block sums: warp b sums the lengths of its block of STRING columns per row and stages the tile's
+//      chars of those columns -- one contiguous global range per column -- into the column's shared-memory slot
+//      with 16-byte cp.async (no registers, no scoreboard);
+//   3. wait for the previous TMA store to have read the buffer, zero it (padding bytes are 0), scan the block sums;
 //   4. independent work items writing disjoint bytes, dealt to the warps once per launch by a
 //      longest-processing-time rule (no atomics in the tile loop):
-//        string block : (offset, len) pairs + chars.  Chars of <= 32 bytes move as aligned 32-bit
-//                       words: up to 10 independent ld.global per lane, funnel-shifted to the
-//                       destination alignment, st.shared.u32 for whole words, st.shared.u8 at the
-//                       two ends; longer strings take a warp-cooperative byte copy;
-//        fixed batch  : 4 columns of one width class: 4 loads in flight, then 4 stores;
-//        validity     : lane = column loads the mask word(s) covering the tile, the 32x32 bit
-//                       butterfly turns them into 4 validity bytes per row;
-//   5. the finished tile -- ONE contiguous byte range of the output -- leaves with a single 1-D TMA
-//      bulk store.
-// A tile that cannot hold 8 rows raises *fail_flag; the generic kernel (to_rows.cu) launched right
-// behind redoes the batch when it sees the flag.
+//        string block : (offset, len) pairs + chars.  Chars of <= 32 bytes move as aligned 32-bit words from the
+//                       staging slot (or from global when a slice did not fit its slot), funnel-shifted to the
+//                       destination alignment, st.shared.u32 for whole words, the <= 3 edge bytes at each end
+//                       straight from the source; longer strings take a warp-cooperative byte copy;
+//        fixed batch  : 8 columns of one width class with cp.async (4/8/16 B; LDG/STS for 1/2 B);
+//        validity     : lane = column loads the mask word(s) covering the tile, the 32x32 bit butterfly turns them
+//                       into 4 validity bytes per row;
+//   5. the finished tile -- ONE contiguous byte range of the output -- leaves with a single 1-D TMA bulk store.
+//
+// to_rows_w_kernel (narrow rows, <= ~600 B: the common Spark shape): see the comment above the kernel.
+//
+// A tile whose rows do not fit raises *fail_flag; the generic kernel (to_rows.cu) launched right behind redoes
+// the batch when it sees the flag.
 #include <algorithm>
 #include <cstdlib>
 
@@ -34,19 +37,7 @@ namespace srj {
 
 constexpr int kT3MaxBlocks = 48;    // string blocks per row
 constexpr int kT3MaxItems  = 1024;
-#ifndef T3_STATIC
-#define T3_STATIC 1
-#endif
-#ifndef T3_U8
-#define T3_U8 0
-#endif
-#ifndef T3_CPASYNC
-#define T3_CPASYNC 1
-#endif
-#ifndef T3_HOIST
-#define T3_HOIST 1
-#endif
-constexpr int kHoist       = T3_HOIST;     // STRING columns whose offsets are fetched together
+constexpr int kHoist       = 1;     // STRING columns of a block whose offsets are fetched together (2 measured +1.6 %, spills at 4)
 
 struct ToRows3Params {
   const void* const* col_data;
@@ -252,7 +243,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
   int32_t* s_items          = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // build order
   int32_t* s_list           = reinterpret_cast<int32_t*>(q);         q += 4 * p.nitems;   // grouped by owning warp
   uint8_t* s_owner          = q;
-  __shared__ int s_nitems, s_next;
+  __shared__ int s_nitems;
   __shared__ int s_direct[2];  // per tile parity: 1 = some column's slice did not fit its slot, read the chars from global
   __shared__ int s_wbeg[kT3Warps + 1];
 
@@ -275,7 +266,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     for (int b = 0; b < p.nblocks; ++b) s_items[n++] = t3_item(kItemString, b, 0);
     for (int k = kNumClasses - 1; k >= 0; --k)
     {
-      const int U = T3_CPASYNC ? 8 : ((k >= 3 || !T3_U8) ? 4 : 8);
+      const int U = 8;
       for (int e = p.class_begin[k]; e < p.class_begin[k + 1]; e += U) s_items[n++] = t3_item(k, e, tmin(U, p.class_begin[k + 1] - e));
     }
     for (int g = 0; g * 32 < p.ncols; ++g) s_items[n++] = t3_item(kItemValidity, g, 0);
@@ -292,7 +283,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
     for (int i = 0; i < n; ++i) {
       const int32_t item = s_items[i];
       const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
-      const int cost = kind == kItemString ? 10 * tmin(p.sb, p.nstr - begin * p.sb) : kind == kItemValidity ? 6 : (T3_CPASYNC && kind >= 2 ? 3 : 4 + count);
+      const int cost = kind == kItemString ? 10 * tmin(p.sb, p.nstr - begin * p.sb) : kind == kItemValidity ? 6 : (kind >= 2 ? 3 : 4 + count);
       const int sel  = static_cast<int>(__reduce_min_sync(0xffffffffu, static_cast<unsigned>((load << 5) | lane)) & 31u);
       if (lane == sel) load += cost;
       if (lane == 0) s_owner[i] = static_cast<uint8_t>(sel);
@@ -395,7 +386,7 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
       const bool act   = lane < rows;
       const uint32_t row_s = image_s + static_cast<uint32_t>(my_off);
       // ---- 3. buffer free -> zero fill -----------------------------------------------------------------
-      if (tid == 0) { tma_store_wait_read<0>(); s_next = 0; s_direct[tile_par ^ 1] = 0; }
+      if (tid == 0) { tma_store_wait_read<0>(); s_direct[tile_par ^ 1] = 0; }
       __syncthreads();
       if (w == kT3Warps - 1) {  // block sums -> exclusive prefix per row (published by the barrier below)
         int32_t acc = p.size_per_row;  // RC:838: chars start right behind the fixed section
@@ -415,17 +406,8 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
       __syncthreads();
       const bool tile_direct = s_direct[tile_par] != 0;
       // ---- 4. this warp's items ----------------------------------------------------------------------------
-#if T3_STATIC
       for (int qi = my_beg; qi < my_end_item; ++qi) {
         const int32_t item = s_list[qi];
-#else
-      for (;;) {
-        int qi = 0;
-        if (lane == 0) qi = atomicAdd(&s_next, 1);
-        qi = __shfl_sync(0xffffffffu, qi, 0);
-        if (qi >= s_nitems) break;
-        const int32_t item = s_items[qi];
-#endif
         const int kind = item & 7, begin = (item >> 3) & 0x1ffff, count = item >> 20;
         if (kind == kItemString) {
           const int s0 = begin * p.sb, s1 = tmin(p.nstr, s0 + p.sb);
@@ -485,19 +467,11 @@ __global__ void __launch_bounds__(kT3Warps * 32, kCtasPerSm) to_rows3_kernel(con
         } else {
           const int64_t ar = abs0 + lane;
           switch (kind) {
-#if T3_CPASYNC
             case 4: t3_fixed_async<16, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 3: t3_fixed_async<8, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 2: t3_fixed_async<4, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             case 1: t3_fixed<2, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
             default: t3_fixed<1, 8>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-#else
-            case 4: t3_fixed<16, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 3: t3_fixed<8, 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 2: t3_fixed<4, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            case 1: t3_fixed<2, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-            default: t3_fixed<1, T3_U8 ? 8 : 4>(s_ent_ptr, s_ent_start, begin, count, ar, act, row_s); break;
-#endif
           }
         }
       }
@@ -808,7 +782,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.nblocks = (nstr + p.sb - 1) / p.sb;
   int nitems = p.nblocks + (p.ncols + 31) / 32;
   for (int k = 0; k < kNumClasses; ++k) {
-    const int U = T3_CPASYNC ? 8 : ((k >= 3 || !T3_U8) ? 4 : 8);
+    const int U = 8;
     nitems += (plan->tr_class_begin[k + 1] - plan->tr_class_begin[k] + U - 1) / U;
   }
   if (nitems > kT3MaxItems) return SRJ_OK;
