@@ -7,6 +7,7 @@
 // column chunks chained through the output column (the accumulator IS the next chunk's seed, which
 // is exactly the Spark chaining rule), so there is no hidden allocation at any width.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "hash_device.cuh"
@@ -168,6 +169,70 @@ __global__ void __launch_bounds__(kHashThreads, KIND == SRJ_HASH_HIVE ? 5 : 4) r
     if (live[j]) reinterpret_cast<acc_t*>(p.out)[r[j]] = h[j];
 }
 
+
+// Every key column is a plain 4- or 8-byte value hashed as stored (32/64-bit integers, dates, timestamps,
+// durations, DECIMAL64): no type dispatch, no 16-byte lane, no string branch -- fewer registers and ~25 % fewer
+// instructions per row than the general kernel above.  Same structure: 4 rows per thread, next column in flight.
+template <int KIND>
+__global__ void __launch_bounds__(kHashThreads, KIND == SRJ_HASH_HIVE ? 5 : 4) row_hash_plain_kernel(const __grid_constant__ HashParams p)
+{
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * (kHashThreads * kRowsPerThread) + threadIdx.x;
+  int64_t r[kRowsPerThread];
+  bool live[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    r[j]    = r0 + static_cast<int64_t>(j) * kHashThreads;
+    live[j] = r[j] < p.n;
+  }
+  if (!live[0]) return;
+  using acc_t = typename std::conditional<KIND == SRJ_HASH_XXHASH64, uint64_t, uint32_t>::type;
+  acc_t h[kRowsPerThread];
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j) {
+    if (p.first || !live[j]) h[j] = KIND == SRJ_HASH_HIVE ? acc_t{0} : static_cast<acc_t>(p.seed);
+    else h[j] = reinterpret_cast<const acc_t*>(p.out)[r[j]];
+  }
+  uint64_t cv[kRowsPerThread], nv[kRowsPerThread];
+  bool cok[kRowsPerThread], nok[kRowsPerThread];
+  auto fetch = [&](const HashCol& col, uint64_t (&v)[kRowsPerThread], bool (&ok)[kRowsPerThread]) {
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      v[j] = 0;
+      if (live[j]) {
+        if (col.kind == 1) v[j] = __ldg(reinterpret_cast<const uint32_t*>(col.data) + r[j]);
+        else v[j] = __ldg(reinterpret_cast<const unsigned long long*>(col.data) + r[j]);
+      }
+      ok[j] = live[j] && row_valid(col.mask, r[j]);
+    }
+  };
+  fetch(p.cols[0], cv, cok);
+  for (int c = 0; c < p.ncols; ++c) {
+    const bool four = p.cols[c].kind == 1;
+    if (c + 1 < p.ncols) fetch(p.cols[c + 1], nv, nok);  // in flight while this column is hashed
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      if constexpr (KIND == SRJ_HASH_XXHASH64) {
+        const uint64_t t = four ? hash::xx_u32(static_cast<uint32_t>(cv[j]), h[j]) : hash::xx_u64(cv[j], h[j]);
+        h[j]             = cok[j] ? t : h[j];  // a null keeps the accumulator (xxhash64.cu:352-353)
+      } else if constexpr (KIND == SRJ_HASH_MURMUR3_32) {
+        const uint32_t t = four ? hash::mm_u32(static_cast<uint32_t>(cv[j]), h[j]) : hash::mm_u64(cv[j], h[j]);
+        h[j]             = cok[j] ? t : h[j];  // murmur_hash.cu:111-117
+      } else {
+        const uint32_t x = four ? static_cast<uint32_t>(cv[j]) : static_cast<uint32_t>((cv[j] >> 32) ^ cv[j]);
+        h[j]             = 31u * h[j] + (cok[j] ? x : 0u);  // hive_hash.cu:179-203 (null -> 0)
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+      cv[j]  = nv[j];
+      cok[j] = nok[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kRowsPerThread; ++j)
+    if (live[j]) reinterpret_cast<acc_t*>(p.out)[r[j]] = h[j];
+}
+
 static int elem_size(int32_t t)
 {
   switch (t) {
@@ -219,7 +284,16 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
       p.cols[i] = HashCol{static_cast<const uint8_t*>(c.data), c.null_mask, c.offsets, static_cast<int16_t>(t),
                           static_cast<int16_t>(kind2), elem_size(t)};
     }
-    if (kind == SRJ_HASH_XXHASH64)
+    bool plain = getenv("SRJ_HASH_GENERAL") == nullptr;
+    for (int i = 0; i < p.ncols; ++i) plain = plain && p.cols[i].kind != 0;
+    if (plain) {
+      if (kind == SRJ_HASH_XXHASH64)
+        row_hash_plain_kernel<SRJ_HASH_XXHASH64><<<grid, kHashThreads, 0, stream>>>(p);
+      else if (kind == SRJ_HASH_MURMUR3_32)
+        row_hash_plain_kernel<SRJ_HASH_MURMUR3_32><<<grid, kHashThreads, 0, stream>>>(p);
+      else
+        row_hash_plain_kernel<SRJ_HASH_HIVE><<<grid, kHashThreads, 0, stream>>>(p);
+    } else if (kind == SRJ_HASH_XXHASH64)
       row_hash_kernel<SRJ_HASH_XXHASH64><<<grid, kHashThreads, 0, stream>>>(p);
     else if (kind == SRJ_HASH_MURMUR3_32)
       row_hash_kernel<SRJ_HASH_MURMUR3_32><<<grid, kHashThreads, 0, stream>>>(p);
