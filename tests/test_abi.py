@@ -77,3 +77,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 src = open(os.path.join(dp, f), errors="replace").read()
                 assert "oracle" not in src.replace("test_product_does_not_import_oracle", ""), f"{f} mentions the oracle"
+
+
+def test_library_holds_the_sm100a_kernels_and_tma_sass():
+    """CPU-side evidence that the shipped .so is the hand-written sm_100a path: the kernels DESIGN.md §3.5 names are
+    in the cubin, and their SASS uses the bulk-copy (TMA, UBLKCP) and cp.async (LDGSTS) instructions."""
+    import shutil
+    import subprocess
+    from srj_b200 import _native as N
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elf = subprocess.run([cuobjdump, "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf
+    sass = subprocess.run([cuobjdump, "-sass", N.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = [l for l in sass.splitlines() if "Function :" in l]
+    for k in ("from_rows_kernel", "strings2_kernel", "strings_from_rows_kernel", "to_rows2_kernel", "to_rows3_kernel",
+              "to_rows_w_kernel", "to_rows_kernel", "row_hash_kernel", "row_hash_plain_kernel"):
+        assert any(k in f for f in funcs), f"kernel {k} missing from the cubin"
+    assert "UBLKCP" in sass, "no TMA bulk copy in the SASS"
+    assert "LDGSTS" in sass, "no cp.async in the SASS"
