@@ -299,13 +299,17 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
       // kernels like 4 rounds (xxhash64 0.87 -> 0.83 ms, murmur3 0.78 -> 0.74 ms against one CTA per row block),
       // hive -- pure streaming -- exactly one (0.67 -> 0.63 ms); a grid that is not a multiple of the resident count
       // leaves a straggler CTA per SM (xxhash64 1.17 ms).
-      int occ = 1;
-      if (kind == SRJ_HASH_XXHASH64)
-        SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_XXHASH64>, kHashThreads, 0));
-      else if (kind == SRJ_HASH_MURMUR3_32)
-        SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_MURMUR3_32>, kHashThreads, 0));
-      else
-        SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_HIVE>, kHashThreads, 0));
+      static int occ_cache[4] = {0, 0, 0, 0};  // per hash kind; the same for every sm_100a device (benign race)
+      int occ = occ_cache[kind & 3];
+      if (occ == 0) {
+        if (kind == SRJ_HASH_XXHASH64)
+          SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_XXHASH64>, kHashThreads, 0));
+        else if (kind == SRJ_HASH_MURMUR3_32)
+          SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_MURMUR3_32>, kHashThreads, 0));
+        else
+          SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_HIVE>, kHashThreads, 0));
+        occ_cache[kind & 3] = occ = std::max(1, occ);
+      }
       const char* e_w      = getenv("SRJ_HASH_WAVES");  // tuning knob (development): CTAs per SM, 0 = one CTA per row block
       const int waves      = e_w ? atoi(e_w) : std::max(1, occ) * (kind == SRJ_HASH_HIVE ? 1 : 4);
       const unsigned pgrid = waves > 0 ? std::min<unsigned>(grid, static_cast<unsigned>(nsm * waves)) : grid;
