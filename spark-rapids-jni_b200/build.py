@@ -14,13 +14,15 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "srj_b200", "libsrj_b200.so")
-SOURCES = ["capi.cu", "from_rows.cu", "to_rows.cu", "to_rows_var.cu", "strings.cu", "hash.cu"]
+SOURCES = ["capi.cu", "from_rows.cu", "from_rows_wide.cu", "to_rows.cu", "to_rows_var.cu", "strings.cu", "hash.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ccbin", "/usr/bin/g++",
     "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("SRJ_PTXAS_V") else "-O3",
 ]
+if os.environ.get("SRJ_DEV_KNOBS"):      # development builds only: tuning knobs read from the environment (common.cuh)
+    FLAGS.append("-DSRJ_DEV_KNOBS")
 
 
 def needs_build() -> bool:

@@ -127,6 +127,16 @@ struct TableLease {
   }
 };
 
+// Phase 1 of a wide variable-width table runs from_rows_wide_kernel (no fused hash there).
+static bool use_wide_from_rows(const srj_plan* plan, const int32_t* row_offsets, const srj_fused_hash* hash)
+{
+  return plan->wide.enabled && row_offsets != nullptr && !(hash && hash->kind != SRJ_HASH_NONE);
+}
+
+// true: between the two phases the STRING offsets are group-local inclusive sums + absolute group bases (phase 2
+// finishes them while it gathers); false: phase 1 leaves finished offsets.
+static bool wide_offsets_protocol(const srj_plan* plan) { return plan->wide.enabled && SRJ_KNOB("SRJ_W_FINALIZE", 0) == 0; }
+
 static int check_cols(const srj_plan* plan, const srj_column* cols, int64_t num_rows, const char* who)
 {
   if (!plan || (plan->num_columns > 0 && !cols)) { set_error("%s: null argument", who); return SRJ_EINVAL; }
@@ -232,8 +242,13 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   tl.tile_rows     = R;
   tl.rows_per_item = R >= 32 ? 32 : R;
 
+  plan_wide(p);  // slabs of a wide variable-width table (from_rows_wide.cu); p->wide.enabled says whether it applies
+
   // device mirror
-  SRJ_CUDA_TRY(cudaGetDevice(&p->device));
+  {
+    const cudaError_t e0 = cudaGetDevice(&p->device);
+    if (e0 != cudaSuccess) { delete p; return cuda_fail(e0, "cudaGetDevice"); }
+  }
   const size_t b_fr = p->fr_entries.size() * sizeof(Entry);
   const size_t b_tr = p->tr_entries.size() * sizeof(Entry);
   const size_t b_cs = static_cast<size_t>(num_columns) * 4;
@@ -246,7 +261,9 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
       for (int e = p->tr_class_begin[k]; e < p->tr_class_begin[k + 1]; ++e) { tr_chunk[e] = acc; acc += 1 << k; }
   }
   const size_t b_tc = tr_chunk.size() * 4;
-  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + b_tc + 64;
+  const size_t b_we = p->wide.enabled ? p->wide.entries.size() * sizeof(WideEntry) : 0;
+  const size_t b_ws = p->wide.enabled ? p->wide.slabs.size() * sizeof(WideSlab) : 0;
+  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + b_tc + b_we + b_ws + 96;
   std::vector<uint8_t> blob(tot, 0);
   size_t o = 0;
   auto put = [&](const void* src, size_t n) { size_t at = o; if (n) memcpy(blob.data() + o, src, n); o += (n + 7) & ~size_t{7}; return at; };
@@ -256,6 +273,8 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   const size_t o_sc = put(p->string_columns.data(), b_sc);
   const size_t o_ss = put(string_start.data(), b_sc);
   const size_t o_tc = put(tr_chunk.data(), b_tc);
+  const size_t o_we = put(p->wide.entries.data(), b_we);
+  const size_t o_ws = put(p->wide.slabs.data(), b_ws);
   cudaError_t e = cudaMalloc(&p->d_blob, tot);
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
   e = cudaMemcpy(p->d_blob, blob.data(), tot, cudaMemcpyHostToDevice);
@@ -267,6 +286,8 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   p->d_string_cols  = reinterpret_cast<const int32_t*>(base + o_sc);
   p->d_string_start = reinterpret_cast<const int32_t*>(base + o_ss);
   p->d_tr_chunk_off = reinterpret_cast<const int32_t*>(base + o_tc);
+  p->wide.d_entries = reinterpret_cast<const WideEntry*>(base + o_we);
+  p->wide.d_slabs   = reinterpret_cast<const WideSlab*>(base + o_ws);
   *out              = p;
   return SRJ_OK;
 }
@@ -479,23 +500,49 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
       if (hash->kind == SRJ_HASH_HIVE && !hash::hive_supported(plan->type_ids[c])) { set_error("fused hive hash: unsupported key type %d", plan->type_ids[c]); return SRJ_EUNSUPPORTED; }
     }
   }
+  for (int c = 0; c < nc; ++c) {
+    if (plan->type_ids[c] == SRJ_STRING) {
+      if (!cols[c].offsets) { set_error("convert_from_rows: STRING column %d has no offsets buffer", c); return SRJ_EINVAL; }
+    } else if (!cols[c].data && num_rows > 0) {
+      set_error("convert_from_rows: column %d has no data buffer", c); return SRJ_EINVAL;
+    }
+    if (!cols[c].null_mask && num_rows > 0) { set_error("convert_from_rows: column %d has no null mask buffer (always allocated, RC:2220)", c); return SRJ_EINVAL; }
+  }
+  if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
+  if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * (nc + 1), stream));
+  if (use_wide_from_rows(plan, row_offsets, hash)) {
+    // wide variable-width table: per-row slabs, offsets leave phase 1 as group-local sums + absolute group bases
+    // pointer tables: [col_ptr nc][masks nc][str_offsets nstr] + group totals
+    std::vector<void*> tab(2 * static_cast<size_t>(nc) + nstr);
+    for (int c = 0; c < nc; ++c) {
+      tab[c]      = plan->type_ids[c] == SRJ_STRING ? static_cast<void*>(cols[c].offsets) : cols[c].data;
+      tab[nc + c] = cols[c].null_mask;
+    }
+    for (int s = 0; s < nstr; ++s) tab[2 * nc + s] = cols[plan->string_columns[s]].offsets;
+    const size_t tab_bytes = (tab.size() * sizeof(void*) + 15) & ~size_t{15};
+    const size_t agg_bytes = static_cast<size_t>(wide_agg_bytes(plan, num_rows));
+    TableLease sc(plan, stream);
+    rc = sc.acquire(tab_bytes + agg_bytes + 16);
+    if (rc != SRJ_OK) return rc;
+    memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
+    rc = sc.upload(tab.size() * sizeof(void*));
+    if (rc != SRJ_OK) return rc;
+    auto** d = static_cast<void**>(sc.dev());
+    return launch_from_rows_wide(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nc),
+                                 reinterpret_cast<int32_t* const*>(d + 2 * nc), d_null_counts, d_char_totals,
+                                 d_char_totals ? d_char_totals + nc : nullptr,
+                                 reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(sc.dev()) + tab_bytes),
+                                 !wide_offsets_protocol(plan), stream);
+  }
   const size_t nent = plan->fr_entries.size();
   // pointer tables: [ent_dst nent][masks nc][str_offsets nstr] + scan partials
   std::vector<void*> tab(nent + nc + nstr);
   for (size_t e = 0; e < nent; ++e) {
     const int c = plan->fr_entries[e].column;
-    if (plan->type_ids[c] == SRJ_STRING) {
-      if (!cols[c].offsets) { set_error("convert_from_rows: STRING column %d has no offsets buffer", c); return SRJ_EINVAL; }
-      tab[e] = reinterpret_cast<uint8_t*>(cols[c].offsets) + 4;  // lengths land at offsets[1..n]
-    } else {
-      if (!cols[c].data && num_rows > 0) { set_error("convert_from_rows: column %d has no data buffer", c); return SRJ_EINVAL; }
-      tab[e] = cols[c].data;
-    }
+    tab[e]      = plan->type_ids[c] == SRJ_STRING ? static_cast<void*>(reinterpret_cast<uint8_t*>(cols[c].offsets) + 4)  // lengths land at offsets[1..n]
+                                                  : cols[c].data;
   }
-  for (int c = 0; c < nc; ++c) {
-    if (!cols[c].null_mask && num_rows > 0) { set_error("convert_from_rows: column %d has no null mask buffer (always allocated, RC:2220)", c); return SRJ_EINVAL; }
-    tab[nent + c] = cols[c].null_mask;
-  }
+  for (int c = 0; c < nc; ++c) tab[nent + c] = cols[c].null_mask;
   for (int s = 0; s < nstr; ++s) tab[nent + nc + s] = cols[plan->string_columns[s]].offsets;
   const size_t tab_bytes  = (tab.size() * sizeof(void*) + 15) & ~size_t{15};
   const size_t part_bytes = static_cast<size_t>(string_scan_partials_bytes(nstr, num_rows));
@@ -506,15 +553,13 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
   rc = sc.upload(tab.size() * sizeof(void*));
   if (rc != SRJ_OK) return rc;
   auto** d = static_cast<void**>(sc.dev());
-  if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
-  if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * (nc + 1), stream));
   rc = launch_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nent),
                         d_null_counts, d_char_totals ? d_char_totals + nc : nullptr, hash, stream);
   if (rc != SRJ_OK) return rc;
   if (nstr > 0) {
     uint8_t* tail = static_cast<uint8_t*>(sc.dev()) + tab_bytes;
     rc = launch_string_offsets_scan(reinterpret_cast<int32_t* const*>(d + nent + nc), plan->d_string_cols, nstr, num_rows,
-                                    d_char_totals, reinterpret_cast<int32_t*>(tail + part_bytes), tail, stream);
+                                    d_char_totals, d_char_totals ? d_char_totals + nc : nullptr, tail, stream);
     if (rc != SRJ_OK) return rc;
   }
   return SRJ_OK;
@@ -545,8 +590,9 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
   if (rc != SRJ_OK) return rc;
   auto** d = static_cast<void**>(sc.dev());
   return launch_strings_from_rows(plan, rows, row_offsets, rows_bytes, num_rows,
-                                  reinterpret_cast<const int32_t* const*>(d), reinterpret_cast<uint8_t* const*>(d + nstr),
-                                  d_char_totals ? d_char_totals + plan->num_columns : nullptr, stream);
+                                  reinterpret_cast<int32_t* const*>(d), reinterpret_cast<uint8_t* const*>(d + nstr),
+                                  d_char_totals ? d_char_totals + plan->num_columns : nullptr,
+                                  wide_offsets_protocol(plan), stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -31,6 +31,28 @@ struct Tiling {
   int32_t num_stages;
 };
 
+// ---- wide variable-width tables (from_rows_wide.cu) ------------------------------------------------------
+// The fixed section of a wide row is cut into byte-range "slabs"; a tile = R rows x one slab, each row's slab
+// fetched by its own TMA bulk copy (the variable section of the row is never read by phase 1).
+struct WideEntry {
+  int32_t start;   // byte offset in the row (STRING: the (offset, len) pair)
+  int32_t column;  // schema column index
+  int32_t sidx;    // index among the STRING columns, or -1
+  int32_t slab;
+};
+struct WideSlab {
+  int32_t begin, end;  // row byte range [begin, end) staged for this slab (multiples of 8)
+  int32_t cb[7];       // entry index boundaries of the width classes, processed in the order 16,8,4,2,1,STRING
+};
+struct WidePlan {
+  bool enabled = false;
+  int32_t R = 0, G = 0, pitch = 0, nstages = 0, nslabs = 0;
+  std::vector<WideEntry> entries;
+  std::vector<WideSlab> slabs;
+  const WideEntry* d_entries = nullptr;
+  const WideSlab* d_slabs    = nullptr;
+};
+
 // Per-call pointer tables (column/mask/offset pointers differ on every call) go host -> device through
 // a small ring of pinned staging buffers + device buffers owned by the plan: one truly asynchronous
 // cudaMemcpyAsync per call, no allocation, re-entrant (a slot is reused only after the event recorded
@@ -70,6 +92,7 @@ struct srj_plan {
   int32_t tr_class_begin[srj::kNumClasses + 1];
 
   srj::Tiling tiling;
+  srj::WidePlan wide;  // from_rows of wide variable-width tables
 
   // device mirrors (one allocation)
   void* d_blob;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.hpp"
+#include "movers.cuh"
 #include "plan.hpp"
 
 namespace srj {
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(int32_t* co
 // exclusive scan of each column's chunk sums, in place; writes the column total
 __global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(int64_t* partials, int nchunks,
                                                                     const int32_t* string_cols, int64_t* char_totals,
-                                                                    int32_t* error)
+                                                                    unsigned long long* status)
 {
   __shared__ int64_t s_warp[kScanThreads / 32];
   __shared__ int64_t s_carry;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(int64_t* part
   if (threadIdx.x == 0) {
     const int64_t total = s_carry;
     if (char_totals) char_totals[string_cols[c]] = total;
-    if (total > INT32_MAX) atomicExch(error, SRJ_EOVERFLOW);  // cudf strings offsets are int32
+    if (total > INT32_MAX && status) atomicOr(status, 2ull);  // cudf strings offsets are int32: bit 1 of the status word
   }
 }
 
@@ -140,7 +141,7 @@ int64_t string_scan_partials_bytes(int nstr, int64_t num_rows)
 }
 
 int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_string_cols, int nstr, int64_t num_rows,
-                               int64_t* d_char_totals, int32_t* d_error, void* d_partials, cudaStream_t stream)
+                               int64_t* d_char_totals, int64_t* d_status, void* d_partials, cudaStream_t stream)
 {
   if (nstr == 0) return SRJ_OK;
   const int64_t n1  = num_rows + 1;
@@ -148,7 +149,8 @@ int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_strin
   auto* partials    = static_cast<int64_t*>(d_partials);
   dim3 grid(nchunks, nstr);
   scan_partials_kernel<<<grid, kScanThreads, 0, stream>>>(d_offsets, n1, nchunks, partials);
-  scan_chunks_kernel<<<nstr, kScanThreads, 0, stream>>>(partials, nchunks, d_string_cols, d_char_totals, d_error);
+  scan_chunks_kernel<<<nstr, kScanThreads, 0, stream>>>(partials, nchunks, d_string_cols, d_char_totals,
+                                                        reinterpret_cast<unsigned long long*>(d_status));
   scan_apply_kernel<<<grid, kScanThreads, 0, stream>>>(d_offsets, n1, nchunks, partials);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
@@ -162,21 +164,6 @@ int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_strin
 // --------------------------------------------------------------------------------------------------
 
 // ---- shared-memory helpers of the chars gathers (32-bit shared-space addresses) ----------------------------------
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
-{
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-
 // A warp's staging line holds the T chars of one (32-row tile, column) at the byte positions [a, a + T), a = the
 // destination's offset inside its 16-byte granule.  Flush: whole 16-byte chunks with one ld.shared.v4 /
 // st.global.v4 per lane; the bytes of the two partial chunks at the ends (their neighbours belong to other tiles /
@@ -265,8 +252,8 @@ constexpr int kStrLine  = 16 + 1024 + 32;  // per-warp staging line
 
 __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
   const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets, int64_t row_stride, int64_t num_rows,
-  int nstr, const int32_t* __restrict__ string_start, const int32_t* const* __restrict__ offsets,
-  uint8_t* const* __restrict__ chars, int64_t ntiles, const int64_t* __restrict__ status)
+  int nstr, const int32_t* __restrict__ string_start, int32_t* const* __restrict__ offsets,
+  uint8_t* const* __restrict__ chars, int64_t ntiles, const int64_t* __restrict__ status, int semi)
 {
   // runs only when phase 1 flagged non-canonical rows (or no status word was passed)
   if (status && !(*status & 1)) return;
@@ -285,7 +272,7 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
     const int64_t rsta = active ? (row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride) : 0;
     {
       uint32_t so = 0, len = 0;
-      int32_t d0 = 0;
+      int32_t v = 0;
       if (active) {
         const uint8_t* pp = rows + rsta + string_start[s];
         if ((reinterpret_cast<uintptr_t>(pp) & 3) == 0) {
@@ -295,13 +282,19 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
           so  = pp[0] | (pp[1] << 8) | (pp[2] << 16) | (static_cast<uint32_t>(pp[3]) << 24);
           len = pp[4] | (pp[5] << 8) | (pp[6] << 16) | (static_cast<uint32_t>(pp[7]) << 24);
         }
-        d0                = offsets[s][r];
+        v = offsets[s][r + 1];
       }
-      const int32_t dbase  = __shfl_sync(0xffffffffu, d0, 0);
-      const uint32_t pe    = static_cast<uint32_t>(d0 - dbase);  // exclusive prefix inside the tile
-      // total = pe + len of the last active lane
+      // offsets entries: absolute, or (semi: wide tables between the two phases) inclusive sums inside the 32-row
+      // group with an absolute entry closing each group -- finished here
       const int last       = static_cast<int>(tmin<int64_t>(31, num_rows - 1 - tile * 32));
-      const uint32_t total = __shfl_sync(0xffffffffu, pe + len, last);
+      const int32_t dbase  = offsets[s][tile * 32];
+      int32_t x            = v;
+      if (!semi || lane == last) x -= dbase;
+      x                    = active ? x : 0;
+      const int32_t up     = __shfl_up_sync(0xffffffffu, x, 1);
+      const uint32_t pe    = static_cast<uint32_t>(lane ? up : 0);  // exclusive prefix inside the tile
+      const uint32_t total = static_cast<uint32_t>(__shfl_sync(0xffffffffu, x, last));
+      if (semi && lane < last) offsets[s][r + 1] = dbase + x;
       const int64_t srcoff = rsta + so;
       uint8_t* dst         = chars[s] + dbase;
       const int maxL       = __reduce_max_sync(0xffffffffu, active ? static_cast<int>(tmin<uint32_t>(len, 1u << 20)) : 0);
@@ -336,342 +329,312 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
 
 
 // --------------------------------------------------------------------------------------------------
-// chars gather, FAST path (canonical rows: a row's chars follow its fixed section in column order,
-// which is what convert_to_rows writes and what phase 1 verified).
+// chars gather, FAST path (canonical rows: a row's chars follow its fixed section in column order, which is
+// what convert_to_rows writes and what phase 1 verified).
 //
-//   producer warp : per tile of <= 32 rows, one TMA bulk load per row of JUST the row's variable
-//                   section (lane = row) into a shared-memory ring, plus the [r0, r0+rows] slice of
-//                   every STRING column's offsets via 16-byte cp.async (completion on the same
-//                   mbarrier) -- so the consumers never wait on a global load;
-//   consumer warps: each owns a block of STRING columns.  lane = row: the string's position in the
-//                   row is the running sum of the lengths of the preceding STRING columns; it is
-//                   read as aligned words, funnel-shifted to the destination's byte alignment and
-//                   written word-wise into a per-warp staging line laid out like the destination;
-//                   the line (the tile's chars of that column: one contiguous range of the chars
-//                   buffer) is flushed with aligned 16-byte st.global.
+// A tile is one 32-row group.  The CTA keeps kSwNG tiles in flight, each owned by a group of `wpt` consumer
+// warps; warp i of a group gathers the STRING columns [i * cpw, (i + 1) * cpw) of its tile.
+//
+//   producer warp : lane = row; one TMA bulk copy per row of JUST the row's variable section
+//                   [offsets[r] + size_per_row, offsets[r + 1]) into a ring of 2 * kSwNG stages (two per
+//                   group), so the fixed section -- 79 % of a C3 row -- is never read by this phase;
+//   consumer warps: lane = row.  The warp reads its columns' offsets entries of the tile (one coalesced 128-byte
+//                   load per column), turns them into lengths, and the warps of the group exchange their
+//                   per-row byte sums through shared memory (one named barrier per tile) to find where in the
+//                   row's variable section their first column starts.  Per column the lane's string moves as
+//                   aligned 32-bit words from the row image, funnel-shifted to the destination's byte
+//                   alignment, into a per-warp staging line laid out like the destination, which leaves with
+//                   aligned 16-byte st.global (the chars of consecutive rows of a column are contiguous).
+//   offsets       : with `semi` (wide tables, from_rows_wide.cu) phase 1 left group-local inclusive sums and an
+//                   absolute base per 32-row group; the absolute offsets are written here, on the way.
 // --------------------------------------------------------------------------------------------------
-constexpr int kS2Consumers  = 19;  // issue/latency-bound gather: more independent warps (80 registers each)
-constexpr int kS2Threads    = (kS2Consumers + 1) * 32;
-constexpr int kS2Rows       = 32;
-constexpr int kS2Stages     = 3;
-constexpr int kS2StageBytes = 44 * 1024;
-constexpr int kS2Front      = 16;   // slack before the payload (word reads may start 4 bytes early)
-constexpr int kS2Back       = 48;   // slack after it (word reads may run past a string)
-constexpr int kS2Slice      = 36;   // ints per offsets slice: rows + 1 <= 33, padded to 16-byte chunks
-constexpr int kS2StageLine  = 16 + 1024 + 32;  // per-warp staging line
-constexpr int kS2MinCols    = 32;   // fewer STRING columns: the generic task-parallel kernel
-constexpr int kS2MaxCols    = 160;  // offsets slices must fit shared memory
+constexpr int kSwNG     = 3;   // tiles in flight per CTA (groups of consumer warps)
+constexpr int kSwMaxWpt = 8;   // consumer warps per tile
+constexpr int kSwMaxCpw = 8;   // STRING columns per warp (held in registers)
+constexpr int kSwStages = 2 * kSwNG;
+constexpr int kSwFront  = 16;  // slack before a stage's payload (word reads may start up to 7 bytes early)
+constexpr int kSwBack   = 48;  // slack after it (word reads may run up to 44 bytes past a string)
+constexpr int kSwLine   = 16 + 1024 + 32;  // per-warp staging line
+constexpr int kSwMaxThreads = (1 + kSwNG * kSwMaxWpt) * 32;
 
-struct S2Hdr {
+struct SwHdr {
   int64_t r0;
-  int32_t rows;
-  int32_t safe;
+  int32_t rows;    // 0 = end
+  int32_t direct;  // 1 = variable sections not staged (tile larger than a stage): read them from global memory
 };
 
-struct S2Params {
+struct SwParams {
   const uint8_t* rows;
   const int32_t* row_offsets;
   int64_t rows_bytes;
   int64_t num_rows;
-  int64_t super_rows;
-  int32_t nstr;
-  int32_t size_per_row;
-  const int32_t* const* offsets;
+  int32_t nstr, size_per_row, wpt, cpw, stage_bytes, semi;
+  int32_t* const* offsets;
   uint8_t* const* chars;
   const int64_t* status;
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+__device__ __forceinline__ int32_t ldg_s32(const int32_t* p)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-// arrive on `bar` once all cp.async issued so far by this thread have landed (does not bump the pending count)
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar)
-{
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  int32_t v;
+  asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
+// lane's string = L bytes at SHARED address srcs -> staging byte ds.  Aligned 32-bit source words, funnel shift to
+// the staging alignment, st.shared.u32 for whole words; the <= 3 edge bytes at each end come straight from the
+// source.  maxL (<= 32) is the warp's longest string; the word loads are unconditional (the stage has slack).
+__device__ __forceinline__ void copy_shared_to_staging(uint32_t srcs, uint32_t ds, int L, int maxL)
+{
+  const int dsh      = static_cast<int>(ds & 3u);
+  const int ssh      = static_cast<int>(srcs & 3u);
+  const int dlt      = ssh - dsh;
+  const int pre      = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
+  const uint32_t sp  = srcs - pre;
+  const int sh       = (dlt & 3) * 8;
+  const int end      = dsh + L;      // one past the last staging byte, relative to word w0
+  const int kfull1   = end >> 2;     // full words: [dsh ? 1 : 0, kfull1)
+  const uint32_t w0s = ds - dsh;
+  const int Kmax     = (maxL + 6) >> 2;  // warp-uniform bound on kfull1 (<= 9)
+  const int nh       = dsh ? tmin(L, 4 - dsh) : 0;
+  const int nt       = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
+  uint32_t hb[3], tb[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    hb[t] = tb[t] = 0;
+    if (t < nh) hb[t] = lds_u8(srcs + t);
+    if (t < nt) tb[t] = lds_u8(srcs + (L - nt) + t);
+  }
+  uint32_t w[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    w[k] = 0;
+    if (k <= Kmax) w[k] = lds_u32(sp + 4 * k);
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t < nh) sts_u8(ds + t, hb[t]);
+    if (t < nt) sts_u8(ds + (L - nt) + t, tb[t]);
+  }
+  const int k0 = dsh ? 1 : 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    if (k < Kmax) {
+      const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+      if (k >= k0 && k < kfull1) sts_u32(w0s + 4 * k, y);
+    }
+  }
+}
 
-__global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_constant__ S2Params p)
+// lane = destination byte, source row by a shuffle search (long strings, tiles that were not staged)
+__device__ __noinline__ void gather_bytes_slow(uint8_t* D, uint32_t T, uint32_t pe, uint64_t src, int last, int lane)
+{
+  const uint32_t bound = (T + 31u) & ~31u;  // all lanes take part in the shuffles
+  for (uint32_t q = lane; q < bound; q += 32) {
+    int j = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int cand   = j + step;
+      const uint32_t v = __shfl_sync(0xffffffffu, pe, cand & 31);
+      if (cand <= last && v <= q) j = cand;
+    }
+    const uint32_t pj = __shfl_sync(0xffffffffu, pe, j);
+    const uint64_t sj = __shfl_sync(0xffffffffu, src, j);
+    if (q < T) D[q] = *reinterpret_cast<const uint8_t*>(sj + (q - pj));
+  }
+}
+
+__global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __grid_constant__ SwParams p)
 {
   if (p.status && (*p.status & 1)) return;  // non-canonical rows: the generic kernel does the work
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int NS        = kS2Stages;
-  constexpr int stage_span = kS2Front + kS2StageBytes + kS2Back;
-  uint8_t* payload0  = smem;
-  int32_t* rowsm0    = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(NS) * stage_span);  // [NS][36]
-  int32_t* slice0    = rowsm0 + NS * kS2Slice;                                                    // [NS][nstr][36]
-  const int slice_sp = p.nstr * kS2Slice;
-  S2Hdr* hdr0        = reinterpret_cast<S2Hdr*>(slice0 + static_cast<size_t>(NS) * slice_sp);
-  uint64_t* full     = reinterpret_cast<uint64_t*>(hdr0 + NS);
-  uint64_t* empty    = full + NS;
-  const int32_t** s_offs = reinterpret_cast<const int32_t**>(empty + NS);
-  uint8_t** s_chars      = reinterpret_cast<uint8_t**>(const_cast<int32_t**>(s_offs) + p.nstr);
-  uint8_t* stg0          = reinterpret_cast<uint8_t*>(s_chars + p.nstr);
-  stg0                   = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stg0) + 15) & ~uintptr_t{15});
+  constexpr int NS     = kSwStages;
+  const int stage_span = kSwFront + p.stage_bytes + kSwBack;  // multiple of 16
+  const int wpt        = p.wpt;
+  uint8_t* payload0    = smem;
+  int32_t* rowsm0      = reinterpret_cast<int32_t*>(smem + static_cast<size_t>(NS) * stage_span);  // [NS][32]
+  SwHdr* hdr0          = reinterpret_cast<SwHdr*>(rowsm0 + NS * 32);
+  uint64_t* full       = reinterpret_cast<uint64_t*>(hdr0 + NS);
+  uint64_t* empty      = full + NS;
+  int32_t** s_offs     = reinterpret_cast<int32_t**>(empty + NS);
+  uint8_t** s_chars    = reinterpret_cast<uint8_t**>(s_offs + p.nstr);
+  int32_t* blk0        = reinterpret_cast<int32_t*>(s_chars + p.nstr);  // [2][kSwNG][kSwMaxWpt][32]
+  uint8_t* stg0        = reinterpret_cast<uint8_t*>(blk0 + 2 * kSwNG * kSwMaxWpt * 32);
+  stg0                 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(stg0) + 15) & ~uintptr_t{15});
 
   const int tid  = threadIdx.x;
   const int lane = lane_id();
-  for (int i = tid; i < p.nstr; i += kS2Threads) {
+  for (int i = tid; i < p.nstr; i += blockDim.x) {
     s_offs[i]  = p.offsets[i];
     s_chars[i] = p.chars[i];
   }
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);  // lane 0's arrive.expect_tx; every byte of the stage arrives by TMA
-      mbar_init(&empty[s], kS2Consumers);
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], wpt);
     }
     fence_mbar_init();
   }
   __syncthreads();
 
   const uintptr_t b_lo = reinterpret_cast<uintptr_t>(p.rows);
-  const uintptr_t b_hi = b_lo + p.rows_bytes;
+  const uintptr_t b_hi = b_lo + static_cast<uintptr_t>(p.rows_bytes);
+  const int64_t ntiles = (p.num_rows + 31) >> 5;
 
   if (warp_id() == 0) {
     // =================================== producer ===================================
-    int64_t sup = blockIdx.x;
-    int64_t r   = sup * p.super_rows;
-    int64_t c1  = tmin(p.num_rows, r + p.super_rows);
-    // per-lane geometry of the NEXT tile (lane = row)
-    int g_rows = 0;
-    bool g_end = false, g_safe = false;
-    uintptr_t a_lo = 0, a_hi = 0, t_lo = 0, t_hi = 0, fl = 0;
-    int32_t slot = 0;
-    auto next_geometry = [&]() {
-      if (r >= c1) {
-        sup += gridDim.x;
-        r  = sup * p.super_rows;
-        c1 = tmin(p.num_rows, r + p.super_rows);
+    int it = 0;
+    for (int64_t T = blockIdx.x;; T += gridDim.x, ++it) {
+      const int s        = it % NS;
+      const uint32_t par = ((it / NS) & 1) ^ 1;
+      if (lane == 0) mbar_wait(&empty[s], par);
+      __syncwarp();
+      SwHdr* h = hdr0 + s;
+      if (T >= ntiles) {
+        // one end marker per group of consumer warps
+        if (lane == 0) {
+          h->rows = 0;
+          mbar_arrive(&full[s]);
+        }
+        if (T >= ntiles + static_cast<int64_t>(kSwNG - 1) * gridDim.x) break;
+        continue;
       }
-      g_end = r >= p.num_rows;
-      if (g_end) return;
-      int rows = static_cast<int>(tmin<int64_t>(kS2Rows, c1 - r));
+      const int64_t r0 = T << 5;
+      const int rows   = static_cast<int>(tmin<int64_t>(32, p.num_rows - r0));
+      uint8_t* pay     = payload0 + static_cast<size_t>(s) * stage_span + kSwFront;
+      int32_t* rowsm   = rowsm0 + s * 32;
       int64_t o0 = 0, o1 = 0;
       if (lane < rows) {
-        o0 = p.row_offsets[r + lane];
-        o1 = p.row_offsets[r + lane + 1];
+        o0 = static_cast<uint32_t>(p.row_offsets[r0 + lane]);
+        o1 = static_cast<uint32_t>(p.row_offsets[r0 + lane + 1]);
       }
       int64_t gs = o0 + p.size_per_row, ge = o1;
       if (ge < gs) ge = gs;
-      a_lo = b_lo + gs;
-      a_hi = b_lo + ge;
-      fl   = a_lo & ~uintptr_t{15};
-      t_lo = fl < b_lo ? fl + 16 : fl;
-      t_hi = (a_hi + 15) & ~uintptr_t{15};
+      const uintptr_t a_lo = b_lo + static_cast<uintptr_t>(gs);
+      const uintptr_t a_hi = b_lo + static_cast<uintptr_t>(ge);
+      const uintptr_t fl   = a_lo & ~uintptr_t{15};
+      uintptr_t t_lo       = fl < b_lo ? fl + 16 : fl;
+      uintptr_t t_hi       = (a_hi + 15) & ~uintptr_t{15};
       if (t_hi > b_hi) t_hi = a_hi & ~uintptr_t{15};
       if (t_hi < t_lo) t_hi = t_lo;
-      if (lane >= rows || a_hi == a_lo) { t_hi = t_lo; }
-      int32_t span = (lane < rows) ? static_cast<int32_t>(tmin<uintptr_t>(((a_hi + 15) & ~uintptr_t{15}) - fl, 1u << 30)) : 0;
-      // exclusive scan of the window spans -> slot of each row; rows that fit the stage
-      int32_t x = span;
+      if (lane >= rows || a_hi == a_lo) t_hi = t_lo;
+      const int32_t span =
+        (lane < rows) ? static_cast<int32_t>(tmin<uintptr_t>(((a_hi + 15) & ~uintptr_t{15}) - fl, 1u << 30)) : 0;
+      int32_t x = span;  // inclusive scan of the window spans -> slot of each row
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
       }
-      slot = x - span;
-      const bool ok = lane < rows && x <= kS2StageBytes;
-      int fit       = __popc(__ballot_sync(0xffffffffu, ok));
-      // ballot counts lanes that fit; spans are non-negative so the set is a prefix
-      if (fit < rows) fit &= ~7;
-      g_safe = false;
-      if (fit == 0) {
-        g_safe = true;
-        rows   = tmin(rows, 8);
-      } else {
-        rows = fit;
+      const int32_t slot = x - span;
+      const bool over    = lane < rows && (x > p.stage_bytes || span >= (1 << 30));
+      const bool direct  = __any_sync(0xffffffffu, over);
+      uint32_t tx        = 0;
+      if (!direct && lane < rows) {
+        tx          = static_cast<uint32_t>(t_hi - t_lo);
+        rowsm[lane] = slot + static_cast<int32_t>(a_lo - fl);
+        // bytes of [a_lo, a_hi) outside the TMA window [t_lo, t_hi) (only at the ends of the buffer): by hand
+        const uintptr_t h_end = tmin(tmax(t_lo, a_lo), a_hi);
+        for (uintptr_t a = a_lo; a < h_end; ++a) pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
+        for (uintptr_t a = tmax(tmin(t_hi, a_hi), h_end); a < a_hi; ++a) pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
       }
-      g_rows = rows;
-    };
-    next_geometry();
-
-    for (int it = 0;; ++it) {
-      const int s        = it % NS;
-      const uint32_t par = ((it / NS) & 1) ^ 1;
-      if (lane == 0) mbar_wait(&empty[s], par);
-      __syncwarp();
-      uint8_t* pay   = payload0 + static_cast<size_t>(s) * stage_span + kS2Front;
-      int32_t* rowsm = rowsm0 + s * kS2Slice;
-      int32_t* slice = slice0 + static_cast<size_t>(s) * slice_sp;
-      S2Hdr* h       = hdr0 + s;
-      if (g_end) {
-        if (lane == 0) {
-          h->rows = 0;
-          mbar_arrive(&full[s]);
-        }
-        break;
-      }
-      const int rows  = g_rows;
-      const bool safe = g_safe;
-      uint32_t tx     = 0;
-      if (!safe && lane < rows) {
-        tx           = static_cast<uint32_t>(t_hi - t_lo);
-        rowsm[lane]  = slot + static_cast<int32_t>(a_lo - fl);
-        // bytes of [a_lo, a_hi) outside the TMA window [t_lo, t_hi): copy by hand
-        for (uintptr_t a = a_lo; a < tmin(tmax(t_lo, a_lo), a_hi); ++a) pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
-        for (uintptr_t a = tmax(tmin(t_hi, a_hi), tmin(tmax(t_lo, a_lo), a_hi)); a < a_hi; ++a)
-          pay[slot + (a - fl)] = *reinterpret_cast<const uint8_t*>(a);
-      }
-      // offsets slices [r, r + rows] of every STRING column: one small TMA bulk copy per column (r is a
-      // multiple of 8, so &offsets[c][r] is 16-byte aligned whenever the buffer is).  Entries past the end
-      // of the array (last tile) and unaligned buffers are copied by hand.
-      const int need     = rows + 1;                                   // entries wanted
-      const int64_t have = p.num_rows + 1 - r;                         // entries that exist from r on
-      const int nbulk    = static_cast<int>(tmin<int64_t>((need + 3) & ~3, have & ~int64_t{3}));  // whole 16-byte chunks
-      uint32_t stx       = 0;
-      for (int sc = lane; sc < p.nstr; sc += 32) {
-        const int32_t* src = s_offs[sc] + r;
-        int32_t* dst       = slice + sc * kS2Slice;
-        int done           = 0;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && nbulk > 0) {
-          stx += static_cast<uint32_t>(nbulk) * 4u;
-          done = nbulk;
-        }
-        for (int e = done; e < need && e < have; ++e) dst[e] = src[e];
-      }
-      uint32_t total = tx + stx;
+      uint32_t total = tx;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
       if (lane == 0) {
-        h->r0   = r;
-        h->rows = rows;
-        h->safe = safe ? 1 : 0;
+        h->r0     = r0;
+        h->rows   = rows;
+        h->direct = direct ? 1 : 0;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], total);  // release: header / rowsm / hand copies visible
+      if (lane == 0) {
+        if (total) mbar_arrive_expect_tx(&full[s], total);  // release: header / rowsm / hand copies visible
+        else mbar_arrive(&full[s]);
+      }
       __syncwarp();
       if (tx) tma_load_1d(pay + slot + (t_lo - fl), reinterpret_cast<const void*>(t_lo), tx, &full[s]);
-      for (int sc = lane; sc < p.nstr; sc += 32) {
-        const int32_t* src = s_offs[sc] + r;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && nbulk > 0)
-          tma_load_1d(slice + sc * kS2Slice, src, static_cast<uint32_t>(nbulk) * 4u, &full[s]);
-      }
-      r += rows;
-      next_geometry();
     }
   } else {
     // =================================== consumers ===================================
-    const int cw       = warp_id() - 1;
-    const int s0       = (cw * p.nstr) / kS2Consumers;
-    const int s1       = ((cw + 1) * p.nstr) / kS2Consumers;
-    uint8_t* stg       = stg0 + static_cast<size_t>(cw) * kS2StageLine;
-    const uint32_t stg_s = smem_u32(stg);
-    for (int it = 0;; ++it) {
+    const int cw         = warp_id() - 1;
+    const int gi         = cw / wpt;        // tile group
+    const int wi         = cw - gi * wpt;   // warp inside the group
+    const int c0         = wi * p.cpw;
+    const int ncol       = tmax(0, tmin(p.nstr, c0 + p.cpw) - c0);
+    const uint32_t stg_s = smem_u32(stg0 + static_cast<size_t>(cw) * kSwLine);
+    const bool semi      = p.semi != 0;
+    for (int it = gi, k = 0;; it += kSwNG, ++k) {
       const int s        = it % NS;
       const uint32_t par = (it / NS) & 1;
-      mbar_wait_backoff(&full[s], par, 256);
-      const S2Hdr h = hdr0[s];
+      mbar_wait(&full[s], par);
+      const SwHdr h = hdr0[s];
       if (h.rows == 0) break;
-      const uint8_t* pay   = payload0 + static_cast<size_t>(s) * stage_span + kS2Front;
-      const int32_t* rowsm = rowsm0 + s * kS2Slice;
-      const int32_t* slice = slice0 + static_cast<size_t>(s) * slice_sp;
-      const int rows       = h.rows;
-      const bool active    = lane < rows;
-      const uint32_t pay_s = smem_u32(pay);
-      const int32_t rowsm_lane = (!h.safe && active) ? rowsm[lane] : 0;
-      // this lane's row: start of its variable section
-      const uint8_t* var0;
-      if (!h.safe) {
-        var0 = pay + (active ? rowsm[lane] : 0);
-      } else {
-        var0 = p.rows + (active ? static_cast<int64_t>(p.row_offsets[h.r0 + lane]) + p.size_per_row : 0);
+      const int rows      = h.rows;
+      const int last      = rows - 1;
+      const bool active   = lane < rows;
+      const bool direct   = h.direct != 0;
+      const uint32_t pay_s = smem_u32(payload0 + static_cast<size_t>(s) * stage_span + kSwFront);
+      // ---- this warp's columns: offsets entries of the tile -> lengths ------------------------------------
+      int32_t base_l = 0;
+      if (lane < ncol) base_l = ldg_s32(s_offs[c0 + lane] + h.r0);
+      int32_t v[kSwMaxCpw];
+#pragma unroll
+      for (int j = 0; j < kSwMaxCpw; ++j) {
+        v[j] = 0;
+        if (j < ncol && active) v[j] = ldg_s32(s_offs[c0 + j] + h.r0 + 1 + lane);
       }
-      // running position inside the variable section: lengths of the STRING columns before s0
+      int32_t inc[kSwMaxCpw], len[kSwMaxCpw];
+      int32_t mysum = 0;
+#pragma unroll
+      for (int j = 0; j < kSwMaxCpw; ++j) {
+        const int32_t bj = __shfl_sync(0xffffffffu, base_l, j);
+        int32_t x        = v[j];
+        if (!semi || lane == last) x -= bj;  // entries of the group's last row (and every finished entry) are absolute
+        x                = active ? x : 0;
+        const int32_t up = __shfl_up_sync(0xffffffffu, x, 1);
+        inc[j]           = x;
+        len[j]           = active ? tmax(x - (lane ? up : 0), 0) : 0;
+        mysum += (j < ncol) ? len[j] : 0;
+      }
+      // ---- where this warp's first column starts inside the row's variable section --------------------------
+      int32_t* blk = blk0 + (((k & 1) * kSwNG + gi) * kSwMaxWpt) * 32;
+      blk[wi * 32 + lane] = mysum;
+      named_bar_sync(1 + gi, wpt * 32);
       int32_t run = 0;
-      if (active)
-        for (int sc = 0; sc < s0; ++sc) run += slice[sc * kS2Slice + lane + 1] - slice[sc * kS2Slice + lane];
-      for (int sc = s0; sc < s1; ++sc) {
-        const int32_t* sl  = slice + sc * kS2Slice;
-        const int32_t base = sl[0];
-        const int32_t T    = sl[rows] - base;
-        int32_t o0 = 0, L = 0;
-        if (active) {
-          o0 = sl[lane];
-          L  = tmax(sl[lane + 1] - o0, 0);
-        }
-        const int32_t pe         = o0 - base;
-        const int32_t run_before = run;
-        const uint8_t* src       = var0 + run;
-        run += L;
-        if (T <= 0) continue;
-        uint8_t* D     = s_chars[sc] + base;
-        const int maxL = __reduce_max_sync(0xffffffffu, L);
-        if (!h.safe && maxL <= 32 && T <= 1024) {
-          // ---- fast: word-granular copy into the staging line, then aligned 16-byte flush ----------
-          // everything below addresses shared memory through 32-bit shared-space addresses (explicit
-          // ld.shared / st.shared: the generic pointers above would compile to LD/ST + 64-bit math)
-          const int a         = static_cast<int>(reinterpret_cast<uintptr_t>(D) & 15);
-          const int d         = a + pe;                 // staging byte of this lane's string
-          const int dsh       = d & 3;
-          const uint32_t srcs = pay_s + static_cast<uint32_t>(rowsm_lane + run_before);
-          const int ssh       = static_cast<int>(srcs & 3u);
-          const int dlt       = ssh - dsh;
-          const int pre       = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
-          const uint32_t sp   = srcs - pre;
-          const int sh        = (dlt & 3) * 8;
-          const int end       = dsh + L;                 // one past the last staging byte, relative to word w0
-          const int kfull1    = end >> 2;                // full words: [dsh ? 1 : 0, kfull1)
-          const uint32_t ds   = stg_s + static_cast<uint32_t>(d);
-          const uint32_t w0s  = ds - dsh;
-          const int lim       = L > 0 ? L + pre : 0;     // source word k overlaps the string iff 4k < lim
-          const int Kmax      = (maxL + 6) >> 2;         // warp-uniform bound on kfull1 (<= 9)
-          // edge bytes straight from the source: the first nh bytes when the string starts inside a staging word,
-          // the last nt bytes when it ends inside one
-          const int nh = dsh ? tmin(L, 4 - dsh) : 0;
-          const int nt = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
-          uint32_t hb[3], tb[3];
+      for (int w2 = 0; w2 < wi; ++w2) run += blk[w2 * 32 + lane];
+      uint32_t var_s   = 0;   // staged: shared address of the lane's variable section
+      uint64_t var_g   = 0;   // direct: its global address
+      if (!direct) {
+        var_s = pay_s + static_cast<uint32_t>(active ? rowsm0[s * 32 + lane] : 0);
+      } else {
+        var_g = reinterpret_cast<uint64_t>(p.rows) +
+                (active ? static_cast<uint64_t>(static_cast<uint32_t>(p.row_offsets[h.r0 + lane])) + p.size_per_row : 0);
+      }
 #pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            hb[t] = tb[t] = 0;
-            if (t < nh) hb[t] = lds_u8(srcs + t);
-            if (t < nt) tb[t] = lds_u8(srcs + (L - nt) + t);
-          }
-          // all source words first (independent loads), then shift + store
-          uint32_t w[10];
-#pragma unroll
-          for (int k = 0; k < 10; ++k) {
-            w[k] = 0;
-            const bool need = k == 0 ? (lim > 0 && pre < 4) : (4 * k < lim);
-            if (need) w[k] = lds_u32(sp + 4 * k);
-          }
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            if (t < nh) sts_u8(ds + t, hb[t]);
-            if (t < nt) sts_u8(ds + (L - nt) + t, tb[t]);
-          }
-#pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            if (k < Kmax) {
-              const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
-              const bool full  = k == 0 ? (dsh == 0 && kfull1 > 0) : (k < kfull1);
-              if (full) sts_u32(w0s + 4 * k, y);
+      for (int j = 0; j < kSwMaxCpw; ++j) {
+        if (j < ncol) {  // warp-uniform
+          const int32_t L  = len[j];
+          const int32_t pe = inc[j] - L;
+          const int32_t T  = __shfl_sync(0xffffffffu, inc[j], last);
+          const int32_t bj = __shfl_sync(0xffffffffu, base_l, j);
+          const int32_t rb = run;
+          run += L;
+          if (semi && lane < last) asm volatile("st.global.s32 [%0], %1;" ::"l"(s_offs[c0 + j] + h.r0 + 1 + lane), "r"(bj + inc[j]));
+          if (T > 0) {
+            uint8_t* D     = s_chars[c0 + j] + bj;
+            const int maxL = __reduce_max_sync(0xffffffffu, L);
+            if (!direct && maxL <= 32 && T <= 1024) {
+              const int a = static_cast<int>(reinterpret_cast<uintptr_t>(D) & 15);
+              copy_shared_to_staging(var_s + static_cast<uint32_t>(rb), stg_s + static_cast<uint32_t>(a + pe), L, maxL);
+              __syncwarp();
+              flush_staging_line(stg_s, D, a, T, lane);
+              __syncwarp();
+            } else {
+              const uint64_t src = direct ? var_g + static_cast<uint64_t>(rb)
+                                          : reinterpret_cast<uint64_t>(payload0 + static_cast<size_t>(s) * stage_span + kSwFront) +
+                                              static_cast<uint64_t>(active ? rowsm0[s * 32 + lane] : 0) + static_cast<uint64_t>(rb);
+              gather_bytes_slow(D, static_cast<uint32_t>(T), static_cast<uint32_t>(pe), src, last, lane);
             }
-          }
-          __syncwarp();
-          flush_staging_line(stg_s, D, a, T, lane);
-          __syncwarp();
-        } else {
-          // ---- slow: long strings / SAFE tiles: lane = destination byte, source row by shuffle search ----
-          const int last       = rows - 1;
-          const uint32_t upe   = static_cast<uint32_t>(pe);
-          const uint32_t bound = (static_cast<uint32_t>(T) + 31u) & ~31u;
-          const uint64_t sbase = reinterpret_cast<uint64_t>(src);
-          for (uint32_t q = lane; q < bound; q += 32) {
-            int j = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const int cand   = j + step;
-              const uint32_t v = __shfl_sync(0xffffffffu, upe, cand & 31);
-              if (cand <= last && v <= q) j = cand;
-            }
-            const uint32_t pj = __shfl_sync(0xffffffffu, upe, j);
-            const uint64_t sj = __shfl_sync(0xffffffffu, sbase, j);
-            if (q < static_cast<uint32_t>(T)) D[q] = *reinterpret_cast<const uint8_t*>(sj + (q - pj));
           }
         }
       }
@@ -681,56 +644,71 @@ __global__ void __launch_bounds__(kS2Threads, 1) strings2_kernel(const __grid_co
   }
 }
 
-static size_t strings2_smem_bytes(int nstr)
+static size_t strings_wide_smem_bytes(int nstr, int stage_bytes, int wpt)
 {
-  size_t b = static_cast<size_t>(kS2Stages) * (kS2Front + kS2StageBytes + kS2Back);
-  b += static_cast<size_t>(kS2Stages) * kS2Slice * 4;
-  b += static_cast<size_t>(kS2Stages) * nstr * kS2Slice * 4;
-  b += static_cast<size_t>(kS2Stages) * sizeof(S2Hdr) + 2 * kS2Stages * 8;
-  b += static_cast<size_t>(nstr) * 16 + 16;
-  b += static_cast<size_t>(kS2Consumers) * kS2StageLine;
+  size_t b = static_cast<size_t>(kSwStages) * (kSwFront + stage_bytes + kSwBack);
+  b += static_cast<size_t>(kSwStages) * 32 * 4 + static_cast<size_t>(kSwStages) * sizeof(SwHdr) + 2 * kSwStages * 8;
+  b += static_cast<size_t>(nstr) * 16;
+  b += static_cast<size_t>(2) * kSwNG * kSwMaxWpt * 32 * 4 + 16;
+  b += static_cast<size_t>(kSwNG) * wpt * kSwLine;
   return (b + 127) & ~size_t{127};
 }
 
+// Can the fast gather serve this schema?  (Host-side, per plan: phase 1 and phase 2 must agree on the offsets
+// protocol.)
+bool strings_wide_eligible(const srj_plan* plan)
+{
+  const int nstr = plan->num_string_columns;
+  return nstr >= SRJ_KNOB("SRJ_SW_MINCOLS", 8) && nstr <= kSwMaxWpt * kSwMaxCpw;
+}
+
 int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
-                             int64_t num_rows, const int32_t* const* d_offsets, uint8_t* const* d_chars,
-                             const int64_t* d_status, cudaStream_t stream)
+                             int64_t num_rows, int32_t* const* d_offsets, uint8_t* const* d_chars,
+                             const int64_t* d_status, bool semi, cudaStream_t stream)
 {
   const int nstr = plan->num_string_columns;
   if (nstr == 0 || num_rows == 0) return SRJ_OK;
   int dev = 0, nsm = 0;
   SRJ_CUDA_TRY(cudaGetDevice(&dev));
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  // strings2 splits the STRING columns of a 32-row tile over its 19 consumer warps: it needs many columns to fill
-  // them.  Tables with few STRING columns take the task-parallel generic kernel (which follows the stored offsets,
-  // so it serves canonical and non-canonical rows alike).
-  const char* e_min  = getenv("SRJ_S2_MINCOLS");  // tuning knob (development)
-  const int min_cols = e_min ? atoi(e_min) : kS2MinCols;
-  const bool fast    = d_status != nullptr && nstr <= kS2MaxCols && nstr >= min_cols;
+  // The fast gather splits the STRING columns of a 32-row tile over the warps of a group: it needs a few columns to
+  // fill them.  Tables with few STRING columns take the task-parallel generic kernel (which follows the stored
+  // offsets, so it serves canonical and non-canonical rows alike).
+  const bool fast = d_status != nullptr && strings_wide_eligible(plan);
   if (fast) {
-    S2Params p{};
+    SwParams p{};
     p.rows         = rows;
     p.row_offsets  = row_offsets;
     p.rows_bytes   = rows_bytes;
     p.num_rows     = num_rows;
-    p.super_rows   = kS2Rows * 8;
     p.nstr         = nstr;
     p.size_per_row = plan->size_per_row;
+    p.wpt          = std::min(kSwMaxWpt, (nstr + 3) / 4);          // >= 4 columns per warp when there are few
+    p.cpw          = (nstr + p.wpt - 1) / p.wpt;
+    p.semi         = semi ? 1 : 0;
     p.offsets      = d_offsets;
     p.chars        = d_chars;
     p.status       = d_status;
-    const int64_t ns   = (num_rows + p.super_rows - 1) / p.super_rows;
-    const int64_t grid = std::min<int64_t>(nsm, ns);
-    const size_t smem  = strings2_smem_bytes(nstr);
-    SRJ_CUDA_TRY(cudaFuncSetAttribute(strings2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    strings2_kernel<<<static_cast<unsigned>(grid), kS2Threads, smem, stream>>>(p);
+    // stage = the variable sections of 32 average rows + 25 %, within what shared memory leaves
+    const size_t fixed_smem = strings_wide_smem_bytes(nstr, 0, p.wpt);
+    const int64_t cap       = (static_cast<int64_t>(232448 - fixed_smem) / kSwStages) & ~int64_t{15};
+    const int64_t avg_var   = std::max<int64_t>(0, rows_bytes / num_rows - plan->size_per_row) + 16;
+    int64_t stage           = (avg_var * 32 * 5 / 4 + 1023) & ~int64_t{1023};
+    stage                   = std::max<int64_t>(4096, std::min(stage, cap));
+    if (const int kb = SRJ_KNOB("SRJ_SW_STAGE_KB", 0)) stage = std::min<int64_t>(cap, static_cast<int64_t>(kb) * 1024);
+    p.stage_bytes           = static_cast<int32_t>(stage);
+    const int64_t ntiles    = (num_rows + 31) / 32;
+    const int64_t grid      = std::min<int64_t>(nsm, ntiles);
+    const size_t smem       = strings_wide_smem_bytes(nstr, p.stage_bytes, p.wpt);
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(strings_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    strings_wide_kernel<<<static_cast<unsigned>(grid), (1 + kSwNG * p.wpt) * 32, smem, stream>>>(p);
   }
   // generic kernel: does the work only when the status word flags non-canonical rows (or is absent)
   const int64_t ntiles = (num_rows + 31) / 32;
   const int64_t grid   = std::min<int64_t>(ntiles, static_cast<int64_t>(nsm) * 8);
   strings_from_rows_kernel<<<static_cast<unsigned>(grid), kStrWarps * 32, 0, stream>>>(
     rows, row_offsets, plan->fixed_row_size, num_rows, nstr, plan->d_string_start, d_offsets, d_chars, ntiles,
-    fast ? d_status : nullptr);
+    fast ? d_status : nullptr, semi ? 1 : 0);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }
