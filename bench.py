@@ -267,7 +267,7 @@ def run_ours(args, wl, rank, world):
 
     def step():
         N.check(lib.srj_convert_from_rows_fixed(plan.handle, rows.data_ptr(), None, rows.numel(), n, carr,
-                                                nulls.data_ptr(), None, C.byref(fh) if fh else None, st))
+                                                nulls.data_ptr(), None, C.byref(fh) if fh else None, None, st))
 
     # correctness gate inside the bench: round trip equals the source columns (cheap, on device)
     step()
@@ -502,15 +502,39 @@ def run_c3(args, wl, rank, world):
             outs.append((o, carr))
         nulls = torch.zeros(len(types), dtype=torch.int64, device="cuda")
         totals = torch.zeros(len(types) + 1, dtype=torch.int64, device="cuda")
+        wsb = lib.srj_from_rows_workspace_bytes(plan.handle, nb)
+        wss = [torch.empty(max(wsb, 8), dtype=torch.uint8, device="cuda") for _ in range(pool)]   # one workspace per call pair
+        overlap = os.environ.get("SRJ_BENCH_OVERLAP") == "1"
+        if overlap:
+            stream2 = torch.cuda.Stream()
+            st2 = int(stream2.cuda_stream)
+            tot_slot = [torch.zeros(len(types) + 1, dtype=torch.int64, device="cuda") for _ in range(pool)]
+            nul_slot = [torch.zeros(len(types), dtype=torch.int64, device="cuda") for _ in range(pool)]
+            ev1 = [torch.cuda.Event() for _ in range(pool)]
+            ev2 = [torch.cuda.Event() for _ in range(pool)]
+            used = [False] * pool
 
         def convert(i):
             bt = batches[i % pool]
             o, carr = outs[i % pool]
             rv = bt["rows"]
+            if overlap:
+                k = i % pool
+                if used[k]:
+                    stream.wait_event(ev2[k])          # phase 1 reuses the slot's outputs: phase 2 of its last use is done
+                N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                        nb, carr, nul_slot[k].data_ptr(), tot_slot[k].data_ptr(), None, wss[k].data_ptr(), st))
+                ev1[k].record(stream)
+                stream2.wait_event(ev1[k])
+                N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                          nb, carr, tot_slot[k].data_ptr(), wss[k].data_ptr(), st2))
+                ev2[k].record(stream2)
+                used[k] = True
+                return
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, st))
+                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, wss[i % pool].data_ptr(), st))
             N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                      nb, carr, totals.data_ptr(), st))
+                                                      nb, carr, totals.data_ptr(), wss[i % pool].data_ptr(), st))
         kernels_per_batch = 1 + 3 + 1
         metric = "rows_per_sec_convert_from_rows"
     else:
@@ -574,6 +598,8 @@ def run_c3(args, wl, rank, world):
     t0.record(stream)
     for _ in range(args.steps):
         step()
+    if args.direction == "from_rows" and overlap:
+        stream.wait_stream(stream2)
     t1.record(stream)
     barrier()
     if cuprof:
@@ -584,6 +610,26 @@ def run_c3(args, wl, rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_per_step = float(tt[0]) / args.steps
     rows_step = nbatches * nb
+    phases = None
+    if args.direction == "from_rows" and os.environ.get("SRJ_BENCH_PHASES") == "1":
+        # diagnostics: the two C-ABI calls of a batch timed separately (events around each call, 3 passes over the pool)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        acc = [0.0, 0.0]
+        cnt = 0
+        for i in range(3 * pool):
+            bt = batches[i % pool]
+            o, carr = outs[i % pool]
+            rv = bt["rows"]
+            ev[0].record(stream)
+            N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, wss[i % pool].data_ptr(), st))
+            ev[1].record(stream)
+            N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
+                                                      nb, carr, totals.data_ptr(), wss[i % pool].data_ptr(), st))
+            ev[2].record(stream)
+            torch.cuda.synchronize()
+            acc[0] += ev[0].elapsed_time(ev[1]); acc[1] += ev[1].elapsed_time(ev[2]); cnt += 1
+        phases = {"phase1_ms": acc[0] / cnt, "phase2_ms": acc[1] / cnt}
     value = world * rows_step / (ms_per_step * 1e-3)
     peak, peak_src = load_peaks()
     achieved = alg_step / (ms_per_step * 1e-3) / 1e9
@@ -661,7 +707,7 @@ def run_c3(args, wl, rank, world):
                                      "avg_row_bytes": batches[0]["rows"].child.size / nb,
                                      "l2": "each batch touches ~%.1f GB >> 126 MB L2; pool of %d distinct batches" % (alg[0] / 1e9, pool)},
                           "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                          "gpu_launches": args.steps * nbatches * kernels_per_batch, "clocks": clocks}))
+                          "gpu_launches": args.steps * nbatches * kernels_per_batch, "clocks": clocks, "phases": phases}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -159,11 +159,22 @@ SRJ_API int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, in
  *                 status word for phase 2: bit 0 set = some row does not use the canonical string layout
  *                 (pair.offset != size_per_row + lengths of the preceding STRING columns); phase 2 then
  *                 follows the stored pair offsets exactly like copy_strings_from_rows (RC:1143) instead of
- *                 its fast path.
+ *                 its fast path.  Bit 1 set = a STRING column's chars exceed INT32_MAX (the caller maps it to
+ *                 SRJ_EOVERFLOW / CudfColumnSizeOverflowException; the totals themselves are exact int64).
+ *                 The STRING offsets children are complete only after phase 2.
  * If hash_kind != SRJ_HASH_NONE the row hash of the listed key columns is computed from the same
  * shared-memory tile and written to hash_out (int64 for xxhash64, int32 otherwise): the fused
  * from_rows + partition-hash of BASELINE config 4.  Keys must be fixed-width columns.
  */
+/*
+ * Workspace of one phase-1 / phase-2 call pair: srj_from_rows_workspace_bytes(plan, num_rows) bytes of device memory
+ * (0 for schemas that need none; then NULL may be passed).  Phase 1 leaves there what phase 2 needs besides the
+ * offsets children (for wide tables: the chars of every STRING column before each 32-row group -- the offsets
+ * children themselves hold group-local sums between the two calls and are finished by phase 2), so the same
+ * buffer must be passed to both calls and must not be shared by two conversions in flight.
+ */
+SRJ_API int64_t srj_from_rows_workspace_bytes(const srj_plan* plan, int64_t num_rows);
+
 typedef enum srj_hash_kind { SRJ_HASH_NONE = 0, SRJ_HASH_XXHASH64 = 1, SRJ_HASH_MURMUR3_32 = 2, SRJ_HASH_HIVE = 3 } srj_hash_kind;
 
 typedef struct srj_fused_hash {
@@ -178,14 +189,15 @@ SRJ_API int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* row
                                         const int32_t* row_offsets, int64_t rows_bytes,
                                         int64_t num_rows, const srj_column* cols,
                                         int64_t* d_null_counts, int64_t* d_char_totals,
-                                        const srj_fused_hash* hash /* may be NULL */, void* stream);
+                                        const srj_fused_hash* hash /* may be NULL */, void* workspace,
+                                        void* stream);
 /* Phase 2 (async): gather the chars of every STRING column (copy_strings_from_rows, RC:1110-1150).
  * d_char_totals is the buffer phase 1 filled (its status word selects the fast path); NULL = always
  * follow the stored pair offsets. */
 SRJ_API int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows,
                                           const int32_t* row_offsets, int64_t rows_bytes, int64_t num_rows,
                                           const srj_column* cols, const int64_t* d_char_totals,
-                                          void* stream);
+                                          const void* workspace, void* stream);
 
 /* ---- row hashes: Hash.xxhash64 / murmurHash32 / hiveHash, hash/hash.hpp:40-74 ------------------ */
 #define SRJ_DEFAULT_XXHASH64_SEED 42 /* hash/hash.hpp:27 */

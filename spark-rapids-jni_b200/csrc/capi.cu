@@ -133,10 +133,6 @@ static bool use_wide_from_rows(const srj_plan* plan, const int32_t* row_offsets,
   return plan->wide.enabled && row_offsets != nullptr && !(hash && hash->kind != SRJ_HASH_NONE);
 }
 
-// true: between the two phases the STRING offsets are group-local inclusive sums + absolute group bases (phase 2
-// finishes them while it gathers); false: phase 1 leaves finished offsets.
-static bool wide_offsets_protocol(const srj_plan* plan) { return plan->wide.enabled && SRJ_KNOB("SRJ_W_FINALIZE", 0) == 0; }
-
 static int check_cols(const srj_plan* plan, const srj_column* cols, int64_t num_rows, const char* who)
 {
   if (!plan || (plan->num_columns > 0 && !cols)) { set_error("%s: null argument", who); return SRJ_EINVAL; }
@@ -475,9 +471,15 @@ int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t nu
 // ---------------------------------------------------------------------------------------------------
 // convert_from_rows
 // ---------------------------------------------------------------------------------------------------
+int64_t srj_from_rows_workspace_bytes(const srj_plan* plan, int64_t num_rows)
+{
+  if (!plan || num_rows <= 0 || !plan->wide.enabled) return 0;
+  return wide_workspace_bytes(plan, num_rows);
+}
+
 int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
                                 int64_t rows_bytes, int64_t num_rows, const srj_column* cols, int64_t* d_null_counts,
-                                int64_t* d_char_totals, const srj_fused_hash* hash, void* stream_)
+                                int64_t* d_char_totals, const srj_fused_hash* hash, void* workspace, void* stream_)
 {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_from_rows");
@@ -508,32 +510,15 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
     }
     if (!cols[c].null_mask && num_rows > 0) { set_error("convert_from_rows: column %d has no null mask buffer (always allocated, RC:2220)", c); return SRJ_EINVAL; }
   }
+  if (use_wide_from_rows(plan, row_offsets, hash)) {
+    // wide variable-width table: per-row slabs; the pointer tables travel as kernel parameters and the kernels publish
+    // null counts / totals / status themselves: no memset, no staging copy, no hidden allocation
+    if (num_rows > 0 && !workspace) { set_error("convert_from_rows: this schema needs a workspace (srj_from_rows_workspace_bytes)"); return SRJ_EINVAL; }
+    return launch_from_rows_wide(plan, rows, row_offsets, rows_bytes, num_rows, cols, d_null_counts, d_char_totals, workspace,
+                                 SRJ_KNOB("SRJ_W_FINALIZE", 0) != 0, stream);
+  }
   if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
   if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * (nc + 1), stream));
-  if (use_wide_from_rows(plan, row_offsets, hash)) {
-    // wide variable-width table: per-row slabs, offsets leave phase 1 as group-local sums + absolute group bases
-    // pointer tables: [col_ptr nc][masks nc][str_offsets nstr] + group totals
-    std::vector<void*> tab(2 * static_cast<size_t>(nc) + nstr);
-    for (int c = 0; c < nc; ++c) {
-      tab[c]      = plan->type_ids[c] == SRJ_STRING ? static_cast<void*>(cols[c].offsets) : cols[c].data;
-      tab[nc + c] = cols[c].null_mask;
-    }
-    for (int s = 0; s < nstr; ++s) tab[2 * nc + s] = cols[plan->string_columns[s]].offsets;
-    const size_t tab_bytes = (tab.size() * sizeof(void*) + 15) & ~size_t{15};
-    const size_t agg_bytes = static_cast<size_t>(wide_agg_bytes(plan, num_rows));
-    TableLease sc(plan, stream);
-    rc = sc.acquire(tab_bytes + agg_bytes + 16);
-    if (rc != SRJ_OK) return rc;
-    memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
-    rc = sc.upload(tab.size() * sizeof(void*));
-    if (rc != SRJ_OK) return rc;
-    auto** d = static_cast<void**>(sc.dev());
-    return launch_from_rows_wide(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nc),
-                                 reinterpret_cast<int32_t* const*>(d + 2 * nc), d_null_counts, d_char_totals,
-                                 d_char_totals ? d_char_totals + nc : nullptr,
-                                 reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(sc.dev()) + tab_bytes),
-                                 !wide_offsets_protocol(plan), stream);
-  }
   const size_t nent = plan->fr_entries.size();
   // pointer tables: [ent_dst nent][masks nc][str_offsets nstr] + scan partials
   std::vector<void*> tab(nent + nc + nstr);
@@ -559,7 +544,7 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
   if (nstr > 0) {
     uint8_t* tail = static_cast<uint8_t*>(sc.dev()) + tab_bytes;
     rc = launch_string_offsets_scan(reinterpret_cast<int32_t* const*>(d + nent + nc), plan->d_string_cols, nstr, num_rows,
-                                    d_char_totals, d_char_totals ? d_char_totals + nc : nullptr, tail, stream);
+                                    d_char_totals, d_char_totals ? d_char_totals + nc : nullptr, tail, plan->wide.enabled, stream);
     if (rc != SRJ_OK) return rc;
   }
   return SRJ_OK;
@@ -567,7 +552,7 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
 
 int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
                                   int64_t rows_bytes, int64_t num_rows, const srj_column* cols,
-                                  const int64_t* d_char_totals, void* stream_)
+                                  const int64_t* d_char_totals, const void* workspace, void* stream_)
 {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_from_rows_strings");
@@ -575,10 +560,20 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
   const int nstr = plan->num_string_columns;
   if (nstr == 0 || num_rows == 0) return SRJ_OK;
   if (!rows || !row_offsets) { set_error("convert_from_rows_strings: rows / offsets are null"); return SRJ_EINVAL; }
+  for (int s = 0; s < nstr; ++s)
+    if (!cols[plan->string_columns[s]].offsets) { set_error("convert_from_rows_strings: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
+  const int64_t* d_status = d_char_totals ? d_char_totals + plan->num_columns : nullptr;
+  // wide tables: phase 1 (from_rows_wide.cu) left group-local offsets + the group bases in the workspace
+  const uint32_t* d_bases = nullptr;
+  if (plan->wide.enabled && SRJ_KNOB("SRJ_W_FINALIZE", 0) == 0) {
+    if (!workspace) { set_error("convert_from_rows_strings: this schema needs the workspace phase 1 filled"); return SRJ_EINVAL; }
+    d_bases = wide_workspace_bases(plan, num_rows, workspace);
+  }
+  if (strings_fast_path(plan, d_status))   // pointer tables travel as kernel parameters
+    return launch_strings_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, cols, nullptr, d_status, d_bases, stream);
   std::vector<void*> tab(2 * static_cast<size_t>(nstr));
   for (int s = 0; s < nstr; ++s) {
     const srj_column& c = cols[plan->string_columns[s]];
-    if (!c.offsets) { set_error("convert_from_rows_strings: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
     tab[s]        = c.offsets;
     tab[nstr + s] = c.data;  // may be NULL only when the column has no chars at all
   }
@@ -588,11 +583,8 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
   memcpy(sc.host(), tab.data(), tab.size() * sizeof(void*));
   rc = sc.upload(tab.size() * sizeof(void*));
   if (rc != SRJ_OK) return rc;
-  auto** d = static_cast<void**>(sc.dev());
-  return launch_strings_from_rows(plan, rows, row_offsets, rows_bytes, num_rows,
-                                  reinterpret_cast<int32_t* const*>(d), reinterpret_cast<uint8_t* const*>(d + nstr),
-                                  d_char_totals ? d_char_totals + plan->num_columns : nullptr,
-                                  wide_offsets_protocol(plan), stream);
+  return launch_strings_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, cols, static_cast<void* const*>(sc.dev()),
+                                  d_status, d_bases, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

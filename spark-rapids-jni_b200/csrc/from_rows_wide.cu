@@ -35,6 +35,7 @@
 namespace srj {
 
 constexpr int kWMaxStages = 4;
+constexpr int kWMaxGrid   = 256;  // CTAs (one per SM)
 constexpr int kWMaxG      = 4;
 constexpr int kWSlack     = 32;
 
@@ -64,11 +65,23 @@ struct WideParams {
   const WideEntry* entries;
   const WideSlab* slabs;
   const int32_t* string_start;  // [nstr]
-  void* const* col_ptr;         // [ncols] column data, STRING: offsets
-  uint32_t* const* masks;       // [ncols]
-  unsigned long long* null_counts;
-  unsigned long long* status;
-  uint32_t* agg;  // [nstr][ngroups] chars of each 32-row group
+  int32_t want_nulls;           // null counts requested
+  uint32_t* agg;                // scratch [nstr][ngroups]: chars of each 32-row group
+  int32_t* null_part;           // scratch [grid][ncols]: per-CTA null counts (reduced by the scan kernel: no memset, no atomics)
+  int32_t* bad_part;            // scratch [grid]: per-CTA "non-canonical row seen" flags
+  uint32_t* sync_words;         // scratch [2]: {ticket, overflow} of the scan kernel, zeroed here by CTA 0
+};
+
+// Per-call pointer tables travel as kernel parameters (no staging copy, no allocation): the column count of a wide
+// plan is capped so that they fit comfortably in the 32 KB parameter space.
+constexpr int kWMaxCols = 448;
+struct WidePtrTab {
+  void* col[kWMaxCols];       // column data, STRING: offsets
+  uint32_t* mask[kWMaxCols];
+};
+struct WideScanTab {
+  int32_t* offs[kWMaxCols];   // [nstr] offsets of the STRING columns
+  int32_t scol[kWMaxCols];    // [nstr] their schema column
 };
 
 __device__ __forceinline__ WDesc lds_desc(uint32_t a)
@@ -84,6 +97,7 @@ __device__ __forceinline__ WDesc lds_desc(uint32_t a)
 
 struct WTables {
   uint32_t desc;  // shared-space address of the descriptor table
+  const int16_t* first;  // [nslabs][6][NCW] first unit of (slab, class) for each consumer warp
   const WideSlab* slabs;
   const int32_t* str_start;
   uint32_t* const* masks;
@@ -107,19 +121,18 @@ __device__ __forceinline__ Reg<W> ld_bytes(const uint8_t* src)
   return r;
 }
 
-// first unit >= cb of this slab whose position in the slab's list is congruent to w (mod NCW)
-template <int NCW>
-__device__ __forceinline__ int first_unit(int cb, int cb0, int w)
+// first unit >= cb of this slab whose position in the slab's list is congruent to w (mod NCW): the units of a slab are
+// dealt round-robin to the consumer warps across the width classes.  Tabulated once per CTA (s_first).
+__device__ __forceinline__ int first_unit_of(int cb, int cb0, int w, int ncw)
 {
-  return cb + (w + NCW - (cb - cb0) % NCW) % NCW;
+  return cb + (w + ncw - (cb - cb0) % ncw) % ncw;
 }
 
 // ---- full tiles: G row groups, rows staged, no predicates ------------------------------------------------
 template <int W, int G, int NCW>
-__device__ __forceinline__ void units_full(uint32_t desc, int ub, int ue, int cb0, int w, const uint32_t (&ra)[G],
-                                           int64_t rowoff)
+__device__ __forceinline__ void units_full(uint32_t desc, int u0, int ue, const uint32_t (&ra)[G], int64_t rowoff)
 {
-  for (int u = first_unit<NCW>(ub, cb0, w); u < ue; u += 2 * NCW) {
+  for (int u = u0; u < ue; u += 2 * NCW) {
     const bool has1 = u + NCW < ue;
     const WDesc d0  = lds_desc(desc + 16u * u);
     const WDesc d1  = lds_desc(desc + 16u * (has1 ? u + NCW : u));
@@ -150,11 +163,11 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t x, int lane)
 }
 
 template <int G, int NCW>
-__device__ __forceinline__ bool strings_full(const WideParams& p, const WTables& t, const WideSlab& sl, int w,
+__device__ __forceinline__ bool strings_full(const WideParams& p, const WTables& t, const WideSlab& sl, int u0,
                                              const uint32_t (&ra)[G], int64_t rowoff, int64_t group0, int lane)
 {
   bool bad = false;
-  for (int u = first_unit<NCW>(sl.cb[5], sl.cb[0], w); u < sl.cb[6]; u += NCW) {
+  for (int u = u0; u < sl.cb[6]; u += NCW) {
     const WDesc d  = lds_desc(t.desc + 16u * u);
     const int prel = d.sidx > 0 ? t.str_start[d.sidx - 1] - sl.begin : -1;
     uint32_t so[G], ln[G], ex[G];
@@ -221,11 +234,11 @@ __device__ __forceinline__ void validity_tile(const WideParams& p, const WTables
 
 // ---- partial tiles (the table's last rows) and SAFE tiles (unaligned rows: global memory, byte-wise) ----------
 template <int W, int NCW, bool SAFE>
-__device__ __forceinline__ void units_slow(uint32_t desc, int ub, int ue, int cb0, int w, const uint32_t* ra,
+__device__ __forceinline__ void units_slow(uint32_t desc, int u0, int ue, const uint32_t* ra,
                                            const uint8_t* const* rp, int64_t rowoff, int rows, int lane)
 {
   const int Gt = (rows + 31) >> 5;
-  for (int u = first_unit<NCW>(ub, cb0, w); u < ue; u += NCW) {
+  for (int u = u0; u < ue; u += NCW) {
     const WDesc d = lds_desc(desc + 16u * u);
     uint8_t* p0   = d.dst + rowoff * W;
     for (int g = 0; g < Gt; ++g) {
@@ -240,13 +253,13 @@ __device__ __forceinline__ void units_slow(uint32_t desc, int ub, int ue, int cb
 }
 
 template <int NCW, bool SAFE>
-__device__ __forceinline__ bool strings_slow(const WideParams& p, const WTables& t, const WideSlab& sl, int w,
+__device__ __forceinline__ bool strings_slow(const WideParams& p, const WTables& t, const WideSlab& sl, int u0,
                                              const uint32_t* ra, const uint8_t* const* rp, int64_t rowoff, int64_t group0,
                                              int rows, int lane)
 {
   bool bad     = false;
   const int Gt = (rows + 31) >> 5;
-  for (int u = first_unit<NCW>(sl.cb[5], sl.cb[0], w); u < sl.cb[6]; u += NCW) {
+  for (int u = u0; u < sl.cb[6]; u += NCW) {
     const WDesc d  = lds_desc(t.desc + 16u * u);
     const int prel = d.sidx > 0 ? t.str_start[d.sidx - 1] - sl.begin : -1;
     uint32_t* dst  = reinterpret_cast<uint32_t*>(d.dst) + rowoff;
@@ -292,12 +305,13 @@ __device__ __noinline__ bool tile_slow(const WideParams& p, const WTables& t, in
     }
   }
   const int64_t rowoff = r0 + lane;
-  units_slow<16, NCW, SAFE>(t.desc, sl.cb[0], sl.cb[1], sl.cb[0], w, ra, rp, rowoff, rows, lane);
-  units_slow<8, NCW, SAFE>(t.desc, sl.cb[1], sl.cb[2], sl.cb[0], w, ra, rp, rowoff, rows, lane);
-  units_slow<4, NCW, SAFE>(t.desc, sl.cb[2], sl.cb[3], sl.cb[0], w, ra, rp, rowoff, rows, lane);
-  units_slow<2, NCW, SAFE>(t.desc, sl.cb[3], sl.cb[4], sl.cb[0], w, ra, rp, rowoff, rows, lane);
-  units_slow<1, NCW, SAFE>(t.desc, sl.cb[4], sl.cb[5], sl.cb[0], w, ra, rp, rowoff, rows, lane);
-  const bool bad = strings_slow<NCW, SAFE>(p, t, sl, w, ra, rp, rowoff, r0 >> 5, rows, lane);
+  const int16_t* fu    = t.first + (slab * 6) * NCW + w;
+  units_slow<16, NCW, SAFE>(t.desc, fu[0 * NCW], sl.cb[1], ra, rp, rowoff, rows, lane);
+  units_slow<8, NCW, SAFE>(t.desc, fu[1 * NCW], sl.cb[2], ra, rp, rowoff, rows, lane);
+  units_slow<4, NCW, SAFE>(t.desc, fu[2 * NCW], sl.cb[3], ra, rp, rowoff, rows, lane);
+  units_slow<2, NCW, SAFE>(t.desc, fu[3 * NCW], sl.cb[4], ra, rp, rowoff, rows, lane);
+  units_slow<1, NCW, SAFE>(t.desc, fu[4 * NCW], sl.cb[5], ra, rp, rowoff, rows, lane);
+  const bool bad = strings_slow<NCW, SAFE>(p, t, sl, fu[5 * NCW], ra, rp, rowoff, r0 >> 5, rows, lane);
   if (slab == p.nslabs - 1) validity_tile<NCW, SAFE>(p, t, p.validity_offset - sl.begin, w, ra, rp, r0, rows, lane);
   return bad;
 }
@@ -311,17 +325,25 @@ __device__ __forceinline__ bool tile_full(const WideParams& p, const WTables& t,
 #pragma unroll
   for (int g = 0; g < G; ++g) ra[g] = pay_s + static_cast<uint32_t>(rpos[g * 32 + lane]);
   const int64_t rowoff = r0 + lane;
-  units_full<16, G, NCW>(t.desc, sl.cb[0], sl.cb[1], sl.cb[0], w, ra, rowoff);
-  units_full<8, G, NCW>(t.desc, sl.cb[1], sl.cb[2], sl.cb[0], w, ra, rowoff);
-  units_full<4, G, NCW>(t.desc, sl.cb[2], sl.cb[3], sl.cb[0], w, ra, rowoff);
-  units_full<2, G, NCW>(t.desc, sl.cb[3], sl.cb[4], sl.cb[0], w, ra, rowoff);
-  units_full<1, G, NCW>(t.desc, sl.cb[4], sl.cb[5], sl.cb[0], w, ra, rowoff);
-  const bool bad = strings_full<G, NCW>(p, t, sl, w, ra, rowoff, r0 >> 5, lane);
+  const int16_t* fu    = t.first + (slab * 6) * NCW + w;
+  units_full<16, G, NCW>(t.desc, fu[0 * NCW], sl.cb[1], ra, rowoff);
+  units_full<8, G, NCW>(t.desc, fu[1 * NCW], sl.cb[2], ra, rowoff);
+  units_full<4, G, NCW>(t.desc, fu[2 * NCW], sl.cb[3], ra, rowoff);
+  units_full<2, G, NCW>(t.desc, fu[3 * NCW], sl.cb[4], ra, rowoff);
+  units_full<1, G, NCW>(t.desc, fu[4 * NCW], sl.cb[5], ra, rowoff);
+  const bool bad = strings_full<G, NCW>(p, t, sl, fu[5 * NCW], ra, rowoff, r0 >> 5, lane);
   if (slab == p.nslabs - 1) validity_tile<NCW, false>(p, t, p.validity_offset - sl.begin, w, ra, nullptr, r0, G * 32, lane);
   return bad;
 }
 
-// ---- producer ---------------------------------------------------------------------------------------
+// ---- producers ------------------------------------------------------------------------------------------
+// One TMA bulk copy per (row, slab) costs its issuing warp ~70 cycles (five R2UR moves + UBLKCP per lane, one lane
+// at a time), so kWProducers warps -- one per scheduler -- share the rows of a tile: producer q issues the copies
+// of the rows whose lane index is congruent to q.  Each arrives on the stage's full barrier with the bytes of its
+// own copies.  All of them read the row offsets of the tile (of the NEXT tile, one tile ahead), so they agree on
+// whether the tile is staged or SAFE.
+constexpr int kWProducers = 4;
+
 struct WProducerArgs {
   const uint8_t* rows;
   const int32_t* row_offsets;
@@ -335,7 +357,7 @@ struct WProducerArgs {
   const WideSlab* slabs;  // shared-memory copy
 };
 
-__device__ __noinline__ void wide_producer(const WProducerArgs p)
+__device__ __noinline__ void wide_producer(const WProducerArgs p, const int q)
 {
   const int lane       = lane_id();
   const int NS         = p.nstages;
@@ -343,6 +365,7 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
   const uintptr_t b_hi = b_lo + static_cast<uintptr_t>(p.rows_bytes);
   const bool base_ok   = (b_lo & 7) == 0;
   const int64_t ntiles = (p.num_rows + p.R - 1) / p.R;
+  const bool mine      = (lane & (kWProducers - 1)) == q;
   int it               = 0;
   auto acquire         = [&](int it_) {
     const int s        = it_ % NS;
@@ -351,6 +374,16 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
     __syncwarp();
     return s;
   };
+  auto load_offsets = [&](int64_t T, int64_t (&off)[kWMaxG]) {
+    const int64_t r0 = T * p.R;
+#pragma unroll
+    for (int k = 0; k < kWMaxG; ++k) {
+      const int64_t r = r0 + k * 32 + lane;
+      off[k]          = (k < p.G && T < ntiles && r < p.num_rows) ? static_cast<int64_t>(static_cast<uint32_t>(p.row_offsets[r])) : 0;
+    }
+  };
+  int64_t nxt[kWMaxG];
+  load_offsets(blockIdx.x, nxt);
   for (int64_t T = blockIdx.x; T < ntiles; T += gridDim.x) {
     const int64_t r0 = T * p.R;
     const int rows   = static_cast<int>(tmin<int64_t>(p.R, p.num_rows - r0));
@@ -358,26 +391,24 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
     bool mis = !base_ok;
 #pragma unroll
     for (int k = 0; k < kWMaxG; ++k) {
-      const int j = k * 32 + lane;
-      off[k]      = 0;
-      if (k < p.G && j < rows) {
-        off[k] = static_cast<int64_t>(static_cast<uint32_t>(p.row_offsets[r0 + j]));
-        if (off[k] & 7) mis = true;
-      }
+      off[k] = nxt[k];
+      if (off[k] & 7) mis = true;  // rows past the tile's end carry 0
     }
     mis = __any_sync(0xffffffffu, mis);
+    load_offsets(T + gridDim.x, nxt);  // in flight while this tile's copies are issued
     for (int sb = 0; sb < p.nslabs; ++sb, ++it) {
       const int s    = acquire(it);
       uint8_t* pay   = p.payload0 + static_cast<size_t>(s) * p.stage_span;
       int32_t* rpos  = p.rpos0 + static_cast<size_t>(s) * p.R;
-      WHdr* h        = p.hdr0 + s;
       const int sbeg = p.slabs[sb].begin, send = p.slabs[sb].end;
       uint32_t tx    = 0;
-      if (!mis) {
 #pragma unroll
-        for (int k = 0; k < kWMaxG; ++k) {
-          const int j = k * 32 + lane;
-          if (k < p.G && j < rows) {
+      for (int k = 0; k < kWMaxG; ++k) {
+        const int j = k * 32 + lane;
+        if (k < p.G && j < rows && mine) {
+          if (mis) {
+            rpos[j] = static_cast<int32_t>(off[k]);  // absolute row offset: the consumers read global memory
+          } else {
             const uintptr_t a_lo = b_lo + static_cast<uintptr_t>(off[k]) + sbeg;
             const uintptr_t a_hi = b_lo + static_cast<uintptr_t>(off[k]) + send;
             const uintptr_t fl   = a_lo & ~uintptr_t{15};
@@ -396,17 +427,12 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
             tx += static_cast<uint32_t>(t_hi - t_lo);
           }
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kWMaxG; ++k) {
-          const int j = k * 32 + lane;
-          if (k < p.G && j < rows) rpos[j] = static_cast<int32_t>(off[k]);  // absolute row offsets
-        }
       }
       uint32_t total = tx;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      if (lane == 0) {
+      if (lane == 0 && q == 0) {
+        WHdr* h = p.hdr0 + s;
         h->r0   = r0;
         h->rows = rows;
         h->slab = sb;
@@ -422,7 +448,7 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
 #pragma unroll
         for (int k = 0; k < kWMaxG; ++k) {
           const int j = k * 32 + lane;
-          if (k < p.G && j < rows) {
+          if (k < p.G && j < rows && mine) {
             const uintptr_t a_lo = b_lo + static_cast<uintptr_t>(off[k]) + sbeg;
             const uintptr_t a_hi = b_lo + static_cast<uintptr_t>(off[k]) + send;
             const uintptr_t fl   = a_lo & ~uintptr_t{15};
@@ -439,16 +465,17 @@ __device__ __noinline__ void wide_producer(const WProducerArgs p)
   }
   const int s = acquire(it);
   if (lane == 0) {
-    p.hdr0[s].rows = 0;
+    if (q == 0) p.hdr0[s].rows = 0;
     mbar_arrive(&p.full[s]);
   }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------
 template <int NCW, int G>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_wide_kernel(const __grid_constant__ WideParams p)
+__global__ void __launch_bounds__((NCW + kWProducers) * 32, 1) from_rows_wide_kernel(const __grid_constant__ WideParams p,
+                                                                                            const __grid_constant__ WidePtrTab tab)
 {
-  constexpr int kThreads = (NCW + 1) * 32;
+  constexpr int kThreads = (NCW + kWProducers) * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const int NS         = p.nstages;
   const int stage_span = p.R * p.pitch + kWSlack;  // multiple of 16
@@ -462,25 +489,38 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_wide_kernel(const
   int32_t* rpos0       = reinterpret_cast<int32_t*>(s_slabs + p.nslabs);
   int32_t* s_nulls     = rpos0 + static_cast<size_t>(NS) * p.R;
   int32_t* s_str_start = s_nulls + p.ncols;
+  int16_t* s_first     = reinterpret_cast<int16_t*>(s_str_start + p.nstr);  // [nslabs][6][NCW]
+  int* s_bad_p         = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(s_first + p.nslabs * 6 * NCW) + 3) & ~uintptr_t{3});
 
   const int tid = threadIdx.x;
   for (int i = tid; i < p.nslabs; i += kThreads) s_slabs[i] = p.slabs[i];
+  for (int i = tid; i < p.nslabs * 6 * NCW; i += kThreads) {
+    const int sb = i / (6 * NCW), k = (i / NCW) % 6, w = i % NCW;
+    s_first[i]   = static_cast<int16_t>(first_unit_of(p.slabs[sb].cb[k], p.slabs[sb].cb[0], w, NCW));
+  }
   for (int i = tid; i < p.nent; i += kThreads) {
     const WideEntry e = p.entries[i];
     WDesc d;
-    d.dst     = static_cast<uint8_t*>(p.col_ptr[e.column]) + (e.sidx >= 0 ? 4 : 0);  // lengths land at offsets[1..n]
+    d.dst     = static_cast<uint8_t*>(tab.col[e.column]) + (e.sidx >= 0 ? 4 : 0);  // lengths land at offsets[1..n]
     d.rel     = e.start - p.slabs[e.slab].begin;
     d.sidx    = e.sidx;
     s_desc[i] = d;
   }
   for (int i = tid; i < p.ncols; i += kThreads) {
-    s_masks[i] = p.masks[i];
+    s_masks[i] = tab.mask[i];
     s_nulls[i] = 0;
+  }
+  if (tid == 0) {
+    *s_bad_p = 0;
+    if (blockIdx.x == 0) {  // nothing else touches these words while this kernel runs; the scan kernel (next in the stream) uses them
+      p.sync_words[0] = 0;
+      p.sync_words[1] = 0;
+    }
   }
   for (int i = tid; i < p.nstr; i += kThreads) s_str_start[i] = p.string_start[i];
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], kWProducers);
       mbar_init(&empty[s], NCW);
     }
     fence_mbar_init();
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_wide_kernel(const
   __syncthreads();
 
   const int lane = lane_id();
-  if (warp_id() == 0) {
+  if (warp_id() < kWProducers) {
     WProducerArgs pa;
     pa.rows        = p.rows;
     pa.row_offsets = p.row_offsets;
@@ -506,10 +546,10 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_wide_kernel(const
     pa.full        = full;
     pa.empty       = empty;
     pa.slabs       = s_slabs;
-    wide_producer(pa);
+    wide_producer(pa, warp_id());
   } else {
-    const int w = warp_id() - 1;
-    const WTables t{smem_u32(s_desc), s_slabs, s_str_start, s_masks, p.null_counts ? s_nulls : nullptr};
+    const int w = warp_id() - kWProducers;
+    const WTables t{smem_u32(s_desc), s_first, s_slabs, s_str_start, s_masks, p.want_nulls ? s_nulls : nullptr};
     bool bad = false;
     for (int it = 0;; ++it) {
       const int s        = it % NS;
@@ -525,33 +565,54 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) from_rows_wide_kernel(const
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
-    if (__any_sync(0xffffffffu, bad) && lane == 0 && p.status) atomicOr(p.status, 1ull);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) *s_bad_p = 1;
   }
   __syncthreads();
-  if (p.null_counts) {
-    for (int i = tid; i < p.ncols; i += kThreads)
-      if (s_nulls[i]) atomicAdd(&p.null_counts[i], static_cast<unsigned long long>(s_nulls[i]));
-  }
+  if (p.want_nulls)
+    for (int i = tid; i < p.ncols; i += kThreads) p.null_part[static_cast<size_t>(blockIdx.x) * p.ncols + i] = s_nulls[i];
+  if (tid == 0) p.bad_part[blockIdx.x] = *s_bad_p;
 }
 
 // ---- scan over the 32-row group totals ----------------------------------------------------------------
-// offsets[c][min(32 (g + 1), n)] <- chars of column c before the end of group g (an ABSOLUTE offset); entries in
-// between keep the inclusive sums inside their group that from_rows_wide_kernel wrote.  Phase 2 (strings.cu) adds
-// the group base while it gathers; wide_finalize_offsets_kernel does it for callers of the generic path.
+// base[c][g] <- chars of column c before 32-row group g (exclusive scan of the group totals), in the caller's
+// workspace.  The offsets arrays keep the inclusive sums inside each group that from_rows_wide_kernel wrote; phase 2
+// (strings.cu) adds the group base while it gathers, wide_finalize_offsets_kernel does it when phase 1 is asked for
+// finished offsets.
 constexpr int kGsThreads = 256;
-constexpr int kGsChunk   = kGsThreads * 4;
+constexpr int kGsPer     = 16;                    // groups per thread
+constexpr int kGsChunk   = kGsThreads * kGsPer;   // groups per CTA
 
-__global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const uint32_t* agg, int64_t ngroups, int64_t num_rows,
-                                                                      int32_t* const* offsets, const int32_t* string_cols,
-                                                                      int64_t* char_totals, unsigned long long* status)
+struct WideScanParams {
+  const uint32_t* agg;
+  uint32_t* base;                   // [nstr][ngroups] chars of the column before each 32-row group
+  int64_t ngroups, num_rows;
+  int64_t* char_totals;             // [ncols + 1] or NULL (entry ncols = status word)
+  int64_t* null_counts;             // [ncols] or NULL
+  const int32_t* null_part;         // [parts][ncols]
+  const int32_t* bad_part;          // [parts]
+  uint32_t* sync_words;             // {ticket, overflow}
+  int32_t parts, ncols, nstr;
+};
+
+__global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const __grid_constant__ WideScanParams q,
+                                                                      const __grid_constant__ WideScanTab tab)
 {
   __shared__ int64_t s_warp[kGsThreads / 32];
   __shared__ int64_t s_pre;
+  __shared__ unsigned s_ticket;
+  const uint32_t* agg      = q.agg;
+  const int64_t ngroups    = q.ngroups;
+  int64_t* char_totals     = q.char_totals;
   const int c       = blockIdx.y;
   const int64_t k   = blockIdx.x;
   const uint32_t* a = agg + static_cast<int64_t>(c) * ngroups;
-  int32_t* offs     = offsets[c];
-  // chars of this column before the chunk
+  uint32_t* bs      = q.base + static_cast<int64_t>(c) * ngroups;
+  // this thread's groups first (their loads overlap the prefix pass below)
+  const int64_t g0 = k * kGsChunk + static_cast<int64_t>(threadIdx.x) * kGsPer;
+  uint32_t v[kGsPer];
+#pragma unroll
+  for (int j = 0; j < kGsPer; ++j) v[j] = (g0 + j < ngroups) ? a[g0 + j] : 0u;
+  // chars of this column before the chunk (<= 3 chunks of 16 KB for a 2 GiB batch of wide rows)
   int64_t pre = 0;
   for (int64_t i = threadIdx.x; i < k * kGsChunk; i += kGsThreads) pre += a[i];
 #pragma unroll
@@ -566,12 +627,10 @@ __global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const uint3
   __syncthreads();
   pre = s_pre;
   __syncthreads();
-  const int64_t g0 = k * kGsChunk + threadIdx.x * 4;
-  int64_t v[4];
+  int64_t tsum = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = (g0 + j < ngroups) ? static_cast<int64_t>(a[g0 + j]) : 0;
-  const int64_t tsum = v[0] + v[1] + v[2] + v[3];
-  int64_t x          = tsum;
+  for (int j = 0; j < kGsPer; ++j) tsum += v[j];
+  int64_t x = tsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -583,28 +642,55 @@ __global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const uint3
   for (int i = 0; i < warp_id(); ++i) wpre += s_warp[i];
   int64_t run = pre + wpre + x - tsum;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < kGsPer; ++j) {
     const int64_t g = g0 + j;
     if (g < ngroups) {
+      bs[g] = static_cast<uint32_t>(run);  // exclusive: chars before group g
       run += v[j];
-      const int64_t pos = tmin<int64_t>(32 * (g + 1), num_rows);
-      offs[pos]         = static_cast<int32_t>(run);
       if (g == ngroups - 1) {
-        if (char_totals) char_totals[string_cols[c]] = run;
-        if (run > INT32_MAX && status) atomicOr(status, 2ull);  // cudf strings offsets are int32
+        if (char_totals) char_totals[tab.scol[c]] = run;
+        if (run > INT32_MAX) atomicOr(&q.sync_words[1], 2u);  // cudf strings offsets are int32
       }
     }
   }
-  if (k == 0 && threadIdx.x == 0) offs[0] = 0;
+  // ---- the last CTA to finish publishes what phase 1 reports besides the offsets: exact null counts (sum of the
+  // per-CTA partials of from_rows_wide_kernel), zeros for the non-STRING entries of char_totals, and the status word
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&q.sync_words[0], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x * gridDim.y - 1) return;
+  __threadfence();
+  if (q.null_counts)
+    for (int col = threadIdx.x; col < q.ncols; col += kGsThreads) {
+      int64_t n = 0;
+#pragma unroll 8
+      for (int b = 0; b < q.parts; ++b) n += q.null_part[static_cast<size_t>(b) * q.ncols + col];  // coalesced across threads
+      q.null_counts[col] = n;
+    }
+  if (char_totals) {
+    for (int col = threadIdx.x; col < q.ncols; col += kGsThreads) {
+      bool is_str = false;  // nstr is small next to ncols * 148: a linear probe per column is cheap here
+      for (int s2 = 0; s2 < q.nstr; ++s2) is_str |= tab.scol[s2] == col;
+      if (!is_str) char_totals[col] = 0;
+    }
+    if (threadIdx.x == 0) {
+      unsigned st = *reinterpret_cast<volatile uint32_t*>(&q.sync_words[1]);
+      for (int b = 0; b < q.parts; ++b) st |= q.bad_part[b] ? 1u : 0u;
+      char_totals[q.ncols] = st;
+    }
+  }
 }
 
 // group-local inclusive sums -> absolute offsets, for consumers that want finished offsets after phase 1
-__global__ void __launch_bounds__(256) wide_finalize_offsets_kernel(int32_t* const* offsets, int64_t num_rows)
+__global__ void __launch_bounds__(256) wide_finalize_offsets_kernel(const __grid_constant__ WideScanTab tab, const uint32_t* base,
+                                                                     int64_t ngroups, int64_t num_rows)
 {
-  int32_t* offs   = offsets[blockIdx.y];
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x + 1;  // position 1..n
-  if (i >= num_rows || (i & 31) == 0) return;  // group boundaries and offs[n] are absolute already
-  offs[i] += offs[(i - 1) & ~int64_t{31}];
+  int32_t* offs   = tab.offs[blockIdx.y];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // position 0..n
+  if (i > num_rows) return;
+  if (i == 0) { offs[0] = 0; return; }
+  offs[i] += static_cast<int32_t>(base[static_cast<int64_t>(blockIdx.y) * ngroups + ((i - 1) >> 5)]);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -618,8 +704,8 @@ bool plan_wide(srj_plan* plan)
   const int spr      = plan->size_per_row;
   const int min_spr  = SRJ_KNOB("SRJ_W_MINROW", 512);
   const int min_nstr = SRJ_KNOB("SRJ_W_MINSTR", 8);
-  if (nstr < min_nstr || spr < min_spr || nc > 2048) return false;
-  const int slab_cap = SRJ_KNOB("SRJ_W_SLABCAP", 1100);
+  if (nstr < min_nstr || spr < min_spr || nc > kWMaxCols) return false;
+  const int slab_cap = SRJ_KNOB("SRJ_W_SLABCAP", 3200);
   int nslabs         = (spr + slab_cap - 1) / slab_cap;
   nslabs             = std::max(1, std::min(nslabs, 16));
   // first column of each slab: the first one starting at or after i * spr / nslabs
@@ -668,7 +754,8 @@ bool plan_wide(srj_plan* plan)
   int pitch = (maxlen + 16 + 15) & ~15;
   if (((pitch >> 4) & 1) == 0) pitch += 16;  // odd multiple of 16 bytes: consecutive rows start 4 banks apart
   const size_t tables = wp.entries.size() * sizeof(WDesc) + kWMaxStages * sizeof(WHdr) + 2 * kWMaxStages * 8 +
-                        static_cast<size_t>(nc) * 12 + nslabs * sizeof(WideSlab) + static_cast<size_t>(nstr) * 4 + 256;
+                        static_cast<size_t>(nc) * 12 + nslabs * sizeof(WideSlab) + static_cast<size_t>(nstr) * 4 +
+                        static_cast<size_t>(nslabs) * 6 * 16 * 2 + 256;
   const size_t budget = 232448;
   if (tables > 64 * 1024) return false;
   int NS = SRJ_KNOB("SRJ_W_STAGES", 3);
@@ -698,9 +785,19 @@ size_t wide_plan_blob_bytes(const srj_plan* plan)
   return plan->wide.enabled ? plan->wide.entries.size() * sizeof(WideEntry) + plan->wide.slabs.size() * sizeof(WideSlab) + 16 : 0;
 }
 
-int64_t wide_agg_bytes(const srj_plan* plan, int64_t num_rows)
+// Workspace of a convert_from_rows call pair (srj_from_rows_workspace_bytes): group totals and group bases of the
+// STRING columns (phase 2 reads the bases), per-CTA null counts and flags, two sync words.
+static int64_t wide_groups_bytes(const srj_plan* plan, int64_t num_rows)
 {
-  return static_cast<int64_t>(plan->num_string_columns) * ((num_rows + 31) / 32) * 4;
+  return (static_cast<int64_t>(plan->num_string_columns) * ((num_rows + 31) / 32) * 4 + 15) & ~int64_t{15};
+}
+int64_t wide_workspace_bytes(const srj_plan* plan, int64_t num_rows)
+{
+  return 2 * wide_groups_bytes(plan, num_rows) + static_cast<int64_t>(kWMaxGrid) * (plan->num_columns + 1) * 4 + 16;
+}
+const uint32_t* wide_workspace_bases(const srj_plan* plan, int64_t num_rows, const void* workspace)
+{
+  return reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(workspace) + wide_groups_bytes(plan, num_rows));
 }
 
 static size_t wide_smem_bytes(const srj_plan* plan)
@@ -711,15 +808,16 @@ static size_t wide_smem_bytes(const srj_plan* plan)
   b += static_cast<size_t>(plan->num_columns) * 8 + wp.slabs.size() * sizeof(WideSlab);
   b += static_cast<size_t>(wp.nstages) * wp.R * 4 + static_cast<size_t>(plan->num_columns) * 4;
   b += static_cast<size_t>(plan->num_string_columns) * 4;
+  b += wp.slabs.size() * 6 * 16 * 2 + 16;  // first-unit table (<= 16 consumer warps)
   return (b + 127) & ~size_t{127};
 }
 
 template <int NCW>
-static int launch_wide_variant(const WideParams& p, unsigned grid, size_t smem, cudaStream_t stream)
+static int launch_wide_variant(const WideParams& p, const WidePtrTab& tab, unsigned grid, size_t smem, cudaStream_t stream)
 {
   auto go = [&](auto kern) -> int {
     SRJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    kern<<<grid, (NCW + 1) * 32, smem, stream>>>(p);
+    kern<<<grid, (NCW + kWProducers) * 32, smem, stream>>>(p, tab);
     return SRJ_OK;
   };
   switch (p.G) {
@@ -730,21 +828,38 @@ static int launch_wide_variant(const WideParams& p, unsigned grid, size_t smem, 
   }
 }
 
+// cols: the caller's output columns (host array).  d_scratch: the call pair's workspace (wide_workspace_bytes()).
 int launch_from_rows_wide(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
-                          int64_t num_rows, void* const* d_col_ptr, uint32_t* const* d_masks,
-                          int32_t* const* d_str_offsets, int64_t* d_null_counts, int64_t* d_char_totals, int64_t* d_status,
-                          uint32_t* d_agg, bool finalize, cudaStream_t stream)
+                          int64_t num_rows, const srj_column* cols, int64_t* d_null_counts, int64_t* d_char_totals,
+                          void* d_scratch, bool finalize, cudaStream_t stream)
 {
   if (num_rows == 0) return SRJ_OK;
   const WidePlan& wp = plan->wide;
+  const int nc = plan->num_columns, nstr = plan->num_string_columns;
+  int dev = 0, nsm = 0;
+  SRJ_CUDA_TRY(cudaGetDevice(&dev));
+  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  if (const int g = SRJ_KNOB("SRJ_W_GRID", 0)) nsm = std::min(nsm, g);
+  const int64_t ntiles = (num_rows + wp.R - 1) / wp.R;
+  const unsigned grid  = static_cast<unsigned>(std::min<int64_t>(std::min(nsm, kWMaxGrid), ntiles));
+  WidePtrTab tab;
+  WideScanTab stab;
+  for (int c = 0; c < nc; ++c) {
+    tab.col[c]  = plan->type_ids[c] == SRJ_STRING ? static_cast<void*>(cols[c].offsets) : cols[c].data;
+    tab.mask[c] = cols[c].null_mask;
+  }
+  for (int s = 0; s < nstr; ++s) {
+    stab.offs[s] = cols[plan->string_columns[s]].offsets;
+    stab.scol[s] = plan->string_columns[s];
+  }
   WideParams p{};
   p.rows            = rows;
   p.row_offsets     = row_offsets;
   p.rows_bytes      = rows_bytes;
   p.num_rows        = num_rows;
   p.ngroups         = (num_rows + 31) / 32;
-  p.ncols           = plan->num_columns;
-  p.nstr            = plan->num_string_columns;
+  p.ncols           = nc;
+  p.nstr            = nstr;
   p.size_per_row    = plan->size_per_row;
   p.validity_offset = plan->validity_offset;
   p.R               = wp.R;
@@ -756,31 +871,40 @@ int launch_from_rows_wide(const srj_plan* plan, const uint8_t* rows, const int32
   p.entries         = wp.d_entries;
   p.slabs           = wp.d_slabs;
   p.string_start    = plan->d_string_start;
-  p.col_ptr         = d_col_ptr;
-  p.masks           = d_masks;
-  p.null_counts     = reinterpret_cast<unsigned long long*>(d_null_counts);
-  p.status          = reinterpret_cast<unsigned long long*>(d_status);
-  p.agg             = d_agg;
-  int dev = 0, nsm = 0;
-  SRJ_CUDA_TRY(cudaGetDevice(&dev));
-  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t ntiles = (num_rows + wp.R - 1) / wp.R;
-  const unsigned grid  = static_cast<unsigned>(std::min<int64_t>(nsm, ntiles));
-  const size_t smem    = wide_smem_bytes(plan);
+  p.want_nulls      = d_null_counts != nullptr;
+  uint8_t* sc       = static_cast<uint8_t*>(d_scratch);
+  const int64_t agg_bytes = wide_groups_bytes(plan, num_rows);
+  p.agg             = reinterpret_cast<uint32_t*>(sc);
+  uint32_t* d_base  = reinterpret_cast<uint32_t*>(sc + agg_bytes);
+  p.null_part       = reinterpret_cast<int32_t*>(sc + 2 * agg_bytes);
+  p.bad_part        = p.null_part + static_cast<size_t>(kWMaxGrid) * nc;
+  p.sync_words      = reinterpret_cast<uint32_t*>(p.bad_part + kWMaxGrid);
+  const size_t smem = wide_smem_bytes(plan);
   int rc;
-  switch (SRJ_KNOB("SRJ_W_WARPS", 15)) {
-    case 11: rc = launch_wide_variant<11>(p, grid, smem, stream); break;
-    case 7: rc = launch_wide_variant<7>(p, grid, smem, stream); break;
-    default: rc = launch_wide_variant<15>(p, grid, smem, stream); break;
+  switch (SRJ_KNOB("SRJ_W_WARPS", 12)) {
+    case 8: rc = launch_wide_variant<8>(p, tab, grid, smem, stream); break;
+    case 16: rc = launch_wide_variant<16>(p, tab, grid, smem, stream); break;
+    default: rc = launch_wide_variant<12>(p, tab, grid, smem, stream); break;
   }
   if (rc != SRJ_OK) return rc;
+  WideScanParams q{};
+  q.agg         = p.agg;
+  q.base        = d_base;
+  q.ngroups     = p.ngroups;
+  q.num_rows    = num_rows;
+  q.char_totals = d_char_totals;
+  q.null_counts = d_null_counts;
+  q.null_part   = p.null_part;
+  q.bad_part    = p.bad_part;
+  q.sync_words  = p.sync_words;
+  q.parts       = static_cast<int32_t>(grid);
+  q.ncols       = nc;
+  q.nstr        = nstr;
   const int64_t nchunks = (p.ngroups + kGsChunk - 1) / kGsChunk;
-  wide_group_scan_kernel<<<dim3(static_cast<unsigned>(nchunks), p.nstr), kGsThreads, 0, stream>>>(
-    d_agg, p.ngroups, num_rows, d_str_offsets, plan->d_string_cols, d_char_totals,
-    reinterpret_cast<unsigned long long*>(d_status));
+  wide_group_scan_kernel<<<dim3(static_cast<unsigned>(nchunks), nstr), kGsThreads, 0, stream>>>(q, stab);
   if (finalize) {
-    const unsigned gx = static_cast<unsigned>((num_rows + 255) / 256);
-    wide_finalize_offsets_kernel<<<dim3(gx, p.nstr), 256, 0, stream>>>(d_str_offsets, num_rows);
+    const unsigned gx = static_cast<unsigned>((num_rows + 1 + 255) / 256);
+    wide_finalize_offsets_kernel<<<dim3(gx, nstr), 256, 0, stream>>>(stab, d_base, p.ngroups, num_rows);
   }
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;

@@ -16,26 +16,31 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
 // from_rows_wide.cu: wide variable-width tables (per-row TMA slabs; offsets leave as group-local inclusive sums +
 // absolute group bases unless `finalize`)
 bool plan_wide(srj_plan* plan);
-int64_t wide_agg_bytes(const srj_plan* plan, int64_t num_rows);
+int64_t wide_workspace_bytes(const srj_plan* plan, int64_t num_rows);
+const uint32_t* wide_workspace_bases(const srj_plan* plan, int64_t num_rows, const void* workspace);  // [nstr][ngroups]
 int launch_from_rows_wide(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
-                          int64_t num_rows, void* const* d_col_ptr, uint32_t* const* d_masks,
-                          int32_t* const* d_str_offsets, int64_t* d_null_counts, int64_t* d_char_totals, int64_t* d_status,
-                          uint32_t* d_agg, bool finalize, cudaStream_t stream);
+                          int64_t num_rows, const srj_column* cols /* host array of the output columns */,
+                          int64_t* d_null_counts, int64_t* d_char_totals, void* d_scratch /* wide_workspace_bytes() */,
+                          bool finalize, cudaStream_t stream);
 
 // strings.cu
 // In-place inclusive scan of the int32 lengths stored at offsets[c][1..n] for every STRING column
 // (offsets[c][0] = 0), per-column totals to d_char_totals[schema col] (int64), a total beyond INT32_MAX sets bit 1 of *d_status.
 int launch_string_offsets_scan(int32_t* const* d_offsets /* device array [nstr] */, const int32_t* d_string_cols,
                                int nstr, int64_t num_rows, int64_t* d_char_totals, int64_t* d_status,
-                               void* d_partials /* int64 [nstr * nchunks] */, cudaStream_t stream);
+                               void* d_partials /* int64 [nstr * nchunks] */,
+                               bool mark_finished /* set bit 2 of *d_status: the offsets are complete */, cudaStream_t stream);
 int64_t string_scan_partials_bytes(int nstr, int64_t num_rows);
-// copy_strings_from_rows replacement
+// copy_strings_from_rows replacement.  cols = the caller's columns (host array); d_tab = device table
+// [offsets nstr][chars nstr], needed (and uploaded by the caller) only when !strings_fast_path().
 int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
-                             int64_t rows_bytes, int64_t num_rows, int32_t* const* d_offsets,
-                             uint8_t* const* d_chars, const int64_t* d_status,
-                             bool semi /* offsets are group-local sums + absolute group bases (wide tables) */,
+                             int64_t rows_bytes, int64_t num_rows, const srj_column* cols, void* const* d_tab,
+                             const int64_t* d_status,
+                             const uint32_t* d_bases /* non-NULL: offsets hold group-local inclusive sums, the chars before
+                                                        each 32-row group are d_bases[nstr][ngroups] (wide tables) */,
                              cudaStream_t stream);
 bool strings_wide_eligible(const srj_plan* plan);
+bool strings_fast_path(const srj_plan* plan, const int64_t* d_status);
 
 // to_rows.cu
 int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(int32_t* co
 // exclusive scan of each column's chunk sums, in place; writes the column total
 __global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(int64_t* partials, int nchunks,
                                                                     const int32_t* string_cols, int64_t* char_totals,
-                                                                    unsigned long long* status)
+                                                                    unsigned long long* status, int mark_finished)
 {
   __shared__ int64_t s_warp[kScanThreads / 32];
   __shared__ int64_t s_carry;
@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(int64_t* part
     const int64_t total = s_carry;
     if (char_totals) char_totals[string_cols[c]] = total;
     if (total > INT32_MAX && status) atomicOr(status, 2ull);  // cudf strings offsets are int32: bit 1 of the status word
+    // bit 2: the offsets are finished (a wide plan whose phase 1 ran this whole-row path, e.g. with a fused hash)
+    if (mark_finished && status && c == 0) atomicOr(status, 4ull);
   }
 }
 
@@ -141,7 +143,8 @@ int64_t string_scan_partials_bytes(int nstr, int64_t num_rows)
 }
 
 int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_string_cols, int nstr, int64_t num_rows,
-                               int64_t* d_char_totals, int64_t* d_status, void* d_partials, cudaStream_t stream)
+                               int64_t* d_char_totals, int64_t* d_status, void* d_partials, bool mark_finished,
+                               cudaStream_t stream)
 {
   if (nstr == 0) return SRJ_OK;
   const int64_t n1  = num_rows + 1;
@@ -150,7 +153,7 @@ int launch_string_offsets_scan(int32_t* const* d_offsets, const int32_t* d_strin
   dim3 grid(nchunks, nstr);
   scan_partials_kernel<<<grid, kScanThreads, 0, stream>>>(d_offsets, n1, nchunks, partials);
   scan_chunks_kernel<<<nstr, kScanThreads, 0, stream>>>(partials, nchunks, d_string_cols, d_char_totals,
-                                                        reinterpret_cast<unsigned long long*>(d_status));
+                                                        reinterpret_cast<unsigned long long*>(d_status), mark_finished ? 1 : 0);
   scan_apply_kernel<<<grid, kScanThreads, 0, stream>>>(d_offsets, n1, nchunks, partials);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
@@ -174,28 +177,33 @@ __device__ __forceinline__ void flush_staging_line(uint32_t stg_s, uint8_t* D, i
   const int aT      = a + T;
   const int c_first = (a + 15) >> 4;  // first whole chunk
   const int c_end   = aT >> 4;        // one past the last whole chunk
-  for (int c = c_first + lane; c < c_end; c += 32) {
-    uint32_t v0, v1, v2, v3;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+  {
+    const int c = c_first + lane;     // T <= 1024: at most three rounds, nearly always one
+    if (c < c_end) {
+      uint32_t v0, v1, v2, v3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+    }
   }
-  // head chunk = chunk 0 when a > 0; tail chunk = chunk c_end when aT is not a multiple of 16.  When both are the
-  // same chunk (c_end == 0) the head lanes cover all of [a, aT).
-  const int hl = lane & 15;
-  int bpos;
-  bool ok;
-  if (lane < 16) {
-    bpos = hl;                                   // head chunk bytes [a, min(16, aT))
-    ok   = hl >= a && hl < tmin(16, aT) && a > 0;
-    if (a == 0 && c_end == 0) ok = hl < aT;      // a single partial chunk starting at an aligned byte
-  } else {
-    bpos = 16 * c_end + hl;                      // tail chunk bytes [16 * c_end, aT)
-    ok   = c_end > 0 && bpos < aT;
+  if (c_end - c_first > 32) {  // warp-uniform
+    for (int c = c_first + 32 + lane; c < c_end; c += 32) {
+      uint32_t v0, v1, v2, v3;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(stg_s + 16 * c));
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(Dal + 16 * c), "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+    }
   }
-  if (ok) {
+  // partial chunks, one byte per lane: lanes 0-15 the head chunk [a, min(16, aT)) when a > 0; lanes 16-31 the tail
+  // chunk [16 c_end, aT) unless it is the head chunk
+  const int hl    = lane & 15;
+  const bool tail = lane >= 16;
+  const int pos   = (tail ? 16 * c_end : 0) + hl;
+  const int lo    = tail ? 0 : a;
+  const int hi    = tail ? aT : tmin(16, aT);
+  const bool en   = tail ? (a == 0 || c_end > 0) : (a > 0);
+  if (en && pos >= lo && pos < hi) {
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + bpos));
-    asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + bpos), "r"(v));
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stg_s + pos));
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(Dal + pos), "r"(v));
   }
 }
 
@@ -250,21 +258,20 @@ __device__ __forceinline__ void copy_global_to_staging(uint64_t S, uint32_t ds, 
 constexpr int kStrWarps = 8;
 constexpr int kStrLine  = 16 + 1024 + 32;  // per-warp staging line
 
-__global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
-  const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets, int64_t row_stride, int64_t num_rows,
-  int nstr, const int32_t* __restrict__ string_start, int32_t* const* __restrict__ offsets,
-  uint8_t* const* __restrict__ chars, int64_t ntiles, const int64_t* __restrict__ status, int semi)
+// The gather itself: warp `wlin` of `wtot` takes the tasks wlin, wlin + wtot, ...; stg_s = the warp's staging line.
+__device__ __forceinline__ void generic_gather(const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets,
+                                               int64_t row_stride, int64_t num_rows, int nstr,
+                                               const int32_t* __restrict__ string_start, int32_t* const* offsets,
+                                               uint8_t* const* chars, int64_t ntiles, const uint32_t* bases, int64_t wlin,
+                                               int64_t wtot, uint32_t stg_s)
 {
-  // runs only when phase 1 flagged non-canonical rows (or no status word was passed)
-  if (status && !(*status & 1)) return;
-  __shared__ __align__(16) uint8_t s_line[kStrWarps * kStrLine];
-  const int lane       = lane_id();
-  const uint32_t stg_s = smem_u32(s_line + warp_id() * kStrLine);
+  // bases != NULL (wide tables between the two phases): offsets[s][r + 1] holds the inclusive sum inside row r's 32-row
+  // group and bases[s][group] the chars of the column before the group; the finished offsets are written here.
+  const int lane = lane_id();
   // one task = (32-row tile, STRING column); tasks are dealt to the warps of the whole grid, so every warp is busy
   // whatever the number of STRING columns (tables with 1-3 strings are the common case)
   const int64_t ntasks = ntiles * nstr;
-  const int64_t wstep  = static_cast<int64_t>(gridDim.x) * kStrWarps;
-  for (int64_t task = static_cast<int64_t>(blockIdx.x) * kStrWarps + warp_id(); task < ntasks; task += wstep) {
+  for (int64_t task = wlin; task < ntasks; task += wtot) {
     const int64_t tile = task / nstr;
     const int s        = static_cast<int>(task - tile * nstr);
     const int64_t r    = tile * 32 + lane;
@@ -284,17 +291,18 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
         }
         v = offsets[s][r + 1];
       }
-      // offsets entries: absolute, or (semi: wide tables between the two phases) inclusive sums inside the 32-row
-      // group with an absolute entry closing each group -- finished here
       const int last       = static_cast<int>(tmin<int64_t>(31, num_rows - 1 - tile * 32));
-      const int32_t dbase  = offsets[s][tile * 32];
+      const int32_t dbase  = bases ? static_cast<int32_t>(bases[static_cast<int64_t>(s) * ntiles + tile]) : offsets[s][tile * 32];
       int32_t x            = v;
-      if (!semi || lane == last) x -= dbase;
+      if (!bases) x -= dbase;
       x                    = active ? x : 0;
       const int32_t up     = __shfl_up_sync(0xffffffffu, x, 1);
       const uint32_t pe    = static_cast<uint32_t>(lane ? up : 0);  // exclusive prefix inside the tile
       const uint32_t total = static_cast<uint32_t>(__shfl_sync(0xffffffffu, x, last));
-      if (semi && lane < last) offsets[s][r + 1] = dbase + x;
+      if (bases) {
+        if (active) offsets[s][r + 1] = dbase + x;
+        if (r == 0) offsets[s][0] = 0;
+      }
       const int64_t srcoff = rsta + so;
       uint8_t* dst         = chars[s] + dbase;
       const int maxL       = __reduce_max_sync(0xffffffffu, active ? static_cast<int>(tmin<uint32_t>(len, 1u << 20)) : 0);
@@ -328,6 +336,19 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
 }
 
 
+__global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
+  const uint8_t* __restrict__ rows, const int32_t* __restrict__ row_offsets, int64_t row_stride, int64_t num_rows,
+  int nstr, const int32_t* __restrict__ string_start, int32_t* const* __restrict__ offsets,
+  uint8_t* const* __restrict__ chars, int64_t ntiles, const int64_t* __restrict__ status, const uint32_t* bases)
+{
+  // status bit 2: phase 1 already left finished offsets (ignore the group bases)
+  if (status && (*status & 4)) bases = nullptr;
+  __shared__ __align__(16) uint8_t s_line[kStrWarps * kStrLine];
+  generic_gather(rows, row_offsets, row_stride, num_rows, nstr, string_start, offsets, chars, ntiles, bases,
+                 static_cast<int64_t>(blockIdx.x) * kStrWarps + warp_id(), static_cast<int64_t>(gridDim.x) * kStrWarps,
+                 smem_u32(s_line + warp_id() * kStrLine));
+}
+
 // --------------------------------------------------------------------------------------------------
 // chars gather, FAST path (canonical rows: a row's chars follow its fixed section in column order, which is
 // what convert_to_rows writes and what phase 1 verified).
@@ -345,8 +366,9 @@ __global__ void __launch_bounds__(kStrWarps * 32) strings_from_rows_kernel(
 //                   aligned 32-bit words from the row image, funnel-shifted to the destination's byte
 //                   alignment, into a per-warp staging line laid out like the destination, which leaves with
 //                   aligned 16-byte st.global (the chars of consecutive rows of a column are contiguous).
-//   offsets       : with `semi` (wide tables, from_rows_wide.cu) phase 1 left group-local inclusive sums and an
-//                   absolute base per 32-row group; the absolute offsets are written here, on the way.
+//   offsets       : for wide tables (from_rows_wide.cu) phase 1 left group-local inclusive sums in the offsets arrays
+//                   and the chars before each 32-row group in the workspace; the absolute offsets are written here,
+//                   on the way (one coalesced store per column and tile).
 // --------------------------------------------------------------------------------------------------
 constexpr int kSwNG     = 3;   // tiles in flight per CTA (groups of consumer warps)
 constexpr int kSwMaxWpt = 8;   // consumer warps per tile
@@ -368,10 +390,13 @@ struct SwParams {
   const int32_t* row_offsets;
   int64_t rows_bytes;
   int64_t num_rows;
-  int32_t nstr, size_per_row, wpt, cpw, stage_bytes, semi;
-  int32_t* const* offsets;
-  uint8_t* const* chars;
+  int32_t nstr, size_per_row, wpt, cpw, stage_bytes, fixed_row_size;
+  const uint32_t* bases;  // non-NULL: offsets hold group-local inclusive sums, bases[nstr][ntiles] the chars before each group
+  const int32_t* string_start;  // [nstr] row byte offset of each pair (generic gather only)
   const int64_t* status;
+  // per-call pointer tables, as kernel parameters (no staging copy): the fast gather takes <= 64 STRING columns
+  int32_t* offsets[kSwMaxWpt * kSwMaxCpw];
+  uint8_t* chars[kSwMaxWpt * kSwMaxCpw];
 };
 
 __device__ __forceinline__ int32_t ldg_s32(const int32_t* p)
@@ -381,49 +406,55 @@ __device__ __forceinline__ int32_t ldg_s32(const int32_t* p)
   return v;
 }
 
-// lane's string = L bytes at SHARED address srcs -> staging byte ds.  Aligned 32-bit source words, funnel shift to
-// the staging alignment, st.shared.u32 for whole words; the <= 3 edge bytes at each end come straight from the
-// source.  maxL (<= 32) is the warp's longest string; the word loads are unconditional (the stage has slack).
-__device__ __forceinline__ void copy_shared_to_staging(uint32_t srcs, uint32_t ds, int L, int maxL)
+// lane's string = L bytes (<= 32) at SHARED address srcs -> staging byte ds.  Nine aligned 32-bit source words are read
+// unconditionally (the stage has slack on both sides), funnel-shifted to the staging alignment and stored as whole
+// words where the string covers a whole staging word; the <= 3 bytes of a partial first / last staging word are taken
+// from the shifted words (the last one is rebuilt from two more loads: its index is not a compile-time constant).
+__device__ __forceinline__ void copy_shared_to_staging(uint32_t srcs, uint32_t ds, int L)
 {
-  const int dsh      = static_cast<int>(ds & 3u);
-  const int ssh      = static_cast<int>(srcs & 3u);
-  const int dlt      = ssh - dsh;
-  const int pre      = ssh + (dlt < 0 ? 4 : 0);  // string byte 0 is byte `pre` of the source word stream
-  const uint32_t sp  = srcs - pre;
-  const int sh       = (dlt & 3) * 8;
-  const int end      = dsh + L;      // one past the last staging byte, relative to word w0
-  const int kfull1   = end >> 2;     // full words: [dsh ? 1 : 0, kfull1)
+  const uint32_t dsh = ds & 3u;
+  const uint32_t ssh = srcs & 3u;
+  const bool back    = ssh < dsh;                            // the word stream starts one word before the string
+  const uint32_t sp  = (srcs - ssh) - (back ? 4u : 0u);      // aligned; staging word k <- stream words k, k + 1
+  const uint32_t sh  = ((ssh - dsh) & 3u) * 8u;
   const uint32_t w0s = ds - dsh;
-  const int Kmax     = (maxL + 6) >> 2;  // warp-uniform bound on kfull1 (<= 9)
-  const int nh       = dsh ? tmin(L, 4 - dsh) : 0;
-  const int nt       = (kfull1 > 0 || !dsh) ? (end & 3) : 0;
-  uint32_t hb[3], tb[3];
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    hb[t] = tb[t] = 0;
-    if (t < nh) hb[t] = lds_u8(srcs + t);
-    if (t < nt) tb[t] = lds_u8(srcs + (L - nt) + t);
-  }
-  uint32_t w[10];
-#pragma unroll
-  for (int k = 0; k < 10; ++k) {
-    w[k] = 0;
-    if (k <= Kmax) w[k] = lds_u32(sp + 4 * k);
-  }
-#pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    if (t < nh) sts_u8(ds + t, hb[t]);
-    if (t < nt) sts_u8(ds + (L - nt) + t, tb[t]);
-  }
-  const int k0 = dsh ? 1 : 0;
+  const int end      = static_cast<int>(dsh) + L;            // one past the last staging byte, relative to word 0
+  const int kfull1   = end >> 2;                             // whole words: [dsh ? 1 : 0, kfull1)
+  // The kernel is bound by shared-memory wavefronts (lanes hit random banks), not by issue slots: every load is
+  // predicated on the lane needing that word, which thins the active lanes of the later words and with them the
+  // bank conflicts (average string 13 bytes, longest of a warp ~32).
+  const int need = L > 0 ? (end + 3) >> 2 : -1;  // staging words 0 .. need-1 are touched; word k needs stream words k, k+1
+  uint32_t w[9];  // end <= 35: whole words are k <= 7, built from stream words 0..8
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
-    if (k < Kmax) {
-      const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
-      if (k >= k0 && k < kfull1) sts_u32(w0s + 4 * k, y);
-    }
+    w[k] = 0;
+    if (k <= need) w[k] = lds_u32(sp + 4 * k);
   }
+  const int nt      = (kfull1 > 0 || dsh == 0) ? (end & 3) : 0;
+  const uint32_t ta = sp + 4u * static_cast<uint32_t>(kfull1);
+  uint32_t t0 = 0, t1 = 0;
+  if (nt > 0) {
+    t0 = lds_u32(ta);
+    t1 = lds_u32(ta + 4);
+  }
+  const uint32_t y0 = __funnelshift_r(w[0], w[1], sh);
+  if (dsh == 0 && kfull1 > 0) sts_u32(w0s, y0);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+    if (k < kfull1) sts_u32(w0s + 4 * k, y);
+  }
+  // partial first word: bytes [dsh, min(4, end)) when dsh > 0
+  const int hend = dsh ? tmin(end, 4) : 0;
+#pragma unroll
+  for (int b = 1; b < 4; ++b)
+    if (b >= static_cast<int>(dsh) && b < hend) sts_u8(w0s + b, y0 >> (8 * b));
+  // partial last word: bytes [0, end & 3) of word kfull1, unless that is the first word again
+  const uint32_t tw = __funnelshift_r(t0, t1, sh);
+  const uint32_t tb = w0s + 4u * static_cast<uint32_t>(kfull1);
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+    if (b < nt) sts_u8(tb + b, tw >> (8 * b));
 }
 
 // lane = destination byte, source row by a shuffle search (long strings, tiles that were not staged)
@@ -446,7 +477,6 @@ __device__ __noinline__ void gather_bytes_slow(uint8_t* D, uint32_t T, uint32_t 
 
 __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __grid_constant__ SwParams p)
 {
-  if (p.status && (*p.status & 1)) return;  // non-canonical rows: the generic kernel does the work
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int NS     = kSwStages;
   const int stage_span = kSwFront + p.stage_bytes + kSwBack;  // multiple of 16
@@ -476,6 +506,17 @@ __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __
     fence_mbar_init();
   }
   __syncthreads();
+  if (p.status && (*p.status & 1)) {
+    // phase 1 saw rows that do not use the canonical layout: follow the stored pair offsets (RC:1143) with the generic
+    // gather, every consumer warp of the grid taking (tile, column) tasks with its own staging line
+    if (warp_id() == 0) return;
+    const int ncons = (blockDim.x >> 5) - 1;
+    generic_gather(p.rows, p.row_offsets, p.fixed_row_size, p.num_rows, p.nstr, p.string_start, s_offs, s_chars,
+                   (p.num_rows + 31) >> 5, (*p.status & 4) ? nullptr : p.bases,
+                   static_cast<int64_t>(blockIdx.x) * ncons + (warp_id() - 1),
+                   static_cast<int64_t>(gridDim.x) * ncons, smem_u32(stg0 + static_cast<size_t>(warp_id() - 1) * kSwLine));
+    return;
+  }
 
   const uintptr_t b_lo = reinterpret_cast<uintptr_t>(p.rows);
   const uintptr_t b_hi = b_lo + static_cast<uintptr_t>(p.rows_bytes);
@@ -562,7 +603,7 @@ __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __
     const int c0         = wi * p.cpw;
     const int ncol       = tmax(0, tmin(p.nstr, c0 + p.cpw) - c0);
     const uint32_t stg_s = smem_u32(stg0 + static_cast<size_t>(cw) * kSwLine);
-    const bool semi      = p.semi != 0;
+    const bool semi      = p.bases != nullptr && !(p.status && (*p.status & 4));  // bit 2: phase 1 left finished offsets
     for (int it = gi, k = 0;; it += kSwNG, ++k) {
       const int s        = it % NS;
       const uint32_t par = (it / NS) & 1;
@@ -575,8 +616,9 @@ __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __
       const bool direct   = h.direct != 0;
       const uint32_t pay_s = smem_u32(payload0 + static_cast<size_t>(s) * stage_span + kSwFront);
       // ---- this warp's columns: offsets entries of the tile -> lengths ------------------------------------
-      int32_t base_l = 0;
-      if (lane < ncol) base_l = ldg_s32(s_offs[c0 + lane] + h.r0);
+      int32_t base_l = 0;  // chars of column c0 + lane before this tile
+      if (lane < ncol)
+        base_l = semi ? static_cast<int32_t>(p.bases[static_cast<int64_t>(c0 + lane) * ntiles + (h.r0 >> 5)]) : ldg_s32(s_offs[c0 + lane] + h.r0);
       int32_t v[kSwMaxCpw];
 #pragma unroll
       for (int j = 0; j < kSwMaxCpw; ++j) {
@@ -589,7 +631,7 @@ __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __
       for (int j = 0; j < kSwMaxCpw; ++j) {
         const int32_t bj = __shfl_sync(0xffffffffu, base_l, j);
         int32_t x        = v[j];
-        if (!semi || lane == last) x -= bj;  // entries of the group's last row (and every finished entry) are absolute
+        if (!semi) x -= bj;  // finished offsets are absolute; otherwise they are sums inside the group already
         x                = active ? x : 0;
         const int32_t up = __shfl_up_sync(0xffffffffu, x, 1);
         inc[j]           = x;
@@ -619,13 +661,16 @@ __global__ void __launch_bounds__(kSwMaxThreads, 1) strings_wide_kernel(const __
           const int32_t bj = __shfl_sync(0xffffffffu, base_l, j);
           const int32_t rb = run;
           run += L;
-          if (semi && lane < last) asm volatile("st.global.s32 [%0], %1;" ::"l"(s_offs[c0 + j] + h.r0 + 1 + lane), "r"(bj + inc[j]));
+          if (semi) {  // finish the offsets: one coalesced 128-byte store per column
+            if (active) asm volatile("st.global.s32 [%0], %1;" ::"l"(s_offs[c0 + j] + h.r0 + 1 + lane), "r"(bj + inc[j]));
+            if (h.r0 == 0 && lane == 0) asm volatile("st.global.s32 [%0], %1;" ::"l"(s_offs[c0 + j]), "r"(0));
+          }
           if (T > 0) {
             uint8_t* D     = s_chars[c0 + j] + bj;
             const int maxL = __reduce_max_sync(0xffffffffu, L);
             if (!direct && maxL <= 32 && T <= 1024) {
               const int a = static_cast<int>(reinterpret_cast<uintptr_t>(D) & 15);
-              copy_shared_to_staging(var_s + static_cast<uint32_t>(rb), stg_s + static_cast<uint32_t>(a + pe), L, maxL);
+              copy_shared_to_staging(var_s + static_cast<uint32_t>(rb), stg_s + static_cast<uint32_t>(a + pe), L);
               __syncwarp();
               flush_staging_line(stg_s, D, a, T, lane);
               __syncwarp();
@@ -662,9 +707,14 @@ bool strings_wide_eligible(const srj_plan* plan)
   return nstr >= SRJ_KNOB("SRJ_SW_MINCOLS", 8) && nstr <= kSwMaxWpt * kSwMaxCpw;
 }
 
+// the fast gather needs phase 1's status word (it tells canonical rows from the rest)
+bool strings_fast_path(const srj_plan* plan, const int64_t* d_status) { return d_status != nullptr && strings_wide_eligible(plan); }
+
+// cols: the caller's columns (host array).  The fast gather gets its pointer tables as kernel parameters; schemas it
+// does not serve upload them through the plan's ring (d_tab: [offsets nstr][chars nstr], already in flight).
 int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
-                             int64_t num_rows, int32_t* const* d_offsets, uint8_t* const* d_chars,
-                             const int64_t* d_status, bool semi, cudaStream_t stream)
+                             int64_t num_rows, const srj_column* cols, void* const* d_tab, const int64_t* d_status,
+                             const uint32_t* d_bases, cudaStream_t stream)
 {
   const int nstr = plan->num_string_columns;
   if (nstr == 0 || num_rows == 0) return SRJ_OK;
@@ -674,21 +724,24 @@ int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const in
   // The fast gather splits the STRING columns of a 32-row tile over the warps of a group: it needs a few columns to
   // fill them.  Tables with few STRING columns take the task-parallel generic kernel (which follows the stored
   // offsets, so it serves canonical and non-canonical rows alike).
-  const bool fast = d_status != nullptr && strings_wide_eligible(plan);
-  if (fast) {
+  if (strings_fast_path(plan, d_status)) {
     SwParams p{};
-    p.rows         = rows;
-    p.row_offsets  = row_offsets;
-    p.rows_bytes   = rows_bytes;
-    p.num_rows     = num_rows;
-    p.nstr         = nstr;
-    p.size_per_row = plan->size_per_row;
-    p.wpt          = std::min(kSwMaxWpt, (nstr + 3) / 4);          // >= 4 columns per warp when there are few
-    p.cpw          = (nstr + p.wpt - 1) / p.wpt;
-    p.semi         = semi ? 1 : 0;
-    p.offsets      = d_offsets;
-    p.chars        = d_chars;
-    p.status       = d_status;
+    p.rows           = rows;
+    p.row_offsets    = row_offsets;
+    p.rows_bytes     = rows_bytes;
+    p.num_rows       = num_rows;
+    p.nstr           = nstr;
+    p.size_per_row   = plan->size_per_row;
+    p.fixed_row_size = plan->fixed_row_size;
+    p.string_start   = plan->d_string_start;
+    p.wpt            = std::min(kSwMaxWpt, (nstr + 3) / 4);          // >= 4 columns per warp when there are few
+    p.cpw            = (nstr + p.wpt - 1) / p.wpt;
+    p.bases          = d_bases;
+    p.status         = d_status;
+    for (int s = 0; s < nstr; ++s) {
+      p.offsets[s] = cols[plan->string_columns[s]].offsets;
+      p.chars[s]   = static_cast<uint8_t*>(cols[plan->string_columns[s]].data);
+    }
     // stage = the variable sections of 32 average rows + 25 %, within what shared memory leaves
     const size_t fixed_smem = strings_wide_smem_bytes(nstr, 0, p.wpt);
     const int64_t cap       = (static_cast<int64_t>(232448 - fixed_smem) / kSwStages) & ~int64_t{15};
@@ -698,17 +751,21 @@ int launch_strings_from_rows(const srj_plan* plan, const uint8_t* rows, const in
     if (const int kb = SRJ_KNOB("SRJ_SW_STAGE_KB", 0)) stage = std::min<int64_t>(cap, static_cast<int64_t>(kb) * 1024);
     p.stage_bytes           = static_cast<int32_t>(stage);
     const int64_t ntiles    = (num_rows + 31) / 32;
-    const int64_t grid      = std::min<int64_t>(nsm, ntiles);
+    int nsm_b               = nsm;
+    if (const int g = SRJ_KNOB("SRJ_SW_GRID", 0)) nsm_b = std::min(nsm, g);
+    const int64_t grid      = std::min<int64_t>(nsm_b, ntiles);
     const size_t smem       = strings_wide_smem_bytes(nstr, p.stage_bytes, p.wpt);
     SRJ_CUDA_TRY(cudaFuncSetAttribute(strings_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     strings_wide_kernel<<<static_cast<unsigned>(grid), (1 + kSwNG * p.wpt) * 32, smem, stream>>>(p);
+    SRJ_CUDA_TRY(cudaGetLastError());
+    return SRJ_OK;
   }
-  // generic kernel: does the work only when the status word flags non-canonical rows (or is absent)
+  // generic kernel: follows the stored pair offsets
   const int64_t ntiles = (num_rows + 31) / 32;
   const int64_t grid   = std::min<int64_t>(ntiles, static_cast<int64_t>(nsm) * 8);
   strings_from_rows_kernel<<<static_cast<unsigned>(grid), kStrWarps * 32, 0, stream>>>(
-    rows, row_offsets, plan->fixed_row_size, num_rows, nstr, plan->d_string_start, d_offsets, d_chars, ntiles,
-    fast ? d_status : nullptr, semi ? 1 : 0);
+    rows, row_offsets, plan->fixed_row_size, num_rows, nstr, plan->d_string_start, reinterpret_cast<int32_t* const*>(d_tab),
+    reinterpret_cast<uint8_t* const*>(d_tab + nstr), ntiles, d_status, d_bases);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }

@@ -319,19 +319,22 @@ class RowConversion:
             totals = torch.zeros(nc + 1, dtype=torch.int64, device=dev)   # + status word for phase 2
             carr = _carray(outs)
             rows_ptr = child.data.data_ptr() if child.data is not None and child.data.numel() else None
+            ws_bytes = lib.srj_from_rows_workspace_bytes(plan.handle, n)
+            ws = _empty(ws_bytes, torch.uint8, dev) if ws_bytes else None          # rmm allocation in the JNI shim
+            ws_ptr = ws.data_ptr() if ws is not None else None
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rows_ptr, vec.offsets.data_ptr(), child.size, n,
-                                                    carr, nulls.data_ptr(), totals.data_ptr(), None, stream),
+                                                    carr, nulls.data_ptr(), totals.data_ptr(), None, ws_ptr, stream),
                     "convertFromRows")
             if plan.layout.num_string_columns:
                 h_tot = totals.cpu().numpy()                                           # the sync of RC:2389
                 for i, d in enumerate(dts):
                     if d.type_id == DType.STRING:
-                        if h_tot[i] > 2**31 - 1:
+                        if h_tot[i] > 2**31 - 1 or (int(h_tot[nc]) & 2):
                             raise CudfColumnSizeOverflowException(f"string column {i} exceeds the int32 chars limit")
                         outs[i].data = _empty(int(h_tot[i]), torch.uint8, dev)
                 carr = _carray(outs)
                 N.check(lib.srj_convert_from_rows_strings(plan.handle, rows_ptr, vec.offsets.data_ptr(), child.size, n,
-                                                          carr, totals.data_ptr(), stream), "convertFromRows")
+                                                          carr, totals.data_ptr(), ws_ptr, stream), "convertFromRows")
             h_nulls = nulls.cpu().numpy()
             for i, o in enumerate(outs):
                 o._null_count = int(h_nulls[i])
@@ -377,7 +380,7 @@ class RowConversion:
             fh.out = hout.data_ptr()
             nulls = torch.zeros(max(len(dts), 1), dtype=torch.int64, device=dev)
             N.check(N.lib().srj_convert_from_rows_fixed(plan.handle, vec.child.data.data_ptr(), None, vec.child.size,
-                                                        n, _carray(outs), nulls.data_ptr(), None, C.byref(fh),
+                                                        n, _carray(outs), nulls.data_ptr(), None, C.byref(fh), None,
                                                         _stream_ptr()), "convertFromRowsWithHash")
             return Table(outs), ColumnVector(DType.INT64 if kind == "xxhash64" else DType.INT32, n,
                                              hout.view(torch.uint8), None)

@@ -49,11 +49,12 @@ SYMBOLS = {
     "srj_convert_to_rows": (C.c_int, [C.c_void_p, C.POINTER(SrjColumn), C.c_int64, C.c_void_p,
                                       C.POINTER(SrjRowBatch), C.c_int32, C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_void_p), C.c_void_p]),
+    "srj_from_rows_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
     "srj_convert_from_rows_fixed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                               C.POINTER(SrjColumn), C.c_void_p, C.c_void_p,
-                                              C.POINTER(SrjFusedHash), C.c_void_p]),
+                                              C.POINTER(SrjFusedHash), C.c_void_p, C.c_void_p]),
     "srj_convert_from_rows_strings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                                C.POINTER(SrjColumn), C.c_void_p, C.c_void_p]),
+                                                C.POINTER(SrjColumn), C.c_void_p, C.c_void_p, C.c_void_p]),
     "srj_get_max_stack_depth": (C.c_int, []),
     "srj_xxhash64": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "srj_murmur_hash3_32": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_uint32, C.c_void_p,

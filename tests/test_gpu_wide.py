@@ -151,8 +151,9 @@ def test_wide_sliced_output_buffers():
     carr = (N.SrjColumn * len(outs))()
     for i, c in enumerate(outs):
         carr[i] = c._c()
+    ws = torch.empty(max(8, lib.srj_from_rows_workspace_bytes(plan.handle, nrows)), dtype=torch.uint8, device="cuda")
     N.check(lib.srj_convert_from_rows_fixed(plan.handle, d_rows.data_ptr(), d_offs.data_ptr(), d_rows.numel(), nrows, carr,
-                                            nulls.data_ptr(), totals.data_ptr(), None, st))
+                                            nulls.data_ptr(), totals.data_ptr(), None, ws.data_ptr(), st))
     h_tot = totals.cpu().numpy()
     assert h_tot[len(dts)] == 0                                   # canonical rows, no overflow
     for i, d in enumerate(dts):
@@ -161,7 +162,7 @@ def test_wide_sliced_output_buffers():
             outs[i].data = torch.empty(int(h_tot[i]) + 3, dtype=torch.uint8, device="cuda")[3:]     # odd chars pointer
             carr[i] = outs[i]._c()
     N.check(lib.srj_convert_from_rows_strings(plan.handle, d_rows.data_ptr(), d_offs.data_ptr(), d_rows.numel(), nrows, carr,
-                                              totals.data_ptr(), st))
+                                              totals.data_ptr(), ws.data_ptr(), st))
     torch.cuda.synchronize()
     assert np.array_equal(nulls.cpu().numpy(), onulls)
     for i, (g, o) in enumerate(zip(outs, ocols)):
