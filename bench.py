@@ -432,6 +432,25 @@ def synth_strings_gpu(torch, S, n, null_frac, g):
     return S.ColumnVector(S.DType(STRING), n, chars, mask, offs.to(torch.int32))
 
 
+def synth_c3_host(types, n, null_frac, seed):
+    """One C3 batch on the HOST (numpy): same distributions as the device generator (fixed-width = random bytes,
+    strings ~ clamp(round(N(16, 8)), 0, 32) printable ASCII, null strings have length 0)."""
+    from oracle import oracle as O
+    rng = np.random.Generator(np.random.Philox(seed))
+    cols = []
+    for t in types:
+        valid = rng.random(n) >= null_frac
+        mask = O.pack_mask(valid)
+        if t == STRING:
+            lens = np.clip(np.rint(rng.normal(16, 8, n)), 0, 32).astype(np.int64) * valid
+            offs = np.zeros(n + 1, np.int32)
+            np.cumsum(lens, out=offs[1:])
+            cols.append(O.HCol(t, rng.integers(32, 127, int(offs[-1]), dtype=np.uint8), mask, offs, 0, n))
+        else:
+            cols.append(O.HCol(t, rng.integers(0, 256, n * SIZE[t], dtype=np.uint8), mask, None, -11 if t == DEC128 else 0, n))
+    return cols
+
+
 def run_c3(args, wl, rank, world):
     import ctypes as C
 
@@ -445,10 +464,13 @@ def run_c3(args, wl, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     types = wl["types"]
+    nc = len(types)
     nb = int(wl["batch_rows"])
     total_rows = int(args.rows or wl["rows"])
-    nbatches = max(1, total_rows // nb)
-    pool = min(int(wl["pool"]), nbatches)
+    # STRONG scaling (BASELINE configs[4]): the job is total_rows rows whatever N; a "round" converts one batch of nb
+    # rows on every rank (the rank's contiguous row range of an N x nb-row global batch), then all-gathers the columns
+    rounds = max(1, total_rows // (nb * world))
+    pool = min(int(wl["pool"]), rounds)
     dts = [S.DType(t, -11 if t == DEC128 else 0) for t in types]
     plan = S.Plan.get(dts)
     lib = N.lib()
@@ -456,12 +478,13 @@ def run_c3(args, wl, rank, world):
     st = int(stream.cuda_stream)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     words = (nb + 31) // 32
+    do_gather = world > 1 and args.direction == "from_rows" and not args.no_gather
 
     # ---- resident pool of distinct batches: columns -> (our) to_rows -> rows ---------------------------
     batches = []
     for b in range(pool):
         cols = []
-        fixed = synth_columns_gpu(torch, S, [t for t in types if t != STRING], nb, wl["null_frac"], seed=77 + 13 * b + rank)
+        fixed = synth_columns_gpu(torch, S, [t for t in types if t != STRING], nb, wl["null_frac"], seed=77 + 13 * b + 1000 * rank)
         fi = iter(fixed)
         for t in types:
             cols.append(synth_strings_gpu(torch, S, nb, wl["null_frac"], g) if t == STRING else next(fi))
@@ -481,61 +504,48 @@ def run_c3(args, wl, rank, world):
             out += (4 * (nb + 1) + c.data.numel()) if c.dtype.type_id == STRING else c.data.numel()
         return rb + out
     alg = [alg_bytes(bt) for bt in batches]
-    alg_step = sum(alg[i % pool] for i in range(nbatches))
+    alg_step = sum(alg[i % pool] for i in range(rounds))
 
+    gather_info = None
     if args.direction == "from_rows":
-        # pre-sized outputs (one set per pool slot); chars sizes are known from generation, so the device-resident
-        # `value` runs fixed+strings back to back without the D2H size read (e2e below includes it)
+        # Outputs of a slot live in ONE packed slab: [fixed-width data | STRING offsets] per column, the masks, the
+        # phase-1 totals (nc + 1 int64) and the chars of the STRING columns back to back -- what the rank contributes to
+        # the all-gather is one contiguous buffer, so the collective is ONE ncclAllGather per round.
+        from srj_b200 import sharding
+        chars_need = [sum((c.data.numel() + 15) & ~15 for c in bt["cols"] if c.dtype.type_id == STRING) for bt in batches]
+        cap = torch.tensor([max(chars_need)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX)          # common chars capacity (equal counts for the all-gather)
+        lay = sharding.SlabLayout([0 if t == STRING else SIZE[t] for t in types], nb, int(cap[0]))
+        at_data, at_mask, at_tot, at_chars, slab_bytes = lay.at_data, lay.at_mask, lay.at_totals, lay.at_chars, lay.nbytes
         outs = []
         for bt in batches:
-            o = []
-            for c in bt["cols"]:
-                m = torch.empty(words, dtype=torch.int32, device="cuda")
+            slab = torch.empty(slab_bytes, dtype=torch.uint8, device="cuda")
+            o, co = [], at_chars
+            for i, c in enumerate(bt["cols"]):
+                m = slab[at_mask[i]: at_mask[i] + words * 4].view(torch.int32)
                 if c.dtype.type_id == STRING:
-                    o.append(S.ColumnVector(c.dtype, nb, torch.empty(c.data.numel(), dtype=torch.uint8, device="cuda"), m,
-                                            torch.empty(nb + 1, dtype=torch.int32, device="cuda")))
+                    offs = slab[at_data[i]: at_data[i] + (nb + 1) * 4].view(torch.int32)
+                    o.append(S.ColumnVector(c.dtype, nb, slab[co: co + c.data.numel()], m, offs))
+                    co += (c.data.numel() + 15) & ~15
                 else:
-                    o.append(S.ColumnVector(c.dtype, nb, torch.empty(c.data.numel(), dtype=torch.uint8, device="cuda"), m))
+                    o.append(S.ColumnVector(c.dtype, nb, slab[at_data[i]: at_data[i] + c.data.numel()], m))
             carr = (N.SrjColumn * len(o))()
             for i, c in enumerate(o):
                 carr[i] = c._c()
-            outs.append((o, carr))
-        nulls = torch.zeros(len(types), dtype=torch.int64, device="cuda")
-        totals = torch.zeros(len(types) + 1, dtype=torch.int64, device="cuda")
+            outs.append(dict(cols=o, carr=carr, slab=slab, totals=slab[at_tot: at_tot + (nc + 1) * 8].view(torch.int64)))
+        nulls = torch.zeros(nc, dtype=torch.int64, device="cuda")
         wsb = lib.srj_from_rows_workspace_bytes(plan.handle, nb)
         wss = [torch.empty(max(wsb, 8), dtype=torch.uint8, device="cuda") for _ in range(pool)]   # one workspace per call pair
-        overlap = os.environ.get("SRJ_BENCH_OVERLAP") == "1"
-        if overlap:
-            stream2 = torch.cuda.Stream()
-            st2 = int(stream2.cuda_stream)
-            tot_slot = [torch.zeros(len(types) + 1, dtype=torch.int64, device="cuda") for _ in range(pool)]
-            nul_slot = [torch.zeros(len(types), dtype=torch.int64, device="cuda") for _ in range(pool)]
-            ev1 = [torch.cuda.Event() for _ in range(pool)]
-            ev2 = [torch.cuda.Event() for _ in range(pool)]
-            used = [False] * pool
 
         def convert(i):
-            bt = batches[i % pool]
-            o, carr = outs[i % pool]
-            rv = bt["rows"]
-            if overlap:
-                k = i % pool
-                if used[k]:
-                    stream.wait_event(ev2[k])          # phase 1 reuses the slot's outputs: phase 2 of its last use is done
-                N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                        nb, carr, nul_slot[k].data_ptr(), tot_slot[k].data_ptr(), None, wss[k].data_ptr(), st))
-                ev1[k].record(stream)
-                stream2.wait_event(ev1[k])
-                N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                          nb, carr, tot_slot[k].data_ptr(), wss[k].data_ptr(), st2))
-                ev2[k].record(stream2)
-                used[k] = True
-                return
+            k = i % pool
+            rv, o = batches[k]["rows"], outs[k]
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, wss[i % pool].data_ptr(), st))
+                                                    nb, o["carr"], nulls.data_ptr(), o["totals"].data_ptr(), None, wss[k].data_ptr(), st))
             N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                      nb, carr, totals.data_ptr(), wss[i % pool].data_ptr(), st))
-        kernels_per_batch = 1 + 3 + 1
+                                                      nb, o["carr"], o["totals"].data_ptr(), wss[k].data_ptr(), st))
+        kernels_per_batch = 3        # from_rows_wide_kernel, wide_group_scan_kernel, strings_wide_kernel
         metric = "rows_per_sec_convert_from_rows"
     else:
         # to_rows: plan (row sizes + scan; its size read-back is part of the API) + convert into preallocated buffers
@@ -565,7 +575,7 @@ def run_c3(args, wl, rank, world):
     torch.cuda.synchronize()
     for i in range(pool):
         if args.direction == "from_rows":
-            for a, b in zip(outs[i][0], batches[i]["cols"]):
+            for a, b in zip(outs[i]["cols"], batches[i]["cols"]):
                 assert torch.equal(a.mask, b.mask), "bench c3: mask mismatch"
                 if a.dtype.type_id == STRING:
                     assert torch.equal(a.offsets, b.offsets) and torch.equal(a.data, b.data), "bench c3: string mismatch"
@@ -580,36 +590,112 @@ def run_c3(args, wl, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        for i in range(nbatches):
-            convert(i)
+    # ---- multi-GPU: one all-gather of the packed slab per round, overlapped with the next round's conversion -------
+    if do_gather:
+        gbuf = [torch.empty(world * slab_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        pre, post = torch.cuda.Stream(), torch.cuda.Stream()
+        ev_conv = [torch.cuda.Event() for _ in range(pool)]
+        ev_done = [None] * pool                      # gather + rebase of the slot's last use finished
+        ev_gfree = [None, None]                      # the gathered buffer has been consumed (rebase done)
+        sidx = [i for i, t in enumerate(types) if t == STRING]
+        d_offs_at = torch.tensor([at_data[i] for i in sidx], dtype=torch.int64, device="cuda")
+        d_scol = torch.tensor(sidx, dtype=torch.int32, device="cuda")
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+        def gather(i):
+            k, gb = i % pool, i % 2
+            ev_conv[k].record(stream)
+            pre.wait_event(ev_conv[k])
+            if ev_gfree[gb] is not None:
+                pre.wait_event(ev_gfree[gb])
+            with torch.cuda.stream(pre):
+                _, work = sharding.gather_slab(dist, outs[k]["slab"], world, out=gbuf[gb], async_op=True)   # ONE ncclAllGather
+            with torch.cuda.stream(post):
+                work.wait()
+                gt = gbuf[gb].view(world, slab_bytes)[:, at_tot: at_tot + (nc + 1) * 8].contiguous().view(torch.int64)
+                N.check(lib.srj_shard_rebase_offsets(gbuf[gb].data_ptr(), slab_bytes, d_offs_at.data_ptr(), d_scol.data_ptr(),
+                                                     gt.data_ptr(), nb, nc, len(sidx), world, int(post.cuda_stream)))
+                e = torch.cuda.Event()
+                e.record(post)
+            ev_done[k], ev_gfree[gb] = e, e
+
+        # check the gathered table once: rank r's chunk of every column equals what rank r converted
+        convert(0)
+        gather(0)
+        torch.cuda.synchronize()
+        mine = gbuf[0].view(world, slab_bytes)[rank]
+        i0 = next(i for i, t in enumerate(types) if t != STRING)
+        assert torch.equal(mine[at_data[i0]: at_data[i0] + nb * SIZE[types[i0]]], outs[0]["cols"][i0].data), "bench c5: gathered chunk differs"
+        barrier()
+
+    def step(with_gather):
+        for i in range(rounds):
+            k = i % pool
+            if with_gather and ev_done[k] is not None:
+                stream.wait_event(ev_done[k])        # the slot's slab is free again
+            convert(i)
+            if with_gather:
+                gather(i)
+        if with_gather:
+            stream.wait_stream(post)
+
+    def timed(with_gather, steps):
+        for _ in range(args.warmup):
+            step(with_gather)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(steps):
+            step(with_gather)
+        t1.record(stream)
+        barrier()
+        tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]) / steps
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     cuprof = os.environ.get("SRJ_CUPROF") == "1"
     if cuprof:
         torch.cuda.cudart().cudaProfilerStart()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record(stream)
-    for _ in range(args.steps):
-        step()
-    if args.direction == "from_rows" and overlap:
-        stream.wait_stream(stream2)
-    t1.record(stream)
-    barrier()
+    ms_convert = timed(False, args.steps)                         # conversion only (no collective)
     if cuprof:
         torch.cuda.cudart().cudaProfilerStop()
+    ms_gather = timed(True, args.steps) if do_gather else None    # conversion + all-gather, inside the step
     clocks = sampler.stop() if rank == 0 else None
-    tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tt[0]) / args.steps
-    rows_step = nbatches * nb
+    ms_per_step = ms_gather if do_gather else ms_convert
+    rows_step = rounds * nb                                       # rows one rank converts per step
+    value = world * rows_step / (ms_per_step * 1e-3)
+    peak, peak_src = load_peaks()
+    achieved = alg_step / (ms_convert * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "kernel": "whole conversion of a batch: from_rows_wide_kernel + wide_group_scan_kernel + strings_wide_kernel"
+                if args.direction == "from_rows" else "whole conversion of a batch (all kernels of the two C-ABI calls)",
+                "algorithmic_bytes_per_row": alg_step / rows_step, "rows_per_launch": nb, "peak_source": peak_src,
+                "ms_per_batch": ms_convert / rounds, "per_gpu": True}
+    tr = os.path.join(ROOT, "profiles", "traffic_c3.json")
+    if os.path.exists(tr) and args.direction == "from_rows":
+        try:
+            j = json.load(open(tr))
+            roofline["traffic"] = j["dram_bytes_per_launch"] * (nb / j["rows_per_launch"])
+            roofline["traffic_source"] = j.get("source")
+        except Exception:
+            pass
+    if do_gather:
+        sent = slab_bytes
+        gms = max(ms_gather - ms_convert, 1e-9) / rounds
+        gather_info = {"collective": "one ncclAllGather of the rank's packed slab per round (columns + masks + STRING offsets + "
+                                     "totals + chars), overlapped with the next round's conversion; STRING offsets rebased by "
+                                     "srj_shard_rebase_offsets",
+                       "bytes_sent_per_gpu_per_round": sent, "bytes_received_per_gpu_per_round": sent * (world - 1),
+                       "rounds_per_step": rounds, "ms_per_step_convert_only": ms_convert, "ms_per_step_convert_plus_gather": ms_gather,
+                       "rows_per_sec_convert_only": world * rows_step / (ms_convert * 1e-3),
+                       "rows_per_sec_convert_plus_gather": world * rows_step / (ms_gather * 1e-3),
+                       "busbw_gbs": round(sent * (world - 1) / ((ms_gather / rounds) * 1e-3) / 1e9, 1),
+                       "exposed_gather_ms_per_round": gms}
+
     phases = None
     if args.direction == "from_rows" and os.environ.get("SRJ_BENCH_PHASES") == "1":
         # diagnostics: the two C-ABI calls of a batch timed separately (events around each call, 3 passes over the pool)
@@ -617,44 +703,70 @@ def run_c3(args, wl, rank, world):
         acc = [0.0, 0.0]
         cnt = 0
         for i in range(3 * pool):
-            bt = batches[i % pool]
-            o, carr = outs[i % pool]
-            rv = bt["rows"]
+            k = i % pool
+            rv, o = batches[k]["rows"], outs[k]
             ev[0].record(stream)
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                    nb, carr, nulls.data_ptr(), totals.data_ptr(), None, wss[i % pool].data_ptr(), st))
+                                                    nb, o["carr"], nulls.data_ptr(), o["totals"].data_ptr(), None, wss[k].data_ptr(), st))
             ev[1].record(stream)
             N.check(lib.srj_convert_from_rows_strings(plan.handle, rv.child.data.data_ptr(), rv.offsets.data_ptr(), rv.child.size,
-                                                      nb, carr, totals.data_ptr(), wss[i % pool].data_ptr(), st))
+                                                      nb, o["carr"], o["totals"].data_ptr(), wss[k].data_ptr(), st))
             ev[2].record(stream)
             torch.cuda.synchronize()
             acc[0] += ev[0].elapsed_time(ev[1]); acc[1] += ev[1].elapsed_time(ev[2]); cnt += 1
         phases = {"phase1_ms": acc[0] / cnt, "phase2_ms": acc[1] / cnt}
-    value = world * rows_step / (ms_per_step * 1e-3)
-    peak, peak_src = load_peaks()
-    achieved = alg_step / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "kernel": "whole conversion of a batch (all kernels of the two C-ABI calls)",
-                "algorithmic_bytes_per_row": alg_step / rows_step, "rows_per_launch": nb, "peak_source": peak_src,
-                "ms_per_batch": ms_per_step / nbatches}
+
     # ---- e2e through the public API with HOST buffers: pinned host rows -> device -> RowConversion.convertFromRows
     # (incl. its size read-back) -> pinned host columns; a bounded number of batches, same batches as above ------
     e2e = None
     cpu = None
     if not args.no_e2e and args.direction == "from_rows":
-        kb = min(pool, 4)
-        h_in, h_out = [], []
-        for i in range(kb):
-            rv = batches[i]["rows"]
-            h_in.append((rv.child.data.cpu().pin_memory(), rv.offsets.cpu().pin_memory()))
-            h_out.append([(torch.empty(c.data.numel(), dtype=torch.uint8, pin_memory=True),
-                           torch.empty(words, dtype=torch.int32, pin_memory=True),
-                           torch.empty(nb + 1, dtype=torch.int32, pin_memory=True) if c.dtype.type_id == STRING else None)
-                          for c in batches[i]["cols"]])
-        h2d = sum(a.numel() + 4 * b.numel() for a, b in h_in)
-        d2h = sum(sum(d.numel() + 4 * m.numel() + (4 * o.numel() if o is not None else 0) for d, m, o in hb) for hb in h_out)
+        e2e = e2e_c3(args, torch, dist, S, batches, dts, nb, words, pool, rank, world, barrier)
+        if rank == 0 and world == 1:
+            cpu = cpu_baseline_c3(batches[0], types, nb, words)
 
-        def e2e_batch(i):
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": wl["name"] + ("; row-range sharded over %d GPUs with one NCCL all-gather of the column "
+                                                     "chunks per round (BASELINE configs[4])" % world if do_gather else ""),
+                           "direction": args.direction, "total_rows_per_step": world * rows_step,
+                           "rows_per_step_per_gpu": rows_step, "batch_rows": nb, "rounds_per_step": rounds,
+                           "resident_pool_batches": pool, "avg_row_bytes": batches[0]["rows"].child.size / nb,
+                           "sharding": "contiguous row range per GPU" + (", all-gather inside the timed step" if do_gather else
+                                                                         ", no collective (single GPU or --no-gather)"),
+                           "l2": "each batch touches ~%.1f GB >> 126 MB L2; pool of %d distinct batches" % (alg[0] / 1e9, pool)},
+                "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": args.steps * rounds * kernels_per_batch, "clocks": clocks}
+        if gather_info:
+            line["allgather"] = gather_info
+        if phases:
+            line["phases"] = phases
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_c3(args, torch, dist, S, batches, dts, nb, words, pool, rank, world, barrier):
+    """Host rows -> host columns through the public API (pinned host buffers; H2D of the rows, the conversion incl. its
+    size read-back, D2H of every output buffer), two batches in flight on two host threads the way concurrent Spark
+    tasks share a GPU (the H2D of one batch overlaps the D2H of the other: PCIe is full duplex)."""
+    kb = min(pool, 4)
+    h_in, h_out = [], []
+    for i in range(kb):
+        rv = batches[i]["rows"]
+        h_in.append((rv.child.data.cpu().pin_memory(), rv.offsets.cpu().pin_memory()))
+        h_out.append([(torch.empty(c.data.numel(), dtype=torch.uint8, pin_memory=True),
+                       torch.empty(words, dtype=torch.int32, pin_memory=True),
+                       torch.empty(nb + 1, dtype=torch.int32, pin_memory=True) if c.dtype.type_id == STRING else None)
+                      for c in batches[i]["cols"]])
+    h2d = sum(a.numel() + 4 * b.numel() for a, b in h_in)
+    d2h = sum(sum(d.numel() + 4 * m.numel() + (4 * o.numel() if o is not None else 0) for d, m, o in hb) for hb in h_out)
+    dev = torch.cuda.current_device()
+
+    def e2e_batch(i, stream):
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
             a, b = h_in[i]
             dv = S.ColumnVector(S.DType.LIST, nb, None, None, b.cuda(non_blocking=True),
                                 S.ColumnVector(S.DType.INT8, a.numel(), a.cuda(non_blocking=True)))
@@ -664,52 +776,55 @@ def run_c3(args, wl, rank, world):
                 m.copy_(c.mask, non_blocking=True)
                 if o is not None:
                     o.copy_(c.offsets, non_blocking=True)
-        e2e_batch(0)
-        torch.cuda.synchronize()
-        barrier()
-        w0 = time.perf_counter()
-        for i in range(kb):
-            e2e_batch(i)
-        torch.cuda.synchronize()
-        barrier()
-        e2e_s = time.perf_counter() - w0
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * kb * nb / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": 1, "ms_per_step": float(te[0]) * 1e3,
-               "api": "srj_b200.RowConversion.convertFromRows on %d batches of %d rows, pinned host rows in / host columns out" % (kb, nb)}
-        if rank == 0:
-            from oracle import oracle as O
-            rvh, offh = h_in[0][0].numpy(), h_in[0][1].numpy()
-            nthreads = os.cpu_count()
-            hc = [O.HCol(t, np.empty(max(c.data.numel(), 1), np.uint8), np.empty(words, np.uint32),
-                         np.empty(nb + 1, np.int32) if t == STRING else None, 0, nb) for t, c in zip(types, batches[0]["cols"])]
-            O.from_rows_mt(rvh, offh, nb, hc, nthreads)
-            reps, tt_ = 0, 0.0
-            while tt_ < 10.0 and reps < 20:
-                t0_ = time.perf_counter()
-                O.from_rows_mt(rvh, offh, nb, hc, nthreads)
-                tt_ += time.perf_counter() - t0_
-                reps += 1
-            cpu = {"value": nb / (tt_ / reps), "unit": "rows/s", "cores": nthreads, "kind": "port",
-                   "sample": "one %d-row batch of the same workload x %d passes, %d OpenMP threads "
-                             "(oracle/srj_oracle.c orc_from_rows_mt: fixed fields + lengths, per-column scan, chars)" % (nb, reps, nthreads),
-                   "ms_per_pass": tt_ / reps * 1e3}
-        del h_in, h_out
+            stream.synchronize()
 
-    if rank == 0:
-        print(json.dumps({"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-                          "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": wl["name"], "direction": args.direction, "rows_per_step_per_gpu": rows_step,
-                                     "batch_rows": nb, "batches_per_step": nbatches, "resident_pool_batches": pool,
-                                     "avg_row_bytes": batches[0]["rows"].child.size / nb,
-                                     "l2": "each batch touches ~%.1f GB >> 126 MB L2; pool of %d distinct batches" % (alg[0] / 1e9, pool)},
-                          "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                          "gpu_launches": args.steps * nbatches * kernels_per_batch, "clocks": clocks, "phases": phases}))
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    e2e_batch(0, streams[0])
+    barrier()
+    reps = 2
+
+    def worker(w):
+        for r in range(reps):
+            for i in range(w, kb, 2):
+                e2e_batch(i, streams[w])
+    w0 = time.perf_counter()
+    th = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.destroy_process_group()
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    return {"value": world * reps * kb * nb / float(te[0]), "unit": "rows/s", "h2d_bytes_per_step": h2d * reps,
+            "d2h_bytes_per_step": d2h * reps, "steps": 1, "ms_per_step": float(te[0]) * 1e3,
+            "api": "srj_b200.RowConversion.convertFromRows on %d batches of %d rows x %d passes, pinned host rows in / host "
+                   "columns out, 2 host threads (2 batches in flight)" % (kb, nb, reps)}
+
+
+def cpu_baseline_c3(batch, types, nb, words, nthreads=None):
+    """The oracle's threaded from_rows over one batch of the same workload (rank 0, N=1)."""
+    from oracle import oracle as O
+    rv = batch["rows"]
+    rvh, offh = rv.child.data.cpu().numpy(), rv.offsets.cpu().numpy()
+    nthreads = nthreads or os.cpu_count()
+    hc = [O.HCol(t, np.empty(max(c.data.numel(), 1), np.uint8), np.empty(words, np.uint32),
+                 np.empty(nb + 1, np.int32) if t == STRING else None, 0, nb) for t, c in zip(types, batch["cols"])]
+    O.from_rows_mt(rvh, offh, nb, hc, nthreads)
+    times = []
+    while sum(times) < 10.0 and len(times) < 20:
+        t0_ = time.perf_counter()
+        O.from_rows_mt(rvh, offh, nb, hc, nthreads)
+        times.append(time.perf_counter() - t0_)
+    best = min(times)
+    return {"value": nb / best, "unit": "rows/s", "cores": nthreads, "kind": "port",
+            "sample": "one %d-row batch of the same workload, best of %d passes (mean %.1f ms), %d OpenMP threads "
+                      "(oracle/srj_oracle.c orc_from_rows_mt: fixed fields + lengths, per-column scan, chars)"
+                      % (nb, len(times), 1e3 * sum(times) / len(times), nthreads),
+            "ms_per_pass": best * 1e3}
 
 
 def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthreads=None):
@@ -740,29 +855,62 @@ def run_reference(args, wl, rank, world):
         return
     from oracle import oracle as O
     types = wl["types"]
-    st, sz, voff, spr = O.compute_layout(types)
-    row_size = (spr + 7) // 8 * 8
-    n = int(min(args.rows or wl["rows"], args.cpu_sample_rows))
-    hashed = "hash_keys" in wl
-    bpr = algorithmic_bytes_per_row(types, row_size, hashed)
-    rng = np.random.Generator(np.random.Philox(42))
-    data = rng.integers(0, 256, n * row_size, dtype=np.uint8)      # any bytes are valid fixed-width JCUDF rows
     nthreads = os.cpu_count()
-    cols = [O.HCol(t, np.empty(n * SIZE[t], np.uint8), np.empty((n + 31) // 32, np.uint32), None, 0, n) for t in types]
-    for _ in range(max(1, args.warmup)):
-        O.from_rows_fixed_mt(data, n, cols, nthreads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.from_rows_fixed_mt(data, n, cols, nthreads)
-    sec = (time.perf_counter() - t0) / args.steps
-    v = n / sec
-    cpu = {"value": v, "unit": "rows/s", "cores": nthreads, "kind": "port",
-           "sample": f"{n} rows per step (bounded sample of the {wl['rows']}-row workload), {nthreads} OpenMP threads"}
+    if STRING in types:
+        # C3: one batch of the workload generated on the host (to_rows by the threaded oracle: first touch of the row
+        # buffer is spread over the cores), converted by the oracle's threaded from_rows; best of the steps
+        nb = int(min(args.rows or wl["batch_rows"], wl["batch_rows"]))
+        cols = synth_c3_host(types, nb, wl["null_frac"], seed=4242)
+        rs = O.row_sizes(cols)
+        offs = np.zeros(nb + 1, np.int32)
+        np.cumsum(rs, out=offs[1:])
+        rows = np.empty(int(offs[-1]), np.uint8)
+        O.to_rows_mt(cols, 0, nb, offs, rows, nthreads)
+        words = (nb + 31) // 32
+        hc = [O.HCol(t, np.empty(max(len(c.data), 1), np.uint8), np.empty(words, np.uint32),
+                     np.empty(nb + 1, np.int32) if t == STRING else None, 0, nb) for t, c in zip(types, cols)]
+        for _ in range(max(1, args.warmup)):
+            O.from_rows_mt(rows, offs, nb, hc, nthreads)
+        assert np.array_equal(hc[3].offsets, cols[3].offsets) and np.array_equal(hc[0].data[: nb * 4], cols[0].data)
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            O.from_rows_mt(rows, offs, nb, hc, nthreads)
+            times.append(time.perf_counter() - t0)
+        sec = float(np.mean(times))
+        v = nb / sec
+        cfg = {"workload": wl["name"], "direction": "from_rows", "rows_per_step": nb, "batch_rows": nb,
+               "avg_row_bytes": len(rows) / nb, "columns": len(types)}
+        cpu = {"value": v, "unit": "rows/s", "cores": nthreads, "kind": "port", "best": nb / min(times),
+               "sample": f"one {nb}-row batch of the {wl['rows']}-row workload per step, {nthreads} OpenMP threads "
+                         f"(oracle/srj_oracle.c orc_from_rows_mt)"}
+    else:
+        st, sz, voff, spr = O.compute_layout(types)
+        row_size = (spr + 7) // 8 * 8
+        n = int(min(args.rows or wl["rows"], args.cpu_sample_rows))
+        data = np.empty(n * row_size, np.uint8)
+        step_ = 1 << 26                                  # filled in pieces: any bytes are valid fixed-width JCUDF rows
+        rng = np.random.Generator(np.random.Philox(42))
+        for o in range(0, len(data), step_):
+            data[o:o + step_] = rng.integers(0, 256, min(step_, len(data) - o), dtype=np.uint8)
+        cols = [O.HCol(t, np.empty(n * SIZE[t], np.uint8), np.empty((n + 31) // 32, np.uint32), None, 0, n) for t in types]
+        for _ in range(max(1, args.warmup)):
+            O.from_rows_fixed_mt(data, n, cols, nthreads)
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            O.from_rows_fixed_mt(data, n, cols, nthreads)
+            times.append(time.perf_counter() - t0)
+        sec = float(np.mean(times))
+        v = n / sec
+        cfg = {"workload": wl["name"], "rows_per_step": n, "row_bytes": row_size, "columns": len(types),
+               "note": "row conversion only" + (" (the fused hash of the GPU arm is not part of this CPU loop)" if "hash_keys" in wl else "")}
+        cpu = {"value": v, "unit": "rows/s", "cores": nthreads, "kind": "port", "best": n / min(times),
+               "sample": f"{n} rows per step (bounded sample of the {wl['rows']}-row workload), {nthreads} OpenMP threads"}
     print(json.dumps({"impl": "reference", "metric": "rows_per_sec_convert_from_rows", "value": v, "unit": "rows/s",
                       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                      "config": {"workload": wl["name"], "rows_per_step": n, "row_bytes": row_size, "columns": len(types)},
-                      "cpu_baseline": cpu,
+                      "higher_is_better": True, "scaling": "strong" if STRING in types else "weak", "vs_baseline": None,
+                      "dtype": "u8", "data": "synthetic", "config": cfg, "cpu_baseline": cpu,
                       "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0,
                       "note": "CPU restatement of the reference algorithm (oracle port); the reference's CUDA path cannot be "
@@ -775,11 +923,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 (default) = the configuration BASELINE.json's metric is quoted on; c2 / c4 = its other 1-GPU configs")
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
     ap.add_argument("--direction", default="from_rows", choices=["from_rows", "to_rows"])
+    ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the all-gather (conversion-only scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -211,6 +211,20 @@ SRJ_API int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int
 SRJ_API int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* out,
                           void* stream);
 
+/* ---- multi-GPU configuration (row-range shards + one all-gather of per-column chunks) ---------------- */
+/*
+ * After the NCCL all-gather of every rank's packed column slab, add to the STRING offsets of rank r's rows the chars
+ * the ranks before r hold for that column, so that the gathered chunks form one column.  No reference counterpart
+ * (the reference has no collective); the plugin-side caller owns the NCCL communicator.
+ *   gathered     : [world][slab_bytes] device buffer (the all-gather's output)
+ *   d_offs_at    : device int64[num_string_columns]: byte offset of each STRING column's int32 offsets[rows + 1] in a slab
+ *   d_scol       : device int32[num_string_columns]: schema column of each STRING column
+ *   d_totals     : device int64[world][num_columns + 1]: every rank's d_char_totals, all-gathered
+ */
+SRJ_API int srj_shard_rebase_offsets(void* gathered, int64_t slab_bytes, const int64_t* d_offs_at, const int32_t* d_scol,
+                                     const int64_t* d_totals, int64_t rows_per_shard, int32_t num_columns,
+                                     int32_t num_string_columns, int32_t world, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path: H2D + convert + D2H, pipelined in chunks) ------- */
 /*
  * Fixed-width-only schemas.  `h_rows` is num_rows * fixed_row_size bytes of HOST memory (pinned for

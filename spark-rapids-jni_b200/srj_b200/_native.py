@@ -60,6 +60,8 @@ SYMBOLS = {
     "srj_murmur_hash3_32": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_uint32, C.c_void_p,
                                       C.c_void_p]),
     "srj_hive_hash": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "srj_shard_rebase_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_void_p]),
     "srj_convert_from_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_void_p,
                                              C.c_int64]),
 }

@@ -44,3 +44,137 @@ def gather_fixed_columns(dist, chunks, world: int):
         dist.all_gather_into_tensor(full.view(-1), c.contiguous().view(-1))
         out.append(full.view(-1))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Packed slab: everything one rank contributes to the column all-gather, in ONE contiguous buffer, so that the
+# collective is a single ncclAllGather per round (north_star's multi-GPU configuration).
+# ---------------------------------------------------------------------------------------------------
+class SlabLayout:
+    """Byte layout of a rank's packed slab for `rows` rows of a schema:
+
+        [per column: fixed-width data (rows * size)  |  STRING: int32 offsets[rows + 1]]   256-byte aligned pieces
+        [per column: validity mask words]
+        [phase-1 totals: int64[ncols + 1]]
+        [chars of the STRING columns, back to back at 16-byte alignment, padded to the common capacity]
+
+    The shard height is a multiple of 32 rows, so the mask words of consecutive ranks concatenate.  After the
+    all-gather the chunks of rank r sit at gathered[r * nbytes + at_*]; STRING offsets of rank r > 0 are local to its
+    shard until srj_shard_rebase_offsets (CUDA) / rebase_offsets_host (numpy, tests) adds the chars of the ranks before.
+    """
+
+    def __init__(self, elem_sizes: Sequence[int], rows: int, chars_capacity: int, align: int = 256):
+        """elem_sizes[c] = bytes per element, 0 for a STRING column."""
+        self.rows = int(rows)
+        self.ncols = len(elem_sizes)
+        self.words = (self.rows + 31) // 32
+        self.string_cols = [c for c, s in enumerate(elem_sizes) if s == 0]
+        size = 0
+
+        def add(n):
+            nonlocal size
+            off = size
+            size = (off + int(n) + align - 1) // align * align
+            return off
+        self.at_data = [add((self.rows + 1) * 4 if s == 0 else self.rows * s) for s in elem_sizes]
+        self.data_bytes = [(self.rows + 1) * 4 if s == 0 else self.rows * s for s in elem_sizes]
+        self.at_mask = [add(self.words * 4) for _ in elem_sizes]
+        self.at_totals = add((self.ncols + 1) * 8)
+        self.chars_capacity = (int(chars_capacity) + align - 1) // align * align
+        self.at_chars = add(self.chars_capacity)
+        self.nbytes = size
+
+    def chars_offsets(self, chars_sizes: Sequence[int]) -> List[int]:
+        """Slab byte offset of each STRING column's chars given their sizes (16-byte aligned, back to back)."""
+        out, at = [], self.at_chars
+        for n in chars_sizes:
+            out.append(at)
+            at += (int(n) + 15) & ~15
+        if at - self.at_chars > self.chars_capacity:
+            raise ValueError("chars exceed the slab's capacity")
+        return out
+
+
+def rebase_offsets_host(gathered, layout: SlabLayout, world: int):
+    """numpy twin of srj_shard_rebase_offsets: gathered = uint8 array [world * layout.nbytes], modified in place."""
+    import numpy as np
+    g = gathered.reshape(world, layout.nbytes)
+    totals = np.stack([g[r, layout.at_totals: layout.at_totals + (layout.ncols + 1) * 8].view(np.int64) for r in range(world)])
+    for c in layout.string_cols:
+        delta = 0
+        for r in range(world):
+            if r:
+                o = g[r, layout.at_data[c]: layout.at_data[c] + (layout.rows + 1) * 4].view(np.int32)
+                o += np.int32(delta)
+            delta += int(totals[r, c])
+    return totals
+
+
+def gather_slab(dist, slab, world: int, out=None, async_op: bool = False):
+    """ONE all-gather of the rank's packed slab (torch uint8 tensor) -> [world * nbytes]."""
+    import torch
+    if out is None:
+        out = torch.empty(world * slab.numel(), dtype=slab.dtype, device=slab.device)
+    work = dist.all_gather_into_tensor(out, slab, async_op=async_op)
+    return out, work
+
+
+def convert_from_rows_into_slab(vec, dtypes, layout: SlabLayout, slab):
+    """This rank's shard: JCUDF rows (LIST<INT8> ColumnView `vec`, layout.rows rows) -> columns written straight into the
+    packed slab (torch uint8 CUDA tensor of layout.nbytes) through the C ABI -- phase 1, the size read-back, phase 2.
+    Returns the output ColumnVectors (views into the slab)."""
+    import ctypes as C
+
+    import torch
+
+    from . import ColumnVector, DType, Plan, _native as N
+    n, nc = layout.rows, layout.ncols
+    assert vec.size == n and slab.numel() >= layout.nbytes
+    plan = Plan.get(dtypes)
+    lib = N.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for i, d in enumerate(dtypes):
+        m = slab[layout.at_mask[i]: layout.at_mask[i] + layout.words * 4].view(torch.int32)
+        if d.type_id == DType.STRING:
+            outs.append(ColumnVector(d, n, None, m, slab[layout.at_data[i]: layout.at_data[i] + (n + 1) * 4].view(torch.int32)))
+        else:
+            outs.append(ColumnVector(d, n, slab[layout.at_data[i]: layout.at_data[i] + n * d.size_in_bytes()], m))
+    carr = (N.SrjColumn * nc)()
+    for i, c in enumerate(outs):
+        carr[i] = c._c()
+    totals = slab[layout.at_totals: layout.at_totals + (nc + 1) * 8].view(torch.int64)
+    nulls = torch.zeros(nc, dtype=torch.int64, device=slab.device)
+    wsb = lib.srj_from_rows_workspace_bytes(plan.handle, n)
+    ws = torch.empty(max(wsb, 8), dtype=torch.uint8, device=slab.device)
+    child = vec.child
+    N.check(lib.srj_convert_from_rows_fixed(plan.handle, child.data.data_ptr(), vec.offsets.data_ptr(), child.size, n, carr,
+                                            nulls.data_ptr(), totals.data_ptr(), None, ws.data_ptr(), st), "convertFromRows")
+    if layout.string_cols:
+        h_tot = totals.cpu().numpy()
+        at = layout.chars_offsets([int(h_tot[c]) for c in layout.string_cols])
+        for a, c in zip(at, layout.string_cols):
+            outs[c].data = slab[a: a + int(h_tot[c])]
+            carr[c] = outs[c]._c()
+        N.check(lib.srj_convert_from_rows_strings(plan.handle, child.data.data_ptr(), vec.offsets.data_ptr(), child.size, n, carr,
+                                                  totals.data_ptr(), ws.data_ptr(), st), "convertFromRows")
+    h_nulls = nulls.cpu().numpy()
+    for i, o in enumerate(outs):
+        o._null_count = int(h_nulls[i])
+    return outs
+
+
+def rebase_gathered_offsets(gathered, layout: SlabLayout, world: int):
+    """srj_shard_rebase_offsets on the all-gathered slabs (torch uint8 CUDA tensor [world * layout.nbytes]), in place."""
+    import torch
+
+    from . import _native as N
+    dev = gathered.device
+    d_at = torch.tensor([layout.at_data[c] for c in layout.string_cols], dtype=torch.int64, device=dev)
+    d_sc = torch.tensor(layout.string_cols, dtype=torch.int32, device=dev)
+    gt = gathered.view(world, layout.nbytes)[:, layout.at_totals: layout.at_totals + (layout.ncols + 1) * 8].contiguous().view(torch.int64)
+    N.check(N.lib().srj_shard_rebase_offsets(gathered.data_ptr(), layout.nbytes, d_at.data_ptr(), d_sc.data_ptr(), gt.data_ptr(),
+                                             layout.rows, layout.ncols, len(layout.string_cols), world,
+                                             int(torch.cuda.current_stream().cuda_stream)), "shard_rebase_offsets")
+    torch.cuda.current_stream().synchronize()     # d_at / d_sc / gt must outlive the kernel
+    return gt

@@ -93,3 +93,86 @@ def test_row_range_properties():
             assert rs[0][0] == 0 and rs[-1][1] == n
             for (a0, a1), (b0, b1) in zip(rs[:-1], rs[1:]):
                 assert a1 == b0 and a0 <= a1 and (a1 % 32 == 0 or a1 == n)
+
+
+# ---------------------------------------------------------------------------------------------------
+# packed slab + ONE all-gather + STRING offsets rebase (the multi-GPU configuration's host logic), world 2 on gloo
+# ---------------------------------------------------------------------------------------------------
+def _slab_worker(rank, world, port, nrows, q):
+    for p in (ROOT, os.path.join(ROOT, "spark-rapids-jni_b200"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        from srj_b200 import sharding
+        from util import random_table
+        types = [O.INT32, O.STRING, O.INT64, O.DECIMAL128, O.STRING, O.BOOL8]
+        cols = random_table(types, nrows, seed=5)             # same seeded table on every rank
+        (offs, data), = O.convert_to_rows(cols)
+        per = nrows // world
+        assert per % 32 == 0 and per * world == nrows
+        r0, r1 = rank * per, (rank + 1) * per
+        b0, b1 = sharding.rows_byte_range(offs, r0, r1)
+        mine, _ = O.convert_from_rows(data[b0:b1], (offs[r0:r1 + 1] - offs[r0]).astype(np.int32), per, types)
+        want, _ = O.convert_from_rows(data, offs, nrows, types)
+        cap = max(sum((len(c.data) + 15) & ~15 for c in want if c.type_id == O.STRING), 16)
+        lay = sharding.SlabLayout([0 if t == O.STRING else O.size_of(t) for t in types], per, cap)
+        slab = np.zeros(lay.nbytes, np.uint8)
+        totals = np.zeros(len(types) + 1, np.int64)
+        sizes = [len(c.data) for c in mine if c.type_id == O.STRING]
+        at_chars = iter(lay.chars_offsets(sizes))
+        for i, c in enumerate(mine):
+            if c.type_id == O.STRING:
+                slab[lay.at_data[i]: lay.at_data[i] + (per + 1) * 4] = c.offsets.view(np.uint8)
+                a = next(at_chars)
+                slab[a: a + len(c.data)] = c.data
+                totals[i] = len(c.data)
+            else:
+                raw = np.ascontiguousarray(c.data).view(np.uint8)
+                slab[lay.at_data[i]: lay.at_data[i] + len(raw)] = raw
+            slab[lay.at_mask[i]: lay.at_mask[i] + lay.words * 4] = c.mask.view(np.uint8)
+        slab[lay.at_totals: lay.at_totals + len(totals) * 8] = totals.view(np.uint8)
+        gathered, _ = sharding.gather_slab(dist, torch.from_numpy(slab), world)       # ONE collective
+        g = gathered.numpy()
+        tot_all = sharding.rebase_offsets_host(g, lay, world)
+        g2 = g.reshape(world, lay.nbytes)
+        ok = True
+        for i, c in enumerate(want):
+            m = np.concatenate([g2[r, lay.at_mask[i]: lay.at_mask[i] + lay.words * 4].view(np.uint32) for r in range(world)])
+            ok &= np.array_equal(m, c.mask)
+            if c.type_id == O.STRING:
+                o = [g2[r, lay.at_data[i]: lay.at_data[i] + (per + 1) * 4].view(np.int32) for r in range(world)]
+                glob = np.concatenate([o[0]] + [x[1:] for x in o[1:]])
+                ok &= np.array_equal(glob, c.offsets)
+                ok &= all(o[r][0] == o[r - 1][-1] for r in range(1, world))       # chunk r starts where r-1 ended
+                chars = []
+                for r in range(world):
+                    sz = [int(tot_all[r, j]) for j in lay.string_cols]
+                    a = lay.chars_offsets(sz)[lay.string_cols.index(i)]
+                    chars.append(g2[r, a: a + int(tot_all[r, i])])
+                ok &= np.array_equal(np.concatenate(chars), c.data)
+            else:
+                w = O.size_of(c.type_id)
+                d = np.concatenate([g2[r, lay.at_data[i]: lay.at_data[i] + per * w] for r in range(world)])
+                ok &= np.array_equal(d, np.ascontiguousarray(c.data).view(np.uint8))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_slab_one_allgather_with_strings():
+    world, nrows = 2, 1024
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, nrows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
