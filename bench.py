@@ -592,7 +592,17 @@ def run_c3(args, wl, rank, world):
 
     # ---- multi-GPU: one all-gather of the packed slab per round, overlapped with the next round's conversion -------
     if do_gather:
-        gbuf = [torch.empty(world * slab_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        peer = None
+        if args.gather == "p2p":
+            try:
+                peer = sharding.PeerGather(dist, slab_bytes, world, rank, torch.device("cuda", local))
+                gbuf = peer.bufs
+            except Exception as ex:                   # symmetric memory unavailable: fall back to the NCCL collective
+                if rank == 0:
+                    print("bench: peer-memory gather unavailable (%s); using ncclAllGather" % ex, file=sys.stderr)
+                peer = None
+        if peer is None:
+            gbuf = [torch.empty(world * slab_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)]
         pre, post = torch.cuda.Stream(), torch.cuda.Stream()
         ev_conv = [torch.cuda.Event() for _ in range(pool)]
         ev_done = [None] * pool                      # gather + rebase of the slot's last use finished
@@ -604,13 +614,20 @@ def run_c3(args, wl, rank, world):
         def gather(i):
             k, gb = i % pool, i % 2
             ev_conv[k].record(stream)
-            pre.wait_event(ev_conv[k])
-            if ev_gfree[gb] is not None:
-                pre.wait_event(ev_gfree[gb])
-            with torch.cuda.stream(pre):
-                _, work = sharding.gather_slab(dist, outs[k]["slab"], world, out=gbuf[gb], async_op=True)   # ONE ncclAllGather
+            if peer is not None:
+                if ev_gfree[gb] is not None:
+                    peer.main.wait_event(ev_gfree[gb])
+                landed = peer.gather(outs[k]["slab"], gb, ev_conv[k])     # copy engines over NVLink peer memory
+                post.wait_event(landed)
+            else:
+                pre.wait_event(ev_conv[k])
+                if ev_gfree[gb] is not None:
+                    pre.wait_event(ev_gfree[gb])
+                with torch.cuda.stream(pre):
+                    _, work = sharding.gather_slab(dist, outs[k]["slab"], world, out=gbuf[gb], async_op=True)   # ONE ncclAllGather
             with torch.cuda.stream(post):
-                work.wait()
+                if peer is None:
+                    work.wait()
                 gt = gbuf[gb].view(world, slab_bytes)[:, at_tot: at_tot + (nc + 1) * 8].contiguous().view(torch.int64)
                 N.check(lib.srj_shard_rebase_offsets(gbuf[gb].data_ptr(), slab_bytes, d_offs_at.data_ptr(), d_scol.data_ptr(),
                                                      gt.data_ptr(), nb, nc, len(sidx), world, int(post.cuda_stream)))
@@ -686,9 +703,12 @@ def run_c3(args, wl, rank, world):
     if do_gather:
         sent = slab_bytes
         gms = max(ms_gather - ms_convert, 1e-9) / rounds
-        gather_info = {"collective": "one ncclAllGather of the rank's packed slab per round (columns + masks + STRING offsets + "
-                                     "totals + chars), overlapped with the next round's conversion; STRING offsets rebased by "
-                                     "srj_shard_rebase_offsets",
+        gather_info = {"collective": ("all-gather of the rank's packed slab per round over NVLink peer memory (symmetric memory, "
+                                      "copy engines: no SM taken from the conversion kernels)" if peer is not None else
+                                      "one ncclAllGather of the rank's packed slab per round") +
+                                     " (columns + masks + STRING offsets + totals + chars), overlapped with the next round's "
+                                     "conversion; STRING offsets rebased by srj_shard_rebase_offsets",
+                       "transport": "p2p-copy-engine" if peer is not None else "nccl",
                        "bytes_sent_per_gpu_per_round": sent, "bytes_received_per_gpu_per_round": sent * (world - 1),
                        "rounds_per_step": rounds, "ms_per_step_convert_only": ms_convert, "ms_per_step_convert_plus_gather": ms_gather,
                        "rows_per_sec_convert_only": world * rows_step / (ms_convert * 1e-3),
@@ -930,6 +950,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
     ap.add_argument("--direction", default="from_rows", choices=["from_rows", "to_rows"])
     ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the all-gather (conversion-only scaling)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU all-gather transport: copy engines over NVLink peer memory (default) or ncclAllGather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

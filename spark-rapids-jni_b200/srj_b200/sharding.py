@@ -178,3 +178,53 @@ def rebase_gathered_offsets(gathered, layout: SlabLayout, world: int):
                                              int(torch.cuda.current_stream().cuda_stream)), "shard_rebase_offsets")
     torch.cuda.current_stream().synchronize()     # d_at / d_sc / gt must outlive the kernel
     return gt
+
+
+class PeerGather:
+    """All-gather of the packed slabs over NVLink / NVSwitch PEER MEMORY with the copy engines: every rank copies its
+    slab straight into slot `rank` of every peer's gathered buffer (symmetric memory), so the collective takes no SM and
+    no shared memory away from the conversion kernels it overlaps with (those are persistent, one CTA per SM with
+    ~all of its shared memory: an SM-based collective kernel can only run in the gaps between them).
+
+    gather(slab, buf_index) enqueues, on the side streams, for round-robin buffer `buf_index`:
+      barrier (every peer is done with this buffer's previous contents) -> N copies -> barrier (all copies landed).
+    `done` (a CUDA event) then marks the gathered buffer complete.
+    """
+
+    def __init__(self, dist, slab_bytes: int, world: int, rank: int, device, nbuf: int = 2):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.world, self.rank, self.slab_bytes = torch, world, rank, int(slab_bytes)
+        self.bufs, self.hdls, self.peers = [], [], []
+        group = dist.group.WORLD
+        for _ in range(nbuf):
+            t = symm_mem.empty(world * self.slab_bytes, dtype=torch.uint8, device=device)
+            h = symm_mem.rendezvous(t, group.group_name)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.peers.append([h.get_buffer(p, (world * self.slab_bytes,), torch.uint8) for p in range(world)])
+        self.main = torch.cuda.Stream()
+        self.side = [torch.cuda.Stream() for _ in range(world)]
+
+    def gather(self, slab, b: int, after_event):
+        """Enqueue the all-gather of `slab` into buffer b once `after_event` (the conversion) has completed.
+        Returns an event recorded when every rank's slab has landed in this rank's buffer b."""
+        torch = self.torch
+        self.main.wait_event(after_event)
+        with torch.cuda.stream(self.main):
+            self.hdls[b].barrier(channel=0)              # peers have consumed the buffer's previous contents
+            start = torch.cuda.Event()
+            start.record(self.main)
+        lo, hi = self.rank * self.slab_bytes, (self.rank + 1) * self.slab_bytes
+        for p in range(self.world):                      # one stream per destination: the copy engines run in parallel
+            q = (self.rank + p) % self.world             # staggered so that no destination is hit by everyone at once
+            s = self.side[p]
+            s.wait_event(start)
+            with torch.cuda.stream(s):
+                self.peers[b][q][lo:hi].copy_(slab, non_blocking=True)
+            self.main.wait_stream(s)
+        with torch.cuda.stream(self.main):
+            self.hdls[b].barrier(channel=1)              # every rank's copies into every buffer b have completed
+            done = torch.cuda.Event()
+            done.record(self.main)
+        return done
