@@ -7,6 +7,8 @@
 #include <cstring>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "hash_device.cuh"
 #include "kernels.hpp"
@@ -15,6 +17,14 @@
 namespace srj {
 
 static thread_local char g_err[512] = "";
+
+// NVTX range of one C-ABI call (the reference wraps its entry points the same way: nvtx_ranges.hpp:24-46,
+// SRJ_FUNC_RANGE); header-only NVTX v3, a no-op unless a profiler is attached.
+struct ApiRange {
+  explicit ApiRange(const char* name) { nvtxRangePushA(name); }
+  ~ApiRange() { nvtxRangePop(); }
+};
+#define SRJ_API_RANGE() ::srj::ApiRange _srj_range(__func__)
 
 void set_error(const char* fmt, ...)
 {
@@ -179,6 +189,7 @@ int srj_compute_layout(const int32_t* type_ids, int32_t num_columns, srj_layout*
 
 int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_columns, srj_plan** out)
 {
+  SRJ_API_RANGE();
   if (!out) { set_error("plan_create: out is null"); return SRJ_EINVAL; }
   *out = nullptr;
   srj_layout lay{};
@@ -232,11 +243,31 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   if (R >= 128) R = R / 128 * 128;  // 4 row groups per unit => predicate-free fast path
   if (R < 32) R = fitrows >= 16 ? 16 : 8;
   // development knobs (tuning only)
-  if (const char* e = getenv("SRJ_FR_STAGES")) tl.num_stages = atoi(e);
-  if (const char* e = getenv("SRJ_FR_TILE_ROWS")) { R = atoi(e); tl.stage_bytes = std::max(R * S, 4096); }
-  if (const char* e = getenv("SRJ_FR_STAGE_KB")) tl.stage_bytes = atoi(e) * 1024;
+  if (const int v = SRJ_KNOB("SRJ_FR_STAGES", 0)) tl.num_stages = v;
+  if (const int v = SRJ_KNOB("SRJ_FR_TILE_ROWS", 0)) { R = v; tl.stage_bytes = std::max(R * S, 4096); }
+  if (const int v = SRJ_KNOB("SRJ_FR_STAGE_KB", 0)) tl.stage_bytes = v * 1024;
   tl.tile_rows     = R;
   tl.rows_per_item = R >= 32 ? 32 : R;
+  // The per-schema shared-memory tables (entry starts, column and mask pointers, null counters) come on top of the
+  // stages: for very wide schemas shrink the stages until the kernel's request fits the 227 KB limit.
+  {
+    const int nent_fr = static_cast<int>(p->fr_entries.size());
+    while (from_rows_smem_bytes(tl, nent_fr, num_columns, lay.num_string_columns) > 232448 && tl.stage_bytes > 8 * 1024) {
+      tl.stage_bytes   = (tl.stage_bytes * 3 / 4) & ~127;
+      int fit          = tl.stage_bytes / S;
+      int r2           = fit / 32 * 32;
+      if (r2 > 512) r2 = 512;
+      if (r2 >= 128) r2 = r2 / 128 * 128;
+      if (r2 < 32) r2 = fit >= 16 ? 16 : 8;
+      tl.tile_rows     = r2;
+      tl.rows_per_item = r2 >= 32 ? 32 : r2;
+    }
+    if (from_rows_smem_bytes(tl, nent_fr, num_columns, lay.num_string_columns) > 232448) {
+      delete p;
+      set_error("plan_create: schema too wide for the kernels' shared-memory tables (%d columns)", num_columns);
+      return SRJ_EUNSUPPORTED;
+    }
+  }
 
   plan_wide(p);  // slabs of a wide variable-width table (from_rows_wide.cu); p->wide.enabled says whether it applies
 
@@ -335,6 +366,7 @@ static int read_u64(const uint64_t* d, int64_t i, uint64_t* out, cudaStream_t s)
 int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64_t num_rows, void* workspace,
                              srj_row_batch* batches, int32_t max_batches, int32_t* num_batches, void* stream_)
 {
+  SRJ_API_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "to_rows_plan_batches");
   if (rc != SRJ_OK) return rc;
@@ -426,6 +458,7 @@ int srj_convert_to_rows(const srj_plan* plan, const srj_column* cols, int64_t nu
                         const srj_row_batch* batches, int32_t num_batches, int32_t* const* batch_offsets,
                         uint8_t* const* batch_data, void* stream_)
 {
+  SRJ_API_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_to_rows");
   if (rc != SRJ_OK) return rc;
@@ -481,6 +514,7 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
                                 int64_t rows_bytes, int64_t num_rows, const srj_column* cols, int64_t* d_null_counts,
                                 int64_t* d_char_totals, const srj_fused_hash* hash, void* workspace, void* stream_)
 {
+  SRJ_API_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_from_rows");
   if (rc != SRJ_OK) return rc;
@@ -554,6 +588,7 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
                                   int64_t rows_bytes, int64_t num_rows, const srj_column* cols,
                                   const int64_t* d_char_totals, const void* workspace, void* stream_)
 {
+  SRJ_API_RANGE();
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc              = check_cols(plan, cols, num_rows, "convert_from_rows_strings");
   if (rc != SRJ_OK) return rc;
@@ -594,6 +629,7 @@ int srj_get_max_stack_depth(void) { return SRJ_MAX_STACK_DEPTH; }
 
 int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, int64_t* out, void* stream)
 {
+  SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("xxhash64: bad argument"); return SRJ_EINVAL; }
   return launch_hash(SRJ_HASH_XXHASH64, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
 }
@@ -601,12 +637,14 @@ int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, 
 int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num_rows, uint32_t seed, int32_t* out,
                         void* stream)
 {
+  SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("murmur_hash3_32: bad argument"); return SRJ_EINVAL; }
   return launch_hash(SRJ_HASH_MURMUR3_32, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
 }
 
 int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* out, void* stream)
 {
+  SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("hive_hash: bad argument"); return SRJ_EINVAL; }
   return launch_hash(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
 }
@@ -617,6 +655,7 @@ int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows,
 int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int64_t num_rows, const srj_column* h_cols,
                                int64_t* h_null_counts, int64_t chunk_rows)
 {
+  SRJ_API_RANGE();
   int rc = check_cols(plan, h_cols, num_rows, "convert_from_rows_host");
   if (rc != SRJ_OK) return rc;
   if (plan->num_string_columns > 0) { set_error("convert_from_rows_host: fixed-width schemas only"); return SRJ_EUNSUPPORTED; }
@@ -628,9 +667,9 @@ int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int6
     // Per chunk there are 2 copies per column (data + mask) of fixed cost, and the first H2D / last D2H of the
     // pipeline are not overlapped: ~1/12 of the input, between 32 MB and 1 GB of rows (measured on C2: 64 MB
     // chunks 153 M rows/s, 256 MB 217 M, 1 GB 238 M).
-    const char* e     = getenv("SRJ_HOST_CHUNK_MB");  // tuning knob (development)
+    const int e       = SRJ_KNOB("SRJ_HOST_CHUNK_MB", 0);  // tuning knob (development builds)
     int64_t cbytes    = std::min<int64_t>(1ll << 30, std::max<int64_t>(32ll << 20, num_rows * S / 12));
-    if (e) cbytes = static_cast<int64_t>(std::max(1, atoi(e))) << 20;
+    if (e) cbytes = static_cast<int64_t>(std::max(1, e)) << 20;
     chunk_rows        = std::max<int64_t>(32 * 1024, cbytes / S);
   }
   const int64_t T = plan->tiling.tile_rows >= 32 ? plan->tiling.tile_rows : 32;

@@ -899,7 +899,7 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   // super-tile = a multiple of the tile height (=> of 32 or 8|16: mask-byte aligned).  Fixed-stride
   // tables: two tiles (measured: 1 -> 2 tiles +1.5 % on C2, flat beyond).  Variable-width tables cut tiles adaptively inside a
   // super-tile of >= 4 tiles so the last, shorter tile of a super-tile is amortised.
-  static const int sup_tiles_env = []() { const char* e = getenv("SRJ_FR_SUPER"); return e ? atoi(e) : 0; }();
+  const int sup_tiles_env = SRJ_KNOB("SRJ_FR_SUPER", 0);
   const int64_t T  = p.tile_rows;
   int sup_tiles    = row_offsets ? 8 : 2;
   if (sup_tiles_env > 0) sup_tiles = sup_tiles_env;
@@ -907,7 +907,7 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
   const int64_t ns = (num_rows + p.super_rows - 1) / p.super_rows;
   int64_t grid     = std::min<int64_t>(nsm, ns);
   const size_t smem    = from_rows_smem_bytes(plan->tiling, p.nentries, p.ncols, plan->num_string_columns);
-  static const int variant = []() { const char* e = getenv("SRJ_FR_VARIANT"); return e ? atoi(e) : 0; }();
+  const int variant = SRJ_KNOB("SRJ_FR_VARIANT", 0);
   int rc;
   switch (variant) {
     case 2: rc = launch_variant<7>(p, static_cast<unsigned>(grid), smem, stream); break;

@@ -288,7 +288,7 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
       p.cols[i] = HashCol{static_cast<const uint8_t*>(c.data), c.null_mask, c.offsets, static_cast<int16_t>(t),
                           static_cast<int16_t>(kind2), elem_size(t)};
     }
-    bool plain = getenv("SRJ_HASH_GENERAL") == nullptr;
+    bool plain = SRJ_KNOB("SRJ_HASH_GENERAL", 0) == 0;
     for (int i = 0; i < p.ncols; ++i) plain = plain && p.cols[i].kind != 0;
     if (plain) {
       // persistent launch: as many CTAs as stay resident (the kernel strides over the row blocks)
@@ -310,8 +310,8 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
           SRJ_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, row_hash_plain_kernel<SRJ_HASH_HIVE>, kHashThreads, 0));
         occ_cache[kind & 3] = occ = std::max(1, occ);
       }
-      const char* e_w      = getenv("SRJ_HASH_WAVES");  // tuning knob (development): CTAs per SM, 0 = one CTA per row block
-      const int waves      = e_w ? atoi(e_w) : std::max(1, occ) * (kind == SRJ_HASH_HIVE ? 1 : 4);
+      const int e_w        = SRJ_KNOB("SRJ_HASH_WAVES", -1);  // tuning knob (development builds): CTAs per SM, 0 = one CTA per row block
+      const int waves      = e_w >= 0 ? e_w : std::max(1, occ) * (kind == SRJ_HASH_HIVE ? 1 : 4);
       const unsigned pgrid = waves > 0 ? std::min<unsigned>(grid, static_cast<unsigned>(nsm * waves)) : grid;
       if (kind == SRJ_HASH_XXHASH64)
         row_hash_plain_kernel<SRJ_HASH_XXHASH64><<<pgrid, kHashThreads, 0, stream>>>(p);

@@ -13,6 +13,8 @@ int launch_from_rows(const srj_plan* plan, const uint8_t* rows, const int32_t* r
                      int64_t num_rows, void* const* d_ent_dst, uint32_t* const* d_masks, int64_t* d_null_counts,
                      int64_t* d_status, const srj_fused_hash* fh, cudaStream_t stream);
 
+size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols, int nstr);  // dynamic shared memory of from_rows_kernel
+
 // from_rows_wide.cu: wide variable-width tables (per-row TMA slabs; offsets leave as group-local inclusive sums +
 // absolute group bases unless `finalize`)
 bool plan_wide(srj_plan* plan);

@@ -828,7 +828,7 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
   const int S = plan->fixed_row_size;
   int D       = 0;
   for (int sz : plan->col_size) D += sz;
-  bool fast = plan->num_string_columns == 0 && plan->d_tr_chunk_off != nullptr && getenv("SRJ_TR_GENERIC") == nullptr;
+  bool fast = plan->num_string_columns == 0 && plan->d_tr_chunk_off != nullptr && SRJ_KNOB("SRJ_TR_GENERIC", 0) == 0;
   int R = 0, NS = 3;
   if (fast) {
     // smem: NS staging stages of R*D bytes + 2 row images of R*S bytes (+ tables)
@@ -920,8 +920,8 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
   // many resident CTAs rather than deep buffering: variable-width tables use ONE 40 KB stage per CTA
   // (4-5 CTAs per SM); fixed-width tails keep two 48 KB stages.
   const bool var        = plan->num_string_columns > 0;
-  static const int env_stage_kb = []() { const char* e = getenv("SRJ_TR_STAGE_KB"); return e ? atoi(e) : 0; }();
-  static const int env_nbuf     = []() { const char* e = getenv("SRJ_TR_NBUF"); return e ? atoi(e) : 0; }();
+  const int env_stage_kb = SRJ_KNOB("SRJ_TR_STAGE_KB", 0);
+  const int env_nbuf     = SRJ_KNOB("SRJ_TR_NBUF", 0);
   int stage_bytes       = (var ? 44 : 48) * 1024;
   int nbuf              = var ? 1 : 2;
   if (env_stage_kb > 0) stage_bytes = env_stage_kb * 1024;
@@ -951,7 +951,24 @@ static int launch_to_rows_generic(const srj_plan* plan, const void* const* d_col
   SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   const int64_t T      = tile_rows;
   const int64_t ntiles = (row_count + T - 1) / T;
-  const size_t smem    = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str, nbuf);
+  size_t smem          = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str, nbuf);
+  // very wide schemas: the per-schema tables (entry starts, column pointers) come on top of the stages -- give up the
+  // second stage, then stage height, before giving up
+  while (smem > 232448 && (p.nbuf > 1 || p.stage_bytes > 16 * 1024)) {
+    if (p.nbuf > 1) p.nbuf = nbuf = 1;
+    else {
+      p.stage_bytes = stage_bytes = stage_bytes / 2;
+      tile_rows     = std::max(8, std::min(tile_rows, (stage_bytes / plan->fixed_row_size) / 8 * 8));
+      p.tile_rows   = tile_rows;
+      p.rpl         = tile_rows >= 32 ? 32 : tile_rows;
+      if (p.nstr > 0) p.max_str_entries = max_str = std::max(p.nstr, std::min(tile_rows * p.nstr, 2048));
+    }
+    smem = to_rows_smem_bytes(plan, tile_rows, stage_bytes, max_str, nbuf);
+  }
+  if (smem > 232448) {
+    set_error("to_rows: schema too wide for the kernel's shared-memory tables (%d columns need %zu bytes)", plan->num_columns, smem);
+    return SRJ_EUNSUPPORTED;
+  }
   const int per_sm     = std::max<int>(1, std::min<int>(8, static_cast<int>((228 * 1024) / (smem + 1024))));
   int64_t grid         = std::min<int64_t>(static_cast<int64_t>(nsm) * per_sm, ntiles);
   const int64_t per    = (ntiles + grid - 1) / grid;

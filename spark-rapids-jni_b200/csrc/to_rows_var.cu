@@ -754,8 +754,8 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   *launched = 0;
   const int nstr = plan->num_string_columns;
   if (nstr == 0 || row_count == 0 || !d_fail_flag || !h_col_data) return SRJ_OK;
-  if (getenv("SRJ_TR_GENERIC")) return SRJ_OK;
-  const bool force = getenv("SRJ_TR_VAR_FORCE") != nullptr;
+  if (SRJ_KNOB("SRJ_TR_GENERIC", 0)) return SRJ_OK;
+  const bool force = SRJ_KNOB("SRJ_TR_VAR_FORCE", 0) != 0;
   if ((reinterpret_cast<uintptr_t>(out_data) & 7) != 0) return SRJ_OK;
   for (const Entry& e : plan->tr_entries)
     if (reinterpret_cast<uintptr_t>(h_col_data[e.column]) & static_cast<uintptr_t>(plan->col_size[e.column] - 1)) return SRJ_OK;
@@ -763,7 +763,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   {
     // narrow rows: warp-private tiles (to_rows_w_kernel); wide rows: CTA tiles (to_rows3_kernel) below
     const int64_t avg = std::max<int64_t>(plan->fixed_row_size, out_bytes / row_count);
-    if (!force && !getenv("SRJ_TR_NOWARP") && (kWarpKernelDefault || getenv("SRJ_TR_WARP"))) {
+    if (!force && !SRJ_KNOB("SRJ_TR_NOWARP", 0) && (kWarpKernelDefault || SRJ_KNOB("SRJ_TR_WARP", 0))) {
       const int rc = launch_to_rows_warp(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets,
                                          out_data, avg, d_fail_flag, stream, launched);
       if (rc != SRJ_OK || *launched) return rc;
@@ -773,9 +773,9 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   p.nfixed  = static_cast<int32_t>(plan->tr_entries.size());
   p.ncols   = plan->num_columns;
   p.nstr    = nstr;
-  const int env_sb = getenv("SRJ_T3_SB") ? atoi(getenv("SRJ_T3_SB")) : 0;  // tuning knobs (development)
-  const int env_su = getenv("SRJ_T3_SUPER") ? atoi(getenv("SRJ_T3_SUPER")) : 0;
-  const int env_w  = getenv("SRJ_T3_WARPS") ? atoi(getenv("SRJ_T3_WARPS")) : 0;
+  const int env_sb = SRJ_KNOB("SRJ_T3_SB", 0);  // tuning knobs (development builds)
+  const int env_su = SRJ_KNOB("SRJ_T3_SUPER", 0);
+  const int env_w  = SRJ_KNOB("SRJ_T3_WARPS", 0);
   const int nwarps = env_w == 12 ? 12 : 24;
   const int cps    = nwarps == 24 ? 1 : 2;  // CTAs per SM
   p.sb      = std::max(env_sb > 0 ? env_sb : (cps == 1 ? 4 : 8), (nstr + kT3MaxBlocks - 1) / kT3MaxBlocks);
@@ -793,7 +793,7 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
   const int64_t budget = 232448 / cps - 1024 - 64;
   // chars staging: a quarter of the budget at most, 1 KB per STRING column at most
   int64_t slot = std::min<int64_t>((budget - static_cast<int64_t>(tables)) / 4, 1024ll * nstr) / nstr / 16 * 16;
-  if (slot < 128 || getenv("SRJ_T3_NOSTAGE")) slot = 0;
+  if (slot < 128 || SRJ_KNOB("SRJ_T3_NOSTAGE", 0)) slot = 0;
   p.slot_bytes         = static_cast<int32_t>(slot);
   int64_t stage        = (budget - static_cast<int64_t>(tables) - slot * nstr) / 16 * 16;
   if (stage < 32 * 1024 || stage < 8ll * (plan->fixed_row_size + 64)) return SRJ_OK;

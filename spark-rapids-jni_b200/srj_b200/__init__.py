@@ -291,6 +291,10 @@ class RowConversion:
     @staticmethod
     def convertFromRows(vec: ColumnView, *schema) -> Table:
         """LIST<INT8> rows + schema -> Table (RowConversion.java:137-146, RC:2149-2441)."""
+        return RowConversion._from_rows(vec, schema, None)
+
+    @staticmethod
+    def _from_rows(vec: ColumnView, schema, fused):
         if vec is None:
             raise TypeError("input column is null")
         if len(schema) == 1 and isinstance(schema[0], (list, tuple)):
@@ -322,8 +326,20 @@ class RowConversion:
             ws_bytes = lib.srj_from_rows_workspace_bytes(plan.handle, n)
             ws = _empty(ws_bytes, torch.uint8, dev) if ws_bytes else None          # rmm allocation in the JNI shim
             ws_ptr = ws.data_ptr() if ws is not None else None
+            fh, hout = None, None
+            if fused is not None:
+                key_columns, kind, seed = fused
+                fh = N.SrjFusedHash()
+                fh.kind = {"xxhash64": N.HASH_XXHASH64, "murmur3": N.HASH_MURMUR3_32, "hive": N.HASH_HIVE}[kind]
+                fh.num_keys = len(key_columns)
+                for i, k in enumerate(key_columns):
+                    fh.key_columns[i] = int(k)
+                fh.seed = int(seed)
+                hout = _empty(n, torch.int64 if kind == "xxhash64" else torch.int32, dev)
+                fh.out = hout.data_ptr()
             N.check(lib.srj_convert_from_rows_fixed(plan.handle, rows_ptr, vec.offsets.data_ptr(), child.size, n,
-                                                    carr, nulls.data_ptr(), totals.data_ptr(), None, ws_ptr, stream),
+                                                    carr, nulls.data_ptr(), totals.data_ptr(),
+                                                    C.byref(fh) if fh is not None else None, ws_ptr, stream),
                     "convertFromRows")
             if plan.layout.num_string_columns:
                 h_tot = totals.cpu().numpy()                                           # the sync of RC:2389
@@ -338,6 +354,10 @@ class RowConversion:
             h_nulls = nulls.cpu().numpy()
             for i, o in enumerate(outs):
                 o._null_count = int(h_nulls[i])
+            if fused is not None:
+                kind = fused[1]
+                return Table(outs), ColumnVector(DType.INT64 if kind == "xxhash64" else DType.INT32, n,
+                                                 hout.view(torch.uint8), None, null_count=0)
             return Table(outs)
 
     @staticmethod
@@ -355,35 +375,15 @@ class RowConversion:
         return RowConversion.convertFromRows(vec, *dts)
 
     # fused from_rows + partition hash (BASELINE config 4); not in the Java surface, used by the plugin-side
-    # GpuHashPartitioning equivalent and by bench.py
+    # GpuHashPartitioning equivalent and by bench.py.  Keys are fixed-width columns; the schema may hold STRING columns.
     @staticmethod
     def convertFromRowsWithHash(vec: ColumnView, schema, key_columns: Sequence[int], kind: str = "xxhash64",
                                 seed: int = 42):
         dts = [_as_dtype(d) for d in schema]
-        for d in dts:
-            if not d.is_fixed_width():
-                raise CudfException("fused hash path: fixed-width schemas only")
-        dev = vec.offsets.device
-        with torch.cuda.device(dev):
-            plan = Plan.get(dts)
-            n = vec.size
-            words = (n + 31) // 32
-            outs = [ColumnVector(d, n, _empty(n * d.size_in_bytes(), torch.uint8, dev), _empty(words, torch.int32, dev))
-                    for d in dts]
-            fh = N.SrjFusedHash()
-            fh.kind = {"xxhash64": N.HASH_XXHASH64, "murmur3": N.HASH_MURMUR3_32, "hive": N.HASH_HIVE}[kind]
-            fh.num_keys = len(key_columns)
-            for i, k in enumerate(key_columns):
-                fh.key_columns[i] = int(k)
-            fh.seed = int(seed)
-            hout = _empty(n, torch.int64 if kind == "xxhash64" else torch.int32, dev)
-            fh.out = hout.data_ptr()
-            nulls = torch.zeros(max(len(dts), 1), dtype=torch.int64, device=dev)
-            N.check(N.lib().srj_convert_from_rows_fixed(plan.handle, vec.child.data.data_ptr(), None, vec.child.size,
-                                                        n, _carray(outs), nulls.data_ptr(), None, C.byref(fh), None,
-                                                        _stream_ptr()), "convertFromRowsWithHash")
-            return Table(outs), ColumnVector(DType.INT64 if kind == "xxhash64" else DType.INT32, n,
-                                             hout.view(torch.uint8), None)
+        for k in key_columns:
+            if not dts[int(k)].is_fixed_width():
+                raise CudfException("fused hash path: keys must be fixed-width columns")
+        return RowConversion._from_rows(vec, dts, (list(key_columns), kind, seed))
 
 
 class Hash:
