@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "hash_device.cuh"
 #include "kernels.hpp"
+#include "movers.cuh"
 
 namespace srj {
 
@@ -237,6 +238,193 @@ __global__ void __launch_bounds__(kHashThreads, KIND == SRJ_HASH_HIVE ? 5 : 4) r
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Streaming row hash for fixed-width keys (the shuffle-partitioning case: a few 4/8-byte key columns, 10^8 rows).
+// The kernels above issue their global loads from the hashing threads, so every row block waits a DRAM round trip
+// before its multiply chains can start (ncu: long-scoreboard 10 stalls per issue, 37 % of the HBM peak).  Here the
+// loads are decoupled from the arithmetic, the way the conversion kernels do it:
+//   producer warp : per chunk of kHsRows rows, one TMA bulk copy per key column (a contiguous, 16-byte aligned piece
+//                   of the column) and per mask into a ring of shared-memory stages guarded by full/empty mbarriers;
+//   consumer warps: lane = row, four rows per lane (four independent multiply chains), values read from shared
+//                   memory (conflict-free: consecutive lanes, consecutive elements), chained across the key columns
+//                   with the Spark rules, one coalesced store of the hash per row group.
+// --------------------------------------------------------------------------------------------------
+constexpr int kHsRows    = 2048;  // rows per chunk
+constexpr int kHsWarps   = 16;    // consumer warps: 4 row groups of a chunk each
+constexpr int kHsMaxCols = 16;    // key columns per launch
+constexpr int kHsMaxStages = 6;
+constexpr int kHsThreads = (kHsWarps + 1) * 32;
+
+struct HsParams {
+  HashCol cols[kHsMaxCols];
+  int32_t col_off[kHsMaxCols];   // byte offset of the column's values inside a stage
+  int32_t mask_off[kHsMaxCols];  // byte offset of its 64 mask words, or -1 (no mask: all valid)
+  int32_t ncols, first, stage_bytes, nstages;
+  int64_t seed;
+  int64_t nchunks;
+  void* out;
+};
+
+// One key column of a chunk for this lane's four rows (values at base + 32 j SIZE in the stage, mask words at mwa + 4 j).
+template <int KIND, int SIZE, bool PLAIN, class acc_t>
+__device__ __forceinline__ void hs_column(acc_t (&h)[4], uint32_t base, uint32_t mwa, int lane, int type)
+{
+  uint32_t mw[4];
+  uint64_t v[4], v2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mw[j] = mwa ? lds_u32(mwa + 4 * j) : 0xffffffffu;
+    const Reg<SIZE> q = lds_elem<SIZE>(base + 32 * j * SIZE);
+    v[j]  = q.v[0];
+    v2[j] = 0;
+    if constexpr (SIZE >= 8) v[j] |= static_cast<uint64_t>(q.v[1]) << 32;
+    if constexpr (SIZE == 16) v2[j] = static_cast<uint64_t>(q.v[2]) | (static_cast<uint64_t>(q.v[3]) << 32);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool ok = (mw[j] >> lane) & 1u;
+    if constexpr (KIND == SRJ_HASH_XXHASH64) {
+      uint64_t t;
+      if constexpr (PLAIN && SIZE == 4) t = hash::xx_u32(static_cast<uint32_t>(v[j]), h[j]);
+      else if constexpr (PLAIN) t = hash::xx_u64(v[j], h[j]);
+      else t = hash::xx_fixed(type, v[j], v2[j], h[j]);
+      h[j] = ok ? t : h[j];   // a null keeps the accumulator (xxhash64.cu:352-353)
+    } else if constexpr (KIND == SRJ_HASH_MURMUR3_32) {
+      uint32_t t;
+      if constexpr (PLAIN && SIZE == 4) t = hash::mm_u32(static_cast<uint32_t>(v[j]), h[j]);
+      else if constexpr (PLAIN) t = hash::mm_u64(v[j], h[j]);
+      else t = hash::mm_fixed(type, v[j], v2[j], h[j]);
+      h[j] = ok ? t : h[j];   // murmur_hash.cu:111-117
+    } else {
+      uint32_t x;
+      if constexpr (PLAIN && SIZE == 4) x = static_cast<uint32_t>(v[j]);
+      else if constexpr (PLAIN) x = static_cast<uint32_t>((v[j] >> 32) ^ v[j]);
+      else x = static_cast<uint32_t>(hash::hive_fixed(type, v[j]));
+      h[j] = 31u * h[j] + (ok ? x : 0u);   // hive_hash.cu:179-203 (null -> 0)
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kHsThreads, 1) row_hash_stream_kernel(const __grid_constant__ HsParams p)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full  = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(p.nstages) * p.stage_bytes);
+  uint64_t* empty = full + kHsMaxStages;
+  const int NS    = p.nstages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kHsWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int lane = lane_id();
+  if (warp_id() == 0) {
+    // =================================== producer ===================================
+    uint32_t tx = 0;
+    for (int c = 0; c < p.ncols; ++c) tx += static_cast<uint32_t>(kHsRows) * p.cols[c].size + (p.mask_off[c] >= 0 ? 256u : 0u);
+    int it = 0;
+    for (int64_t ch = blockIdx.x; ch < p.nchunks; ch += gridDim.x, ++it) {
+      const int s        = it % NS;
+      const uint32_t par = ((it / NS) & 1) ^ 1;
+      if (lane == 0) {
+        mbar_wait(&empty[s], par);
+        mbar_arrive_expect_tx(&full[s], tx);
+      }
+      __syncwarp();
+      uint8_t* st = smem + static_cast<size_t>(s) * p.stage_bytes;
+      if (lane < p.ncols) {   // one lane per key column: its values, then its mask words
+        const HashCol& col = p.cols[lane];
+        tma_load_1d(st + p.col_off[lane], col.data + ch * kHsRows * col.size, static_cast<uint32_t>(kHsRows) * col.size, &full[s]);
+        if (p.mask_off[lane] >= 0) tma_load_1d(st + p.mask_off[lane], col.mask + ch * (kHsRows / 32), 256u, &full[s]);
+      }
+    }
+  } else {
+    // =================================== consumers ===================================
+    using acc_t  = typename std::conditional<KIND == SRJ_HASH_XXHASH64, uint64_t, uint32_t>::type;
+    const int w  = warp_id() - 1;
+    int it       = 0;
+    for (int64_t ch = blockIdx.x; ch < p.nchunks; ch += gridDim.x, ++it) {
+      const int s        = it % NS;
+      const uint32_t par = (it / NS) & 1;
+      mbar_wait(&full[s], par);
+      const uint32_t st_s = smem_u32(smem + static_cast<size_t>(s) * p.stage_bytes);
+      const int64_t r0    = ch * kHsRows + (w * 4) * 32 + lane;   // this lane's rows: r0 + 32 j
+      acc_t h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.first) h[j] = KIND == SRJ_HASH_HIVE ? acc_t{0} : static_cast<acc_t>(p.seed);
+        else h[j] = reinterpret_cast<const acc_t*>(p.out)[r0 + 32 * j];
+      }
+      for (int c = 0; c < p.ncols; ++c) {
+        // the column's element size and hash flavour are warp-uniform: dispatch once per column, not per value
+        const int size = p.cols[c].size, type = p.cols[c].type;
+        const uint32_t base = st_s + static_cast<uint32_t>(p.col_off[c]) + static_cast<uint32_t>((w * 128 + lane) * size);
+        const uint32_t mwa  = p.mask_off[c] >= 0 ? st_s + static_cast<uint32_t>(p.mask_off[c]) + static_cast<uint32_t>(w * 16) : 0u;
+        if (p.cols[c].kind == 1) hs_column<KIND, 4, true>(h, base, mwa, lane, type);
+        else if (p.cols[c].kind == 2) hs_column<KIND, 8, true>(h, base, mwa, lane, type);
+        else if (size == 4) hs_column<KIND, 4, false>(h, base, mwa, lane, type);
+        else if (size == 8) hs_column<KIND, 8, false>(h, base, mwa, lane, type);
+        else if (size == 16) hs_column<KIND, 16, false>(h, base, mwa, lane, type);
+        else if (size == 2) hs_column<KIND, 2, false>(h, base, mwa, lane, type);
+        else hs_column<KIND, 1, false>(h, base, mwa, lane, type);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);   // the stage is free once its values are in registers
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<acc_t*>(p.out)[r0 + 32 * j] = h[j];
+    }
+  }
+}
+
+// Runs the streaming kernel over the whole chunks of the table when it applies; *done = rows it covered.
+static int launch_hash_stream(int kind, const HashParams& hp, int64_t num_rows, cudaStream_t stream, int64_t* done)
+{
+  *done = 0;
+  if (SRJ_KNOB("SRJ_HASH_NOSTREAM", 0) || hp.ncols > kHsMaxCols || num_rows < 4 * kHsRows) return SRJ_OK;
+  HsParams p{};
+  int off = 0;
+  for (int c = 0; c < hp.ncols; ++c) {
+    const HashCol& col = hp.cols[c];
+    if (col.size == 0) return SRJ_OK;                                              // STRING key: not staged
+    if (reinterpret_cast<uintptr_t>(col.data) & 15) return SRJ_OK;                 // TMA needs 16-byte aligned pieces
+    if (col.mask && (reinterpret_cast<uintptr_t>(col.mask) & 15)) return SRJ_OK;
+    p.cols[c]    = col;
+    p.col_off[c] = off;
+    off += kHsRows * col.size;
+    p.mask_off[c] = col.mask ? off : -1;
+    if (col.mask) off += 256;
+  }
+  p.ncols       = hp.ncols;
+  p.first       = hp.first;
+  p.seed        = hp.seed;
+  p.out         = hp.out;
+  p.stage_bytes = (off + 127) & ~127;
+  p.nstages     = std::min<int>(kHsMaxStages, (200 * 1024) / p.stage_bytes);
+  if (const int ns = SRJ_KNOB("SRJ_HASH_STAGES", 0)) p.nstages = std::min(p.nstages, ns);
+  if (p.nstages < 2) return SRJ_OK;
+  p.nchunks = num_rows / kHsRows;
+  int dev = 0, nsm = 0;
+  SRJ_CUDA_TRY(cudaGetDevice(&dev));
+  SRJ_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(nsm, p.nchunks));
+  const size_t smem   = static_cast<size_t>(p.nstages) * p.stage_bytes + 2 * kHsMaxStages * 8;
+  auto go = [&](auto kern) -> int {
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    kern<<<grid, kHsThreads, smem, stream>>>(p);
+    return SRJ_OK;
+  };
+  int rc;
+  if (kind == SRJ_HASH_XXHASH64) rc = go(row_hash_stream_kernel<SRJ_HASH_XXHASH64>);
+  else if (kind == SRJ_HASH_MURMUR3_32) rc = go(row_hash_stream_kernel<SRJ_HASH_MURMUR3_32>);
+  else rc = go(row_hash_stream_kernel<SRJ_HASH_HIVE>);
+  if (rc != SRJ_OK) return rc;
+  *done = p.nchunks * kHsRows;
+  return SRJ_OK;
+}
+
 static int elem_size(int32_t t)
 {
   switch (t) {
@@ -265,7 +453,6 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
     if (cols[c].size != num_rows) { set_error("hash: column %d has %lld rows, expected %lld", c, (long long)cols[c].size, (long long)num_rows); return SRJ_EINVAL; }
   }
   const int64_t per_block = static_cast<int64_t>(kHashThreads) * kRowsPerThread;
-  const unsigned grid     = static_cast<unsigned>((num_rows + per_block - 1) / per_block);
   for (int c0 = 0; c0 < num_columns; c0 += kHashColsPerLaunch) {
     HashParams p{};
     p.ncols = std::min(kHashColsPerLaunch, num_columns - c0);
@@ -288,6 +475,22 @@ int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t n
       p.cols[i] = HashCol{static_cast<const uint8_t*>(c.data), c.null_mask, c.offsets, static_cast<int16_t>(t),
                           static_cast<int16_t>(kind2), elem_size(t)};
     }
+    // whole chunks of fixed-width keys: the streaming kernel; the kernels below take what is left (tail rows, STRING keys)
+    {
+      int64_t done = 0;
+      const int rcs = launch_hash_stream(kind, p, num_rows, stream, &done);
+      if (rcs != SRJ_OK) return rcs;
+      if (done == num_rows) continue;
+      if (done > 0) {   // done is a multiple of 2048 rows: element, mask-word and output pointers simply advance
+        for (int i = 0; i < p.ncols; ++i) {
+          p.cols[i].data += done * p.cols[i].size;
+          if (p.cols[i].mask) p.cols[i].mask += done / 32;
+        }
+        p.n   = num_rows - done;
+        p.out = static_cast<uint8_t*>(out) + done * (kind == SRJ_HASH_XXHASH64 ? 8 : 4);
+      }
+    }
+    const unsigned grid = static_cast<unsigned>((p.n + per_block - 1) / per_block);
     bool plain = SRJ_KNOB("SRJ_HASH_GENERAL", 0) == 0;
     for (int i = 0; i < p.ncols; ++i) plain = plain && p.cols[i].kind != 0;
     if (plain) {

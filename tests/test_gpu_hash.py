@@ -75,3 +75,36 @@ def test_unsupported_and_default_seeds():
     assert np.array_equal(S.Hash.xxhash64([i]).data.cpu().numpy(), S.Hash.xxhash64(42, [i]).data.cpu().numpy())
     assert np.array_equal(S.Hash.murmurHash32([i]).data.cpu().numpy(), S.Hash.murmurHash32(0, [i]).data.cpu().numpy())
     assert S.Hash.getMaxStackDepth() == 8
+
+
+@pytest.mark.parametrize("nrows", [8192 * 3 + 777, 8192 * 2])
+@pytest.mark.parametrize("name", ["int32_int64", "all_fixed", "floats_decimals", "no_masks"])
+def test_streaming_hash_kernel_matches_oracle(name, nrows):
+    """Tables large enough for row_hash_stream_kernel (whole 2048-row chunks staged by TMA) + the tail rows on the
+    per-thread kernels; every fixed-width key type, with and without null masks."""
+    import gpu_util as G
+    import numpy as np
+    import srj_b200 as S
+    from oracle import oracle as O
+    from util import random_table
+    G.require_cuda()
+    schemas = {
+        "int32_int64": [O.INT32, O.INT64],
+        "all_fixed": [O.BOOL8, O.INT8, O.INT16, O.INT32, O.INT64, O.FLOAT32, O.FLOAT64, O.TIMESTAMP_DAYS, O.TIMESTAMP_MICROSECONDS],
+        "floats_decimals": [O.FLOAT64, O.DECIMAL32, O.DECIMAL64, O.DECIMAL128, O.FLOAT32, O.UINT32, O.UINT64],
+        "no_masks": [O.INT64, O.INT32, O.INT16],
+    }
+    types = schemas[name]
+    cols = random_table(types, nrows, seed=nrows % 97 + len(types), null_frac=0.0 if name == "no_masks" else 0.2)
+    for c in cols:
+        if c.type_id in (O.FLOAT32, O.FLOAT64):
+            v = c.data.view(np.float32 if c.type_id == O.FLOAT32 else np.float64)
+            v[::5] = np.nan
+            v[1::5] = -0.0
+    dk = [G.to_device(c) for c in cols]
+    assert np.array_equal(S.Hash.xxhash64(42, dk).data.cpu().numpy().view(np.int64), O.xxhash64(cols, 42))
+    assert np.array_equal(S.Hash.murmurHash32(42, dk).data.cpu().numpy().view(np.int32), O.murmur_hash3_32(cols, 42))
+    hive_ok = [c for c in cols if c.type_id not in (O.DECIMAL32, O.DECIMAL64, O.DECIMAL128, O.UINT32, O.UINT64)]
+    if hive_ok:
+        dh = [G.to_device(c) for c in hive_ok]
+        assert np.array_equal(S.Hash.hiveHash(dh).data.cpu().numpy().view(np.int32), O.hive_hash(hive_ok))
