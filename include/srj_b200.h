@@ -225,16 +225,39 @@ SRJ_API int srj_shard_rebase_offsets(void* gathered, int64_t slab_bytes, const i
                                      const int64_t* d_totals, int64_t rows_per_shard, int32_t num_columns,
                                      int32_t num_string_columns, int32_t world, void* stream);
 
-/* ---- host-buffer convenience (end-to-end path: H2D + convert + D2H, pipelined in chunks) ------- */
+/* ---- host-buffer entry points (end-to-end path: H2D + convert + D2H inside the call) ---------------------- */
 /*
- * Fixed-width-only schemas.  `h_rows` is num_rows * fixed_row_size bytes of HOST memory (pinned for
- * full PCIe speed); h_cols[i].data / null_mask are HOST buffers to fill.  Rows are streamed through
- * the device in chunks of `chunk_rows` (0 = library default) on internal streams so that the H2D
- * copy, the conversion kernel and the D2H copies of consecutive chunks overlap.  Synchronizes.
+ * What a caller holding HOST buffers uses (the plugin's row<->columnar transitions hand over host memory: the
+ * reference's consumers copy to the device, call convertFromRows / convertToRows, copy back).  Device staging
+ * buffers and streams live in a small per-plan pool and are reused by later calls (no cudaMalloc per call); calls are
+ * re-entrant (concurrent calls take different pool entries) and synchronize before returning.  Pinned host buffers
+ * give full PCIe speed.  Two calls in flight on two threads overlap one's H2D with the other's D2H (full duplex).
+ *
+ * srj_host_alloc_fn: the library calls it when an output buffer's size is known only during the call; it returns HOST
+ * memory of `bytes` bytes (JNI shim: HostMemoryBuffer.allocate) or NULL on failure (-> SRJ_ENOMEM).
+ *   from_rows: index = schema column of a STRING column -> its chars buffer
+ *   to_rows  : index = 2 * batch -> int32 offsets[row_count + 1] of the batch, 2 * batch + 1 -> its row bytes
  */
-SRJ_API int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int64_t num_rows,
-                                       const srj_column* h_cols, int64_t* h_null_counts,
-                                       int64_t chunk_rows);
+typedef void* (*srj_host_alloc_fn)(void* ctx, int32_t index, int64_t bytes);
+
+/*
+ * Rows -> columns.  h_rows / h_row_offsets are the LIST's children in host memory (h_row_offsets may be NULL for a
+ * fixed-width-only schema: rows at stride fixed_row_size); rows_bytes = size of h_rows.  h_cols[i].data / null_mask /
+ * offsets are HOST buffers to fill (null_mask may be NULL to skip it); a STRING column's data pointer is an OUTPUT:
+ * obtained from `alloc` and stored into h_cols[i].data.  Fixed-width-only schemas are streamed through the device in
+ * chunks of `chunk_rows` rows (0 = library default) so that H2D, kernel and D2H of consecutive chunks overlap.
+ */
+SRJ_API int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, const int32_t* h_row_offsets,
+                                       int64_t rows_bytes, int64_t num_rows, srj_column* h_cols, int64_t* h_null_counts,
+                                       int64_t chunk_rows, srj_host_alloc_fn alloc, void* alloc_ctx);
+/*
+ * Columns -> rows.  h_cols are HOST columns; batches[] receives the <= 2 GiB batch cut (build_batches, RC:1466-1557),
+ * h_batch_offsets[b] / h_batch_data[b] the host buffers obtained from `alloc` for each batch.
+ */
+SRJ_API int srj_convert_to_rows_host(const srj_plan* plan, const srj_column* h_cols, int64_t num_rows,
+                                     srj_row_batch* batches, int32_t max_batches, int32_t* num_batches,
+                                     int32_t** h_batch_offsets, uint8_t** h_batch_data, srj_host_alloc_fn alloc,
+                                     void* alloc_ctx);
 
 #ifdef __cplusplus
 }

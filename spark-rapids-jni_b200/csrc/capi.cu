@@ -323,6 +323,11 @@ void srj_plan_destroy(srj_plan* plan)
 {
   if (!plan) return;
   if (plan->d_blob) cudaFree(plan->d_blob);
+  for (auto& ar : plan->host_pool.a) {
+    for (auto& s : ar.st) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (auto& d : ar.d_buf) if (d) cudaFree(d);
+    if (ar.h_pin) cudaFreeHost(ar.h_pin);
+  }
   for (auto& sl : plan->ring.slots) {
     if (sl.used && sl.ev) cudaEventSynchronize(sl.ev);
     if (sl.d_buf) cudaFree(sl.d_buf);
@@ -647,96 +652,6 @@ int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows,
   SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("hive_hash: bad argument"); return SRJ_EINVAL; }
   return launch_hash(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
-}
-
-// ---------------------------------------------------------------------------------------------------
-// host-buffer end-to-end path (fixed-width schemas): chunked H2D -> convert -> D2H on 3 streams
-// ---------------------------------------------------------------------------------------------------
-int srj_convert_from_rows_host(const srj_plan* plan, const uint8_t* h_rows, int64_t num_rows, const srj_column* h_cols,
-                               int64_t* h_null_counts, int64_t chunk_rows)
-{
-  SRJ_API_RANGE();
-  int rc = check_cols(plan, h_cols, num_rows, "convert_from_rows_host");
-  if (rc != SRJ_OK) return rc;
-  if (plan->num_string_columns > 0) { set_error("convert_from_rows_host: fixed-width schemas only"); return SRJ_EUNSUPPORTED; }
-  const int nc = plan->num_columns;
-  if (h_null_counts) std::fill(h_null_counts, h_null_counts + nc, 0);
-  if (num_rows == 0) return SRJ_OK;
-  const int64_t S = plan->fixed_row_size;
-  if (chunk_rows <= 0) {
-    // Per chunk there are 2 copies per column (data + mask) of fixed cost, and the first H2D / last D2H of the
-    // pipeline are not overlapped: ~1/12 of the input, between 32 MB and 1 GB of rows (measured on C2: 64 MB
-    // chunks 153 M rows/s, 256 MB 217 M, 1 GB 238 M).
-    const int e       = SRJ_KNOB("SRJ_HOST_CHUNK_MB", 0);  // tuning knob (development builds)
-    int64_t cbytes    = std::min<int64_t>(1ll << 30, std::max<int64_t>(32ll << 20, num_rows * S / 12));
-    if (e) cbytes = static_cast<int64_t>(std::max(1, e)) << 20;
-    chunk_rows        = std::max<int64_t>(32 * 1024, cbytes / S);
-  }
-  const int64_t T = plan->tiling.tile_rows >= 32 ? plan->tiling.tile_rows : 32;
-  chunk_rows      = (chunk_rows + T - 1) / T * T;
-  chunk_rows      = std::min<int64_t>(chunk_rows, (num_rows + T - 1) / T * T);
-  constexpr int kSlots = 3;
-  cudaStream_t st[kSlots] = {};
-  uint8_t* d_rows[kSlots] = {};
-  uint8_t* d_cols[kSlots] = {};
-  void** d_tab[kSlots]    = {};
-  int64_t* d_nulls        = nullptr;
-  size_t col_bytes = 0;  // per slot: all column chunks + masks, 256-byte aligned pieces
-  std::vector<size_t> off_data(nc), off_mask(nc);
-  for (int c = 0; c < nc; ++c) {
-    off_data[c] = col_bytes;
-    col_bytes += (static_cast<size_t>(chunk_rows) * plan->col_size[c] + 255) & ~size_t{255};
-    off_mask[c] = col_bytes;
-    col_bytes += (static_cast<size_t>(chunk_rows) / 8 + 255) & ~size_t{255};
-  }
-  const size_t nent = plan->fr_entries.size();
-  auto cleanup = [&]() {
-    for (int s = 0; s < kSlots; ++s) {
-      if (st[s]) cudaStreamSynchronize(st[s]);
-      if (d_rows[s]) cudaFree(d_rows[s]);
-      if (d_cols[s]) cudaFree(d_cols[s]);
-      if (d_tab[s]) cudaFree(d_tab[s]);
-      if (st[s]) cudaStreamDestroy(st[s]);
-    }
-    if (d_nulls) cudaFree(d_nulls);
-  };
-#define SRJ_TRY_CLEAN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
-  SRJ_TRY_CLEAN(cudaMalloc(&d_nulls, sizeof(int64_t) * nc));
-  SRJ_TRY_CLEAN(cudaMemset(d_nulls, 0, sizeof(int64_t) * nc));
-  const int nslots = static_cast<int>(std::min<int64_t>(kSlots, (num_rows + chunk_rows - 1) / chunk_rows));
-  for (int s = 0; s < nslots; ++s) {
-    SRJ_TRY_CLEAN(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-    SRJ_TRY_CLEAN(cudaMalloc(&d_rows[s], static_cast<size_t>(chunk_rows) * S));
-    SRJ_TRY_CLEAN(cudaMalloc(&d_cols[s], col_bytes));
-    SRJ_TRY_CLEAN(cudaMalloc(&d_tab[s], sizeof(void*) * (nent + nc)));
-    std::vector<void*> tab(nent + nc);
-    for (size_t e = 0; e < nent; ++e) tab[e] = d_cols[s] + off_data[plan->fr_entries[e].column];
-    for (int c = 0; c < nc; ++c) tab[nent + c] = d_cols[s] + off_mask[c];
-    SRJ_TRY_CLEAN(cudaMemcpy(d_tab[s], tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice));
-  }
-  // null counts accumulate on the device across chunks: launch_from_rows only adds
-  int64_t k = 0;
-  for (int64_t r0 = 0; r0 < num_rows; r0 += chunk_rows, ++k) {
-    const int s      = static_cast<int>(k % nslots);
-    const int64_t n  = std::min(chunk_rows, num_rows - r0);
-    SRJ_TRY_CLEAN(cudaMemcpyAsync(d_rows[s], h_rows + r0 * S, static_cast<size_t>(n) * S, cudaMemcpyHostToDevice, st[s]));
-    // the kernel sees a chunk-local table whose last mask word is zero-tailed; chunk starts are multiples of 32
-    rc = launch_from_rows(plan, d_rows[s], nullptr, n * S, n, d_tab[s], reinterpret_cast<uint32_t* const*>(d_tab[s] + nent),
-                          d_nulls, nullptr, nullptr, st[s]);
-    if (rc != SRJ_OK) { cleanup(); return rc; }
-    for (int c = 0; c < nc; ++c) {
-      SRJ_TRY_CLEAN(cudaMemcpyAsync(static_cast<uint8_t*>(h_cols[c].data) + r0 * plan->col_size[c], d_cols[s] + off_data[c],
-                                    static_cast<size_t>(n) * plan->col_size[c], cudaMemcpyDeviceToHost, st[s]));
-      if (h_cols[c].null_mask)
-        SRJ_TRY_CLEAN(cudaMemcpyAsync(h_cols[c].null_mask + r0 / 32, d_cols[s] + off_mask[c], static_cast<size_t>((n + 31) / 32) * 4,
-                                      cudaMemcpyDeviceToHost, st[s]));
-    }
-  }
-  for (int s = 0; s < nslots; ++s) SRJ_TRY_CLEAN(cudaStreamSynchronize(st[s]));
-  if (h_null_counts) SRJ_TRY_CLEAN(cudaMemcpy(h_null_counts, d_nulls, sizeof(int64_t) * nc, cudaMemcpyDeviceToHost));
-#undef SRJ_TRY_CLEAN
-  cleanup();
-  return SRJ_OK;
 }
 
 }  // extern "C"

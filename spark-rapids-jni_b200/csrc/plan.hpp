@@ -72,6 +72,20 @@ struct TableRing {
   unsigned next = 0;
 };
 
+// Device staging of the host-buffer entry points (srj_convert_*_host): grow-only buffers + streams, pooled per plan.
+struct HostArena {
+  std::mutex busy;
+  cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+  void* d_buf[4]     = {nullptr, nullptr, nullptr, nullptr};  // rows | outputs / inputs | misc (offsets, workspace, counters) | chars
+  size_t d_cap[4]    = {0, 0, 0, 0};
+  void* h_pin        = nullptr;  // pinned host scratch (counters)
+  size_t h_cap       = 0;
+};
+struct HostArenaPool {
+  static constexpr int kArenas = 4;
+  HostArena a[kArenas];
+};
+
 }  // namespace srj
 
 struct srj_plan {
@@ -104,4 +118,5 @@ struct srj_plan {
   const int32_t* d_tr_chunk_off;  // [tr_entries] staging byte offset per row unit (to_rows2)
 
   mutable srj::TableRing ring;
+  mutable srj::HostArenaPool host_pool;
 };

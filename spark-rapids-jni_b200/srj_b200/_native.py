@@ -62,9 +62,14 @@ SYMBOLS = {
     "srj_hive_hash": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "srj_shard_rebase_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]),
-    "srj_convert_from_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_void_p,
-                                             C.c_int64]),
+    "srj_convert_from_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(SrjColumn),
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "srj_convert_to_rows_host": (C.c_int, [C.c_void_p, C.POINTER(SrjColumn), C.c_int64, C.POINTER(SrjRowBatch), C.c_int32,
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p,
+                                           C.c_void_p]),
 }
+
+HOST_ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int32, C.c_int64)     # srj_host_alloc_fn
 
 _lib = None
 
