@@ -66,6 +66,8 @@ typedef enum srj_type_id {
  * outputs; for outputs the caller allocates every buffer and the library fills it.
  *   fixed-width column : data = size * size_of(type) bytes
  *   STRING column      : data = chars, offsets = int32[size + 1]   (RC:1919-1923, 2421-2428)
+ *   LIST column        : offsets = int32[size + 1], children[0] = the element column     (hash entry points only)
+ *   STRUCT column      : children[0 .. num_children) = the fields, each `size` rows        (hash entry points only)
  * Sliced views (offset != 0) are not supported, as in the reference (RC:1809-1811).
  */
 typedef struct srj_column {
@@ -74,7 +76,10 @@ typedef struct srj_column {
   int64_t size;        /* rows                                                */
   void* data;          /* device                                              */
   uint32_t* null_mask; /* device, ceil(size/32) words, or NULL (= all valid)  */
-  int32_t* offsets;    /* device, STRING only                                 */
+  int32_t* offsets;    /* device, STRING / LIST                               */
+  const struct srj_column* children; /* HOST array of child descriptors (LIST / STRUCT), else NULL */
+  int32_t num_children;
+  int32_t reserved;
 } srj_column;
 
 /* One output batch of convert_to_rows = one LIST<INT8> column of <= INT32_MAX bytes (RC:174-190). */
@@ -201,9 +206,13 @@ SRJ_API int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* r
 
 /* ---- row hashes: Hash.xxhash64 / murmurHash32 / hiveHash, hash/hash.hpp:40-74 ------------------ */
 #define SRJ_DEFAULT_XXHASH64_SEED 42 /* hash/hash.hpp:27 */
-#define SRJ_MAX_STACK_DEPTH 8        /* hash/hash.hpp:28 (nested types; not on this path yet) */
+#define SRJ_MAX_STACK_DEPTH 8        /* hash/hash.hpp:28: nesting limit of LIST / STRUCT keys */
 SRJ_API int srj_get_max_stack_depth(void); /* Hash.getMaxStackDepth, HashJni.cpp:26-30 */
-/* out has no null mask (xxhash64.cu:556-562).  num_columns == 0 or num_rows == 0 is a no-op. */
+/* out has no null mask (xxhash64.cu:556-562).  num_columns == 0 or num_rows == 0 is a no-op.
+ * LIST / STRUCT keys are hashed like the reference (xxhash64.cu:446-506, murmur_hash.cu:119-144,
+ * hive_hash.cu:363-433): xxhash64 / murmur chain the leaf values depth first (nulls keep the accumulator; murmur
+ * rejects LIST<STRUCT>, murmur_hash.cu:167-187), hive folds 31 * h + x over the fields of a struct and over the
+ * elements of a list.  Nesting beyond SRJ_MAX_STACK_DEPTH returns SRJ_EINVAL (CudfException). */
 SRJ_API int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed,
                          int64_t* out, void* stream);
 SRJ_API int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num_rows,

@@ -62,14 +62,17 @@ class HCol:
     type_id: int
     data: Optional[np.ndarray]            # fixed width: typed or uint8 array; STRING: uint8 chars
     mask: Optional[np.ndarray] = None     # uint32 words, bit i%32 of word i/32, 1 = valid
-    offsets: Optional[np.ndarray] = None  # STRING: int32[size+1]
+    offsets: Optional[np.ndarray] = None  # STRING / LIST: int32[size+1]
     scale: int = 0
     size: int = -1
+    children: Optional[list] = None       # LIST: [element column]; STRUCT: the fields
 
     def __post_init__(self):
         if self.size < 0:
-            if self.type_id == STRING:
+            if self.type_id in (STRING, LIST):
                 self.size = len(self.offsets) - 1
+            elif self.type_id == STRUCT:
+                self.size = self.children[0].size if self.children else 0
             else:
                 self.size = (self.data.nbytes // size_of(self.type_id)) if self.data is not None else 0
 
@@ -266,6 +269,82 @@ def hive_hash(cols: Sequence[HCol]) -> np.ndarray:
     arr, keep = _carr(cols)
     _check(lib().orc_hive_hash(arr, len(cols), C.c_int64(n), out.ctypes.data_as(C.c_void_p)), "hive_hash")
     return out[:n]
+
+
+# ---- nested keys (LIST / STRUCT): the tree walk of xxhash64.cu:446-506 / murmur_hash.cu:119-144 / hive_hash.cu:363-433,
+# restated recursively over small tables; leaves go through the C element hashers above -------------------------------
+def list_col(offsets, child: HCol, valid=None) -> HCol:
+    offsets = np.asarray(offsets, dtype=np.int32)
+    mask = None if valid is None or all(valid) else pack_mask(np.asarray(valid, dtype=bool))
+    return HCol(LIST, None, mask, offsets, 0, len(offsets) - 1, [child])
+
+
+def struct_col(*fields: HCol, valid=None) -> HCol:
+    mask = None if valid is None or all(valid) else pack_mask(np.asarray(valid, dtype=bool))
+    return HCol(STRUCT, None, mask, None, 0, fields[0].size if fields else 0, list(fields))
+
+
+def _leaf_c(c: HCol):
+    arr, keep = _carr([c])
+    return arr, keep
+
+
+def nested_hash(kind: str, cols: Sequence[HCol], seed: int = 0) -> np.ndarray:
+    """kind in {"xxhash64", "murmur3", "hive"}; cols may hold LIST / STRUCT columns."""
+    L = lib()
+    L.orc_xx_elem.restype = C.c_uint64
+    L.orc_xx_elem.argtypes = [C.c_void_p, C.c_int64, C.c_uint64]
+    L.orc_mm_elem.restype = C.c_uint32
+    L.orc_mm_elem.argtypes = [C.c_void_p, C.c_int64, C.c_uint32]
+    L.orc_hive_leaf.restype = C.c_int32
+    L.orc_hive_leaf.argtypes = [C.c_void_p, C.c_int64]
+    cache = {}
+
+    def cptr(c):
+        if id(c) not in cache:
+            cache[id(c)] = _leaf_c(c)
+        return C.cast(cache[id(c)][0], C.c_void_p)
+
+    def chain(c, lo, hi, h):                       # xxhash64 / murmur3: depth-first over the leaves of [lo, hi)
+        if c.type_id == LIST:
+            return chain(c.children[0], int(c.offsets[lo]), int(c.offsets[hi]), h)
+        if c.type_id == STRUCT:
+            for i in range(lo, hi):
+                for f in c.children:
+                    h = chain(f, i, i + 1, h)
+            return h
+        for i in range(lo, hi):
+            h = L.orc_xx_elem(cptr(c), i, h) if kind == "xxhash64" else L.orc_mm_elem(cptr(c), i, h)
+        return h
+
+    def hive(c, i):                                # hive: structural 31-fold
+        if c.type_id == LIST:
+            h = 0
+            for e in range(int(c.offsets[i]), int(c.offsets[i + 1])):
+                h = (31 * h + hive(c.children[0], e)) & 0xFFFFFFFF
+            return h
+        if c.type_id == STRUCT:
+            h = 0
+            for f in c.children:
+                h = (31 * h + hive(f, i)) & 0xFFFFFFFF
+            return h
+        return L.orc_hive_leaf(cptr(c), i) & 0xFFFFFFFF
+    n = cols[0].size if cols else 0
+    if kind == "xxhash64":
+        out = np.zeros(n, np.uint64)
+        for r in range(n):
+            h = seed & (2**64 - 1)
+            for c in cols:
+                h = chain(c, r, r + 1, h)
+            out[r] = h
+        return out.view(np.int64)
+    out = np.zeros(n, np.uint32)
+    for r in range(n):
+        h = (seed & 0xFFFFFFFF) if kind == "murmur3" else 0
+        for c in cols:
+            h = chain(c, r, r + 1, h) if kind == "murmur3" else (31 * h + hive(c, r)) & 0xFFFFFFFF
+        out[r] = h
+    return out.view(np.int32)
 
 
 def xxh64_bytes(b: bytes, seed: int) -> int:

@@ -522,6 +522,29 @@ int orc_hive_hash(const orc_col* cols, int32_t ncols, int64_t nrows, int32_t* ou
   return rc;
 }
 
+/* ---- single-element entry points for the nested-type restatement in oracle.py (LIST / STRUCT keys: the tree walk is
+ * done in Python over small tables; xxhash64.cu:446-506, murmur_hash.cu:119-144, hive_hash.cu:363-433) ------------- */
+uint64_t orc_xx_elem(const orc_col* c, int64_t r, uint64_t h)   /* a null element keeps the accumulator */
+{
+  if (!is_valid(c->null_mask, r)) return h;
+  uint8_t buf[16]; const uint8_t* ext;
+  int n = elem_bytes(c, r, 1, buf, &ext);
+  return n < 0 ? h : orc_xxh64_bytes(ext ? ext : buf, n, h);
+}
+uint32_t orc_mm_elem(const orc_col* c, int64_t r, uint32_t h)
+{
+  if (!is_valid(c->null_mask, r)) return h;
+  uint8_t buf[16]; const uint8_t* ext;
+  int n = elem_bytes(c, r, 0, buf, &ext);
+  return n < 0 ? h : orc_murmur3_bytes(ext ? ext : buf, n, h);
+}
+int32_t orc_hive_leaf(const orc_col* c, int64_t r)              /* a null element hashes to 0 */
+{
+  int32_t x = 0;
+  if (is_valid(c->null_mask, r)) hive_elem(c, r, &x);
+  return x;
+}
+
 /* ------------------------------------------------------------------------------------------
  * CPU baseline ("Spark InternalRow -> ColumnarBatch on host cores"):
  * the same per-row / per-field loops as above, one contiguous row range per thread.  Used only

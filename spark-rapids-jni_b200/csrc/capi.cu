@@ -632,11 +632,25 @@ int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, con
 // ---------------------------------------------------------------------------------------------------
 int srj_get_max_stack_depth(void) { return SRJ_MAX_STACK_DEPTH; }
 
+// Tables with LIST / STRUCT keys: the column trees are uploaded through a process-wide staging ring (there is no plan
+// on the hash entry points) and hashed by hash_nested.cu.
+static int hash_any(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out, cudaStream_t stream)
+{
+  if (!hash_has_nested(cols, num_columns)) return launch_hash(kind, cols, num_columns, num_rows, seed, out, stream);
+  if (num_columns == 0 || num_rows == 0) return SRJ_OK;
+  static srj_plan staging{};              // only its pointer-table ring is used
+  constexpr size_t kBytes = 256 * 1024;   // ~5000 tree nodes
+  TableLease sc(&staging, stream);
+  int rc = sc.acquire(kBytes);
+  if (rc != SRJ_OK) return rc;
+  return launch_hash_nested(kind, cols, num_columns, num_rows, seed, out, sc.dev(), sc.host(), kBytes, stream);
+}
+
 int srj_xxhash64(const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, int64_t* out, void* stream)
 {
   SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("xxhash64: bad argument"); return SRJ_EINVAL; }
-  return launch_hash(SRJ_HASH_XXHASH64, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
+  return hash_any(SRJ_HASH_XXHASH64, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
 }
 
 int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num_rows, uint32_t seed, int32_t* out,
@@ -644,14 +658,14 @@ int srj_murmur_hash3_32(const srj_column* cols, int32_t num_columns, int64_t num
 {
   SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("murmur_hash3_32: bad argument"); return SRJ_EINVAL; }
-  return launch_hash(SRJ_HASH_MURMUR3_32, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
+  return hash_any(SRJ_HASH_MURMUR3_32, cols, num_columns, num_rows, seed, out, static_cast<cudaStream_t>(stream));
 }
 
 int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* out, void* stream)
 {
   SRJ_API_RANGE();
   if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && !cols) || (num_rows > 0 && !out)) { set_error("hive_hash: bad argument"); return SRJ_EINVAL; }
-  return launch_hash(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
+  return hash_any(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

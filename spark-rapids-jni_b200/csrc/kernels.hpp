@@ -59,6 +59,11 @@ int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, cons
                        int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes,
                        int32_t* d_fail_flag, cudaStream_t stream, const void* const* h_col_data, int* launched);
 
+// hash_nested.cu: tables with LIST / STRUCT key columns
+bool hash_has_nested(const srj_column* cols, int32_t num_columns);
+int launch_hash_nested(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out,
+                       void* d_scratch, void* h_pinned, size_t scratch_bytes, cudaStream_t stream);
+
 // hash.cu
 int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out,
                 cudaStream_t stream);

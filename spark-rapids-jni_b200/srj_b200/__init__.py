@@ -82,14 +82,26 @@ class ColumnView:
 
     def __init__(self, dtype, size: int, data: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
                  offsets: Optional[torch.Tensor] = None, child: Optional["ColumnView"] = None,
-                 null_count: Optional[int] = None):
+                 null_count: Optional[int] = None, children: Optional[Sequence["ColumnView"]] = None):
         self.dtype = _as_dtype(dtype)
         self.size = int(size)
         self.data = data
         self.mask = mask
         self.offsets = offsets
-        self.child = child
+        self.child = child                 # LIST: the element column
+        self.children = list(children) if children is not None else None   # STRUCT: the fields
         self._null_count = null_count
+
+    @staticmethod
+    def makeStructView(*fields: "ColumnView", mask: Optional[torch.Tensor] = None) -> "ColumnView":
+        """ai.rapids.cudf.ColumnView.makeStructView: a STRUCT view over existing columns (all the same row count)."""
+        n = fields[0].size if fields else 0
+        return ColumnView(DType.STRUCT, n, None, mask, None, None, None, children=fields)
+
+    @staticmethod
+    def makeListView(offsets: torch.Tensor, child: "ColumnView", mask: Optional[torch.Tensor] = None) -> "ColumnView":
+        """A LIST view: int32 offsets[rows + 1] into `child`."""
+        return ColumnView(DType.LIST, offsets.numel() - 1, None, mask, offsets, child)
 
     # --- ai.rapids.cudf.ColumnView-ish accessors
     def getRowCount(self) -> int:
@@ -151,6 +163,18 @@ class ColumnView:
         c.data = self.data.data_ptr() if self.data is not None and self.data.numel() else None
         c.null_mask = self.mask.data_ptr() if self.mask is not None else None
         c.offsets = self.offsets.data_ptr() if self.offsets is not None else None
+        kids = None
+        if self.dtype.type_id == DType.LIST and self.child is not None:
+            kids = [self.child]
+        elif self.dtype.type_id == DType.STRUCT and self.children:
+            kids = self.children
+        if kids:
+            arr = (N.SrjColumn * len(kids))()
+            for i, k in enumerate(kids):
+                arr[i] = k._c()
+            c.children = arr
+            c.num_children = len(kids)
+            self._c_keep = arr           # the child descriptors must outlive the call (the view does)
         return c
 
 
@@ -405,7 +429,16 @@ class Hash:
             assert c is not None, "Column vectors passed may not be null"
             assert c.size == n, "Row count mismatch, all columns must be the same size"   # Hash.java:51-53
             assert not (17 <= c.dtype.type_id <= 21), "Unsupported column type Duration"  # Hash.java:54
-        dev = cols[0].data.device if cols[0].data is not None else cols[0].offsets.device
+        def device_of(c):
+            for t in (c.data, c.offsets, c.mask):
+                if t is not None:
+                    return t.device
+            for k in ([c.child] if c.child is not None else []) + list(c.children or []):
+                d = device_of(k)
+                if d is not None:
+                    return d
+            return None
+        dev = next((d for d in map(device_of, cols) if d is not None), torch.device("cuda", torch.cuda.current_device()))
         return cols, n, dev
 
     @staticmethod

@@ -16,8 +16,12 @@ HASH_NONE, HASH_XXHASH64, HASH_MURMUR3_32, HASH_HIVE = 0, 1, 2, 3
 
 
 class SrjColumn(C.Structure):
-    _fields_ = [("type_id", C.c_int32), ("scale", C.c_int32), ("size", C.c_int64), ("data", C.c_void_p),
-                ("null_mask", C.c_void_p), ("offsets", C.c_void_p)]
+    pass
+
+
+SrjColumn._fields_ = [("type_id", C.c_int32), ("scale", C.c_int32), ("size", C.c_int64), ("data", C.c_void_p),
+                      ("null_mask", C.c_void_p), ("offsets", C.c_void_p), ("children", C.POINTER(SrjColumn)),
+                      ("num_children", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SrjRowBatch(C.Structure):

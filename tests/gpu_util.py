@@ -14,6 +14,13 @@ def require_cuda():
 
 
 def to_device(c: O.HCol) -> S.ColumnVector:
+    if c.type_id in (O.LIST, O.STRUCT):
+        mask = torch.from_numpy(c.mask.view(np.int32).copy()).cuda() if c.mask is not None else None
+        kids = [to_device(k) for k in (c.children or [])]
+        if c.type_id == O.LIST:
+            offs = torch.from_numpy(np.ascontiguousarray(c.offsets, dtype=np.int32)).cuda()
+            return S.ColumnVector(S.DType.LIST, c.size, None, mask, offs, kids[0])
+        return S.ColumnVector(S.DType.STRUCT, c.size, None, mask, None, None, None, children=kids)
     return S.ColumnVector.from_numpy(c.type_id, c.data if c.data is not None else np.zeros(0, np.uint8), c.mask,
                                      c.offsets, c.scale, c.size)
 
