@@ -33,7 +33,16 @@ import numpy as np  # noqa: E402
 
 # cudf type ids used by the workloads
 INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US, STRING, DEC32, DEC128 = 1, 2, 3, 4, 9, 10, 11, 15, 23, 25, 27
-SIZE = {INT8: 1, INT16: 2, INT32: 4, INT64: 8, FLOAT32: 4, FLOAT64: 8, BOOL8: 1, TS_US: 8, DEC32: 4, DEC128: 16}
+UINT8, UINT16, UINT64 = 5, 6, 8
+SIZE = {INT8: 1, INT16: 2, INT32: 4, INT64: 8, FLOAT32: 4, FLOAT64: 8, BOOL8: 1, TS_US: 8, DEC32: 4, DEC128: 16,
+        UINT8: 1, UINT16: 2, UINT64: 8}
+# the reference's own nvbench shapes (src/main/cpp/benchmarks/row_conversion.cpp:27-147)
+NVB_CYCLE = [INT8, INT32, INT16, INT64, INT32, BOOL8, UINT16, UINT8, UINT64]
+NVB_CYCLE_STR = [INT8, INT32, INT16, INT64, INT32, BOOL8, STRING, UINT16, UINT8, UINT64]
+
+
+def cycle(types, n):
+    return [types[i % len(types)] for i in range(n)]
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 100M rows x 32 fixed-width cols convert_from_rows, 1xB200
@@ -46,6 +55,15 @@ WORKLOADS = {
     # BASELINE.json configs[2]: 100M rows x 256 mixed cols (int32/int64/decimal128/utf8, 20% null), to+from rows.
     # ~390 GB of rows cannot be resident: a step streams 100M rows as `batches` x `batch_rows` conversions over a
     # resident pool of distinct <=2 GiB batches (each batch is what one LIST<INT8> column / one JNI call carries).
+    # the reference's nvbench shapes, timed through the public API like nvbench's exec_tag::sync (allocation and the
+    # size read-backs included): "Fixed Width Only" 212 columns, "Fixed or Variable Width" 155 columns +- STRING
+    "nvbench_fixed": dict(name="nvbench 'Fixed Width Only': 212 cols cycling [INT8,INT32,INT16,INT64,INT32,BOOL8,UINT16,UINT8,UINT64] "
+                               "(benchmarks/row_conversion.cpp:27-64)", types=cycle(NVB_CYCLE, 212), rows=1 << 20, null_frac=0.0, nvbench=True),
+    "nvbench_nostr": dict(name="nvbench 'Fixed or Variable Width', no strings: 155 cols (benchmarks/row_conversion.cpp:66-147)",
+                          types=cycle(NVB_CYCLE, 155), rows=1 << 20, null_frac=0.0, nvbench=True),
+    "nvbench_var": dict(name="nvbench 'Fixed or Variable Width', include strings: 155 cols cycling [...,BOOL8,STRING,UINT16,...], "
+                             "strings ~N(16,8) in [0,32] B (benchmarks/row_conversion.cpp:66-147)",
+                        types=cycle(NVB_CYCLE_STR, 155), rows=1 << 20, null_frac=0.0, nvbench=True),
     "c3": dict(name="C3: 100M rows x 256 mixed cols ([INT32,INT64,DECIMAL128,STRING]x64, 20% nulls, strings ~N(16,8) in [0,32] B) "
                     "convert_from_rows, streamed as 200 batches of 500K rows (<=2 GiB each)",
                types=[INT32, INT64, DEC128, STRING] * 64, rows=100_000_000, null_frac=0.2, batch_rows=500_000, pool=4),
@@ -842,6 +860,54 @@ def cpu_baseline_c3(batch, types, nb, words, nthreads=None):
             "ms_per_pass": best * 1e3}
 
 
+def run_nvbench(args, wl, rank, world):
+    """The reference's nvbench shapes through the PUBLIC API (RowConversion.convertToRows / convertFromRows: output
+    allocation, batch planning and size read-backs inside the timed call, as nvbench's exec_tag::sync measures them)."""
+    import torch
+    import srj_b200 as S
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    types = wl["types"]
+    n = int(args.rows or wl["rows"])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    fixed = iter(synth_columns_gpu(torch, S, [t for t in types if t != STRING], n, wl["null_frac"], seed=11))
+    cols = [synth_strings_gpu(torch, S, n, wl["null_frac"], g) if t == STRING else next(fixed) for t in types]
+    dts = [c.dtype for c in cols]
+    tbl = S.Table(cols)
+    rows = S.RowConversion.convertToRows(tbl)
+    back = S.RowConversion.convertFromRows(rows[0], dts)
+    for a, c in zip(back.columns, cols):
+        assert torch.equal(a.data, c.data), "nvbench shape: round trip differs"
+    row_bytes = sum(r.child.size for r in rows)
+    col_bytes = sum(c.data.numel() + ((n + 31) // 32) * 4 + (4 * (n + 1) if c.offsets is not None else 0) for c in cols)
+    alg = row_bytes + 4 * (n + 1) * (STRING in types) + col_bytes
+    res = {}
+    for direction in ("to_rows", "from_rows"):
+        fn = (lambda: S.RowConversion.convertToRows(tbl)) if direction == "to_rows" else \
+             (lambda: [S.RowConversion.convertFromRows(r, dts) for r in rows])
+        for _ in range(max(3, args.warmup)):
+            fn()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        res[direction] = float(np.median(times))
+    peak, peak_src = load_peaks()
+    sec = res[args.direction]
+    print(json.dumps({"metric": "rows_per_sec_convert_" + args.direction, "value": n / sec, "unit": "rows/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": wl["name"], "rows": n, "columns": len(types), "direction": args.direction,
+                                 "timing": "host wall clock around the public API call + synchronize (allocation and read-backs included)"},
+                      "roofline": {"bound": "hbm", "achieved": round(alg / sec / 1e9, 1), "peak": peak, "unit": "GB/s",
+                                   "frac": round(alg / sec / 1e9 / peak, 4), "traffic": None, "kernel": "whole public-API call",
+                                   "peak_source": peak_src},
+                      "both_directions_ms": {k: v * 1e3 for k, v in res.items()}, "cpu_baseline": None, "e2e": None,
+                      "gpu_launches": args.steps, "clocks": None}))
+
+
 def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthreads=None):
     """Oracle's threaded row->column loop on a bounded sample of the same rows (host cores)."""
     from oracle import oracle as O
@@ -954,6 +1020,9 @@ def main():
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
+    elif wl.get("nvbench"):
+        if rank == 0:
+            run_nvbench(args, wl, rank, world)
     elif args.workload == "c3":
         run_c3(args, wl, rank, world)
     else:

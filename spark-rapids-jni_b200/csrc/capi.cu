@@ -361,13 +361,6 @@ int64_t srj_to_rows_workspace_bytes(const srj_plan* plan, int64_t num_rows)
   return (num_rows + nchunks) * 8;
 }
 
-static int read_u64(const uint64_t* d, int64_t i, uint64_t* out, cudaStream_t s)
-{
-  SRJ_CUDA_TRY(cudaMemcpyAsync(out, d + i, 8, cudaMemcpyDeviceToHost, s));
-  SRJ_CUDA_TRY(cudaStreamSynchronize(s));
-  return SRJ_OK;
-}
-
 int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64_t num_rows, void* workspace,
                              srj_row_batch* batches, int32_t max_batches, int32_t* num_batches, void* stream_)
 {
@@ -405,8 +398,12 @@ int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64
     h_off[s] = cols[plan->string_columns[s]].offsets;
     if (!h_off[s]) { set_error("to_rows: STRING column %d has no offsets", plan->string_columns[s]); return SRJ_EINVAL; }
   }
+  // pointer table of the STRING offsets + room for the batch list the device computes
+  const int cap          = std::min<int>(max_batches, 4096);
+  const size_t tab_bytes = (sizeof(void*) * nstr + 15) & ~size_t{15};
+  const size_t out_bytes = sizeof(int64_t) * (1 + 3 * static_cast<size_t>(cap));
   TableLease sc(plan, stream);
-  rc = sc.acquire(sizeof(void*) * nstr);
+  rc = sc.acquire(tab_bytes + out_bytes);
   if (rc != SRJ_OK) return rc;
   memcpy(sc.host(), h_off.data(), sizeof(void*) * nstr);
   rc = sc.upload(sizeof(void*) * nstr);
@@ -414,48 +411,22 @@ int srj_to_rows_plan_batches(const srj_plan* plan, const srj_column* cols, int64
   uint64_t* cum = static_cast<uint64_t*>(workspace);
   rc            = launch_row_sizes(plan, static_cast<const int32_t* const*>(sc.dev()), num_rows, cum, stream);
   if (rc != SRJ_OK) return rc;
-  uint64_t total = 0;
-  rc             = read_u64(cum, num_rows - 1, &total, stream);
+  // build_batches on the device, one read-back (the sync of RC:1534-1544, once instead of once per batch)
+  int64_t* d_out = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(sc.dev()) + tab_bytes);
+  int64_t* h_out = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(sc.host()) + tab_bytes);
+  rc             = launch_batch_cut(cum, num_rows, cap, d_out, stream);
   if (rc != SRJ_OK) return rc;
-  int64_t last      = 0;
-  uint64_t cum_last = 0;  // cum[last - 1]
-  while (last < num_rows) {
-    int64_t row_end;
-    if (total - cum_last < MAXB) {
-      // common case: everything left fits one batch.  (The reference's lower_bound compares
-      // cum[i] - cum[last], i.e. it ignores the first row of the batch; the guard below covers the
-      // overshoot that can cause.)
-      row_end = num_rows;
-    } else {
-      uint64_t cl = 0;
-      rc          = read_u64(cum, last, &cl, stream);
-      if (rc != SRJ_OK) return rc;
-      int64_t lo = last, hi = num_rows;  // first i with cum[i] - cum[last] >= MAXB
-      while (lo < hi) {
-        const int64_t mid = lo + (hi - lo) / 2;
-        uint64_t v        = 0;
-        rc                = read_u64(cum, mid, &v, stream);
-        if (rc != SRJ_OK) return rc;
-        if (v - cl < MAXB) lo = mid + 1; else hi = mid;
-      }
-      const int64_t bs = lo - last;
-      row_end          = (lo == num_rows) ? last + bs : last + bs / 32 * 32;
-    }
-    uint64_t cend = 0;
-    for (;;) {
-      if (row_end <= last) { set_error("to_rows: a single row exceeds 2 GiB"); return SRJ_EOVERFLOW; }
-      rc = read_u64(cum, row_end - 1, &cend, stream);
-      if (rc != SRJ_OK) return rc;
-      if (cend - cum_last <= MAXB) break;
-      const int64_t n = row_end - last;
-      row_end -= (n % 32) ? (n % 32) : 32;
-    }
-    if (*num_batches >= max_batches) { set_error("to_rows: more than %d batches", max_batches); return SRJ_EINVAL; }
-    batches[*num_batches] = srj_row_batch{last, row_end - last, static_cast<int64_t>(cend - cum_last)};
-    ++*num_batches;
-    last     = row_end;
-    cum_last = cend;
+  const size_t first = sizeof(int64_t) * (1 + 3 * static_cast<size_t>(std::min(cap, 8)));   // nearly always one batch
+  SRJ_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, first, cudaMemcpyDeviceToHost, stream));
+  SRJ_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (h_out[0] > 8) {
+    SRJ_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, sizeof(int64_t) * (1 + 3 * static_cast<size_t>(h_out[0])), cudaMemcpyDeviceToHost, stream));
+    SRJ_CUDA_TRY(cudaStreamSynchronize(stream));
   }
+  if (h_out[0] == -1) { set_error("to_rows: a single row exceeds 2 GiB"); return SRJ_EOVERFLOW; }
+  if (h_out[0] < 0) { set_error("to_rows: more than %d batches", cap); return SRJ_EINVAL; }
+  *num_batches = static_cast<int32_t>(h_out[0]);
+  for (int b = 0; b < *num_batches; ++b) batches[b] = srj_row_batch{h_out[1 + 3 * b], h_out[2 + 3 * b], h_out[3 + 3 * b]};
   return SRJ_OK;
 }
 

@@ -47,6 +47,8 @@ bool strings_fast_path(const srj_plan* plan, const int64_t* d_status);
 // to_rows.cu
 int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, int64_t num_rows,
                      uint64_t* d_cum_sizes, cudaStream_t stream);
+// batch cut on the device: d_out = int64[1 + 3 * max_batches]
+int launch_batch_cut(const uint64_t* d_cum, int64_t num_rows, int32_t max_batches, int64_t* d_out, cudaStream_t stream);
 int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
                    const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
                    int64_t row_count, const uint64_t* d_cum_sizes /* NULL for fixed */, int32_t* out_offsets,

@@ -770,6 +770,60 @@ int launch_row_sizes(const srj_plan* plan, const int32_t* const* d_str_offsets, 
   return SRJ_OK;
 }
 
+// build_batches (RC:1466-1557) on the device: one thread walks the inclusive cumulative row sizes and cuts a new batch
+// wherever the bytes would pass INT32_MAX, on a 32-row boundary (a binary search per batch); the host reads the result
+// with ONE copy (the reference does a thrust::lower_bound + D2H per batch, RC:1500-1544).
+// out[0] = number of batches (or -1: a single row exceeds 2 GiB, -2: more than max_batches), then {row_start, row_count,
+// num_bytes} triples.
+__global__ void batch_cut_kernel(const uint64_t* __restrict__ cum, int64_t n, int32_t max_batches, int64_t* __restrict__ out)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const uint64_t MAXB = INT32_MAX;  // MAX_BATCH_SIZE, RC:65
+  const uint64_t total = cum[n - 1];
+  int64_t last = 0, nb = 0;
+  uint64_t cum_last = 0;  // cum[last - 1]
+  while (last < n) {
+    int64_t row_end;
+    if (total - cum_last < MAXB) {
+      row_end = n;  // everything left fits one batch
+    } else {
+      // first i with cum[i] - cum[last] >= MAXB (the reference's lower_bound ignores the first row of the batch; the
+      // guard below covers the overshoot that can cause)
+      const uint64_t cl = cum[last];
+      int64_t lo = last, hi = n;
+      while (lo < hi) {
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (cum[mid] - cl < MAXB) lo = mid + 1; else hi = mid;
+      }
+      const int64_t bs = lo - last;
+      row_end          = (lo == n) ? last + bs : last + bs / 32 * 32;
+    }
+    uint64_t cend = 0;
+    for (;;) {
+      if (row_end <= last) { out[0] = -1; return; }
+      cend = cum[row_end - 1];
+      if (cend - cum_last <= MAXB) break;
+      const int64_t m = row_end - last;
+      row_end -= (m % 32) ? (m % 32) : 32;
+    }
+    if (nb >= max_batches) { out[0] = -2; return; }
+    out[1 + 3 * nb] = last;
+    out[2 + 3 * nb] = row_end - last;
+    out[3 + 3 * nb] = static_cast<int64_t>(cend - cum_last);
+    ++nb;
+    last     = row_end;
+    cum_last = cend;
+  }
+  out[0] = nb;
+}
+
+int launch_batch_cut(const uint64_t* d_cum, int64_t num_rows, int32_t max_batches, int64_t* d_out, cudaStream_t stream)
+{
+  batch_cut_kernel<<<1, 32, 0, stream>>>(d_cum, num_rows, max_batches, d_out);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
 static size_t to_rows_smem_bytes(const srj_plan* plan, int tile_rows, int stage_bytes, int max_str_entries, int nbuf)
 {
   const int nent = static_cast<int>(plan->tr_entries.size());
