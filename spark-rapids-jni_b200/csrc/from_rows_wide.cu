@@ -592,6 +592,7 @@ struct WideScanParams {
   const int32_t* bad_part;          // [parts]
   uint32_t* sync_words;             // {ticket, overflow}
   int32_t parts, ncols, nstr;
+  uint64_t str_bits[kWMaxCols / 64];   // bit c set: schema column c is a STRING column
 };
 
 __global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const __grid_constant__ WideScanParams q,
@@ -653,33 +654,40 @@ __global__ void __launch_bounds__(kGsThreads) wide_group_scan_kernel(const __gri
       }
     }
   }
-  // ---- the last CTA to finish publishes what phase 1 reports besides the offsets: exact null counts (sum of the
-  // per-CTA partials of from_rows_wide_kernel), zeros for the non-STRING entries of char_totals, and the status word
+  // ---- what phase 1 reports besides the offsets.  Every CTA of this grid takes a few columns: exact null counts (sum of
+  // the per-CTA partials of from_rows_wide_kernel, one thread per partial) and zeros for the non-STRING entries of
+  // char_totals; the last CTA to finish writes the status word.
+  {
+    const int ncta = gridDim.x * gridDim.y;
+    const int me   = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int col = me; col < q.ncols; col += ncta) {
+      if (q.null_counts) {
+        int64_t nn = 0;
+        for (int b = threadIdx.x; b < q.parts; b += kGsThreads) nn += q.null_part[static_cast<size_t>(b) * q.ncols + col];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nn += __shfl_down_sync(0xffffffffu, nn, o);
+        __syncthreads();
+        if (lane_id() == 0) s_warp[warp_id()] = nn;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int64_t t = 0;
+          for (int i = 0; i < kGsThreads / 32; ++i) t += s_warp[i];
+          q.null_counts[col] = t;
+        }
+      }
+      if (char_totals && threadIdx.x == 0 && !((q.str_bits[col >> 6] >> (col & 63)) & 1ull)) char_totals[col] = 0;
+    }
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(&q.sync_words[0], 1u);
   __syncthreads();
-  if (s_ticket != gridDim.x * gridDim.y - 1) return;
+  if (s_ticket != gridDim.x * gridDim.y - 1 || !char_totals) return;
   __threadfence();
-  if (q.null_counts)
-    for (int col = threadIdx.x; col < q.ncols; col += kGsThreads) {
-      int64_t n = 0;
-#pragma unroll 8
-      for (int b = 0; b < q.parts; ++b) n += q.null_part[static_cast<size_t>(b) * q.ncols + col];  // coalesced across threads
-      q.null_counts[col] = n;
-    }
-  if (char_totals) {
-    for (int col = threadIdx.x; col < q.ncols; col += kGsThreads) {
-      bool is_str = false;  // nstr is small next to ncols * 148: a linear probe per column is cheap here
-      for (int s2 = 0; s2 < q.nstr; ++s2) is_str |= tab.scol[s2] == col;
-      if (!is_str) char_totals[col] = 0;
-    }
-    if (threadIdx.x == 0) {
-      unsigned st = *reinterpret_cast<volatile uint32_t*>(&q.sync_words[1]);
-      for (int b = 0; b < q.parts; ++b) st |= q.bad_part[b] ? 1u : 0u;
-      char_totals[q.ncols] = st;
-    }
-  }
+  int bad = 0;
+  for (int b = threadIdx.x; b < q.parts; b += kGsThreads) bad |= q.bad_part[b];
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) char_totals[q.ncols] = (*reinterpret_cast<volatile uint32_t*>(&q.sync_words[1])) | (bad ? 1u : 0u);
 }
 
 // group-local inclusive sums -> absolute offsets, for consumers that want finished offsets after phase 1
@@ -900,6 +908,7 @@ int launch_from_rows_wide(const srj_plan* plan, const uint8_t* rows, const int32
   q.parts       = static_cast<int32_t>(grid);
   q.ncols       = nc;
   q.nstr        = nstr;
+  for (int s2 = 0; s2 < nstr; ++s2) q.str_bits[plan->string_columns[s2] >> 6] |= 1ull << (plan->string_columns[s2] & 63);
   const int64_t nchunks = (p.ngroups + kGsChunk - 1) / kGsChunk;
   wide_group_scan_kernel<<<dim3(static_cast<unsigned>(nchunks), nstr), kGsThreads, 0, stream>>>(q, stab);
   if (finalize) {
