@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-CUDA-source-line instruction counts of one kernel from an ncu report (needs -lineinfo + --import-source on).
 
-    python profiles/by_line.py gpurun_out/x.ncu-rep [units_per_launch] [top_n]
+    python profiles/by_line.py gpurun_out/x.ncu-rep [units_per_launch] [top_n] [kernel-name regex]
 
 Prints executed warp instructions per source line (divided by units_per_launch when given, e.g. tasks per launch),
 largest first, plus per-file totals."""
@@ -14,7 +14,8 @@ from collections import defaultdict
 rep = sys.argv[1]
 units = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 50
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["-k", "regex:" + sys.argv[4]] if len(sys.argv) > 4 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 agg = {}
 fname = "?"

@@ -122,4 +122,55 @@ __device__ __forceinline__ Reg<W> lds_elem(uint32_t a)
   return r;
 }
 
+// lane's string = L bytes (<= 32) at SHARED address srcs -> staging byte ds.  Nine aligned 32-bit source words are read
+// unconditionally (the stage has slack on both sides), funnel-shifted to the staging alignment and stored as whole
+// words where the string covers a whole staging word; the <= 3 bytes of a partial first / last staging word are taken
+// from the shifted words (the last one is rebuilt from two more loads: its index is not a compile-time constant).
+__device__ __forceinline__ void copy_shared_to_staging(uint32_t srcs, uint32_t ds, int L)
+{
+  const uint32_t dsh = ds & 3u;
+  const uint32_t ssh = srcs & 3u;
+  const bool back    = ssh < dsh;                            // the word stream starts one word before the string
+  const uint32_t sp  = (srcs - ssh) - (back ? 4u : 0u);      // aligned; staging word k <- stream words k, k + 1
+  const uint32_t sh  = ((ssh - dsh) & 3u) * 8u;
+  const uint32_t w0s = ds - dsh;
+  const int end      = static_cast<int>(dsh) + L;            // one past the last staging byte, relative to word 0
+  const int kfull1   = end >> 2;                             // whole words: [dsh ? 1 : 0, kfull1)
+  // The kernel is bound by shared-memory wavefronts (lanes hit random banks), not by issue slots: every load is
+  // predicated on the lane needing that word, which thins the active lanes of the later words and with them the
+  // bank conflicts (average string 13 bytes, longest of a warp ~32).
+  const int need = L > 0 ? (end + 3) >> 2 : -1;  // staging words 0 .. need-1 are touched; word k needs stream words k, k+1
+  uint32_t w[9];  // end <= 35: whole words are k <= 7, built from stream words 0..8
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    w[k] = 0;
+    if (k <= need) w[k] = lds_u32(sp + 4 * k);
+  }
+  const int nt      = (kfull1 > 0 || dsh == 0) ? (end & 3) : 0;
+  const uint32_t ta = sp + 4u * static_cast<uint32_t>(kfull1);
+  uint32_t t0 = 0, t1 = 0;
+  if (nt > 0) {
+    t0 = lds_u32(ta);
+    t1 = lds_u32(ta + 4);
+  }
+  const uint32_t y0 = __funnelshift_r(w[0], w[1], sh);
+  if (dsh == 0 && kfull1 > 0) sts_u32(w0s, y0);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    const uint32_t y = __funnelshift_r(w[k], w[k + 1], sh);
+    if (k < kfull1) sts_u32(w0s + 4 * k, y);
+  }
+  // partial first word: bytes [dsh, min(4, end)) when dsh > 0
+  const int hend = dsh ? tmin(end, 4) : 0;
+#pragma unroll
+  for (int b = 1; b < 4; ++b)
+    if (b >= static_cast<int>(dsh) && b < hend) sts_u8(w0s + b, y0 >> (8 * b));
+  // partial last word: bytes [0, end & 3) of word kfull1, unless that is the first word again
+  const uint32_t tw = __funnelshift_r(t0, t1, sh);
+  const uint32_t tb = w0s + 4u * static_cast<uint32_t>(kfull1);
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+    if (b < nt) sts_u8(tb + b, tw >> (8 * b));
+}
+
 }  // namespace srj

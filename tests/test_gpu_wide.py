@@ -190,3 +190,104 @@ def test_wide_long_strings_take_the_slow_gather():
     (offs, data), = O.convert_to_rows(cols)
     tbl = S.RowConversion.convertFromRows(G.rows_to_device(offs, data), [S.DType(t) for t in types])
     _check_table(G, tbl, data, offs, nrows, types, cols)
+
+
+# ======================================== to_rows (to_rows_wide.cu) =================================================
+def _check_to_rows(cols):
+    G = _gpu()
+    import srj_b200 as S
+    batches = O.convert_to_rows(cols)
+    out = S.RowConversion.convertToRows(G.table_to_device(cols))
+    assert len(out) == len(batches)
+    for o, (offs, data) in zip(out, batches):
+        goffs, gdata = G.rows_to_host(o)
+        assert np.array_equal(goffs, offs)
+        assert np.array_equal(gdata, data), f"first diff at byte {np.flatnonzero(gdata != data)[:5]} of {len(data)}"
+
+
+WIDE_TO_ROWS = dict(WIDE_SCHEMAS)
+WIDE_TO_ROWS.update({
+    # several slabs whose cuts fall next to 16-byte fields
+    "dec_slabs": [O.DECIMAL128] * 500 + [O.STRING] * 10,
+    # size_per_row not a multiple of 8: the variable section starts inside an 8-byte store unit
+    "phase": [O.INT64] * 70 + [O.STRING] * 9 + [O.INT8] * 3,
+    # 33 STRING columns: 8 warps x 5 columns, the last warp of a tile has none
+    "str33": [O.STRING] * 33 + [O.INT32] * 90,
+})
+
+
+@pytest.mark.parametrize("nrows", [1, 31, 32, 33, 64, 65, 1000, 4099])
+@pytest.mark.parametrize("name", sorted(WIDE_TO_ROWS))
+def test_wide_to_rows(name, nrows):
+    types = WIDE_TO_ROWS[name]
+    _check_to_rows(random_table(types, nrows, seed=nrows * 5 + len(types)))
+
+
+@pytest.mark.parametrize("null_frac", [0.0, 0.5, 1.0])
+def test_wide_to_rows_null_masks(null_frac):
+    """0.0: no masks at all (NULL mask pointers = all valid); 1.0: every value null (payload still copied)."""
+    _check_to_rows(random_table(WIDE_SCHEMAS["odd"], 2500, seed=17, null_frac=null_frac))
+
+
+@pytest.mark.parametrize("max_str", [0, 1, 31, 32, 33, 100])
+def test_wide_to_rows_string_lengths(max_str):
+    """0: empty chars buffers; <= 32: word mover; > 32: the byte-wise rounds (and tiles that exceed the images)."""
+    _check_to_rows(random_table(WIDE_SCHEMAS["c3"], 777, seed=max_str, max_str=max_str))
+
+
+def test_wide_to_rows_huge_rows_fall_back():
+    """Rows far larger than the tile images raise the flag; the generic kernel behind redoes the batch."""
+    rng = np.random.default_rng(4)
+    types = WIDE_SCHEMAS["strings_last"]
+    n = 200
+    cols = random_table(types, n, seed=2)
+    lens = np.where(np.arange(n) % 50 == 7, 90_000, 4)
+    offs = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=offs[1:])
+    cols[105] = O.HCol(O.STRING, rng.integers(32, 127, int(offs[-1]), dtype=np.uint8), None, offs, 0, n)
+    _check_to_rows(cols)
+
+
+def test_wide_to_rows_unaligned_column_buffers():
+    """Chars at odd addresses (cp.async chunks that start below the buffer: head bytes by hand), fixed-width data,
+    masks and offsets as element-offset slices of larger allocations (cudf's alignment contract: element-aligned)."""
+    G = _gpu()
+    import srj_b200 as S
+    types = WIDE_SCHEMAS["c3"]
+    n = 1300
+    cols = random_table(types, n, seed=31)
+    batches = O.convert_to_rows(cols)
+
+    def shifted(t, nbytes):
+        raw = t.view(torch.uint8).reshape(-1)
+        big = torch.empty(raw.numel() + nbytes, dtype=torch.uint8, device="cuda")
+        big[nbytes:] = raw
+        return big[nbytes:]
+
+    dcols = []
+    for c, t in zip(cols, types):
+        d = G.to_device(c)
+        if t == O.STRING:
+            d.data = shifted(d.data, 5)
+            d.offsets = shifted(d.offsets, 4).view(torch.int32)
+        else:
+            d.data = shifted(d.data, S.DType(t).size_in_bytes())
+        if d.mask is not None:
+            d.mask = shifted(d.mask, 4).view(torch.int32)
+        dcols.append(d)
+    out = S.RowConversion.convertToRows(S.Table(dcols))
+    assert len(out) == 1
+    goffs, gdata = G.rows_to_host(out[0])
+    assert np.array_equal(goffs, batches[0][0])
+    assert np.array_equal(gdata, batches[0][1]), f"first diff at byte {np.flatnonzero(gdata != batches[0][1])[:5]}"
+
+
+def test_wide_round_trip_is_identity():
+    G = _gpu()
+    import srj_b200 as S
+    types = WIDE_SCHEMAS["c3"]
+    cols = random_table(types, 9000, seed=12)
+    out = S.RowConversion.convertToRows(G.table_to_device(cols))
+    tbl = S.RowConversion.convertFromRows(out[0], [S.DType(t) for t in types])
+    for g, c in zip(tbl.columns, cols):
+        assert cols_equal(G.to_host(g), c)
