@@ -270,7 +270,6 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   }
 
   plan_wide(p);  // slabs of a wide variable-width table (from_rows_wide.cu); p->wide.enabled says whether it applies
-  plan_wide_to_rows(p);  // ... and of its to_rows direction (to_rows_wide.cu); p->wide.tr_enabled
 
   // device mirror
   {
@@ -291,9 +290,7 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   const size_t b_tc = tr_chunk.size() * 4;
   const size_t b_we = p->wide.enabled ? p->wide.entries.size() * sizeof(WideEntry) : 0;
   const size_t b_ws = p->wide.enabled ? p->wide.slabs.size() * sizeof(WideSlab) : 0;
-  const size_t b_te = p->wide.tr_enabled ? p->wide.tr_entries.size() * sizeof(WideEntry) : 0;
-  const size_t b_ts = p->wide.tr_enabled ? p->wide.tr_slabs.size() * sizeof(WideSlabTr) : 0;
-  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + b_tc + b_we + b_ws + b_te + b_ts + 128;
+  const size_t tot  = b_fr + b_tr + b_cs + 2 * b_sc + b_tc + b_we + b_ws + 96;
   std::vector<uint8_t> blob(tot, 0);
   size_t o = 0;
   auto put = [&](const void* src, size_t n) { size_t at = o; if (n) memcpy(blob.data() + o, src, n); o += (n + 7) & ~size_t{7}; return at; };
@@ -305,8 +302,6 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   const size_t o_tc = put(tr_chunk.data(), b_tc);
   const size_t o_we = put(p->wide.entries.data(), b_we);
   const size_t o_ws = put(p->wide.slabs.data(), b_ws);
-  const size_t o_te = put(p->wide.tr_entries.data(), b_te);
-  const size_t o_ts = put(p->wide.tr_slabs.data(), b_ts);
   cudaError_t e = cudaMalloc(&p->d_blob, tot);
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan)"); }
   e = cudaMemcpy(p->d_blob, blob.data(), tot, cudaMemcpyHostToDevice);
@@ -320,8 +315,6 @@ int srj_plan_create(const int32_t* type_ids, const int32_t* scales, int32_t num_
   p->d_tr_chunk_off = reinterpret_cast<const int32_t*>(base + o_tc);
   p->wide.d_entries = reinterpret_cast<const WideEntry*>(base + o_we);
   p->wide.d_slabs   = reinterpret_cast<const WideSlab*>(base + o_ws);
-  p->wide.d_tr_entries = reinterpret_cast<const WideEntry*>(base + o_te);
-  p->wide.d_tr_slabs   = reinterpret_cast<const WideSlabTr*>(base + o_ts);
   *out              = p;
   return SRJ_OK;
 }

@@ -18,7 +18,6 @@ size_t from_rows_smem_bytes(const Tiling& tl, int nentries, int ncols, int nstr)
 // from_rows_wide.cu: wide variable-width tables (per-row TMA slabs; offsets leave as group-local inclusive sums +
 // absolute group bases unless `finalize`)
 bool plan_wide(srj_plan* plan);
-bool plan_wide_to_rows(srj_plan* plan);  // to_rows_wide.cu; needs plan_wide() first
 int64_t wide_workspace_bytes(const srj_plan* plan, int64_t num_rows);
 const uint32_t* wide_workspace_bases(const srj_plan* plan, int64_t num_rows, const void* workspace);  // [nstr][ngroups]
 int launch_from_rows_wide(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets, int64_t rows_bytes,
@@ -57,10 +56,6 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
                    const void* const* h_col_data /* host copy of the column pointers (alignment checks) */,
                    int32_t* d_fail_flag /* 4 bytes of device scratch (variable-width tables), may be NULL */);
 // to_rows_var.cu: wide rows with STRING columns.  *launched = 0: table not eligible, nothing was launched.
-int launch_to_rows_wide(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
-                        const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
-                        int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes,
-                        int32_t* d_fail_flag, cudaStream_t stream, const void* const* h_col_data, int* launched);
 int launch_to_rows_var(const srj_plan* plan, const void* const* d_col_data, const uint32_t* const* d_masks,
                        const int32_t* const* d_str_offsets, const uint8_t* const* d_str_chars, int64_t row_start,
                        int64_t row_count, const int32_t* out_offsets, uint8_t* out_data, int64_t out_bytes,

@@ -44,12 +44,6 @@ struct WideSlab {
   int32_t begin, end;  // row byte range [begin, end) staged for this slab (multiples of 8)
   int32_t cb[7];       // entry index boundaries of the width classes, processed in the order 16,8,4,2,1,STRING
 };
-// to_rows (to_rows_wide.cu): slabs partition [0, size_per_row); units in the order 16,8,4,2,1-byte fields, STRING
-// columns, zero pieces (alignment gaps: WideEntry{start, column = -1, sidx = size in bytes})
-struct WideSlabTr {
-  int32_t begin, end;
-  int32_t cb[8];
-};
 struct WidePlan {
   bool enabled = false;
   int32_t R = 0, G = 0, pitch = 0, nstages = 0, nslabs = 0;
@@ -57,13 +51,6 @@ struct WidePlan {
   std::vector<WideSlab> slabs;
   const WideEntry* d_entries = nullptr;
   const WideSlab* d_slabs    = nullptr;
-  // to_rows of the same tables (to_rows_wide.cu): slabs that partition [0, size_per_row), one entry per column
-  bool tr_enabled = false;
-  int32_t tr_pitch = 0;
-  std::vector<WideEntry> tr_entries;
-  std::vector<WideSlabTr> tr_slabs;
-  const WideEntry* d_tr_entries = nullptr;
-  const WideSlabTr* d_tr_slabs  = nullptr;
 };
 
 // Per-call pointer tables (column/mask/offset pointers differ on every call) go host -> device through

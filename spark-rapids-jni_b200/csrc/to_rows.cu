@@ -872,11 +872,8 @@ int launch_to_rows(const srj_plan* plan, const void* const* d_col_data, const ui
     batch_offsets_kernel<<<static_cast<unsigned>((row_count + 1 + kRsThreads - 1) / kRsThreads), kRsThreads, 0, stream>>>(
       d_cum_sizes, row_start, row_count, out_offsets);
     int launched = 0;
-    int rc = launch_to_rows_wide(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets, out_data,
-                                 out_bytes, d_fail_flag, stream, h_col_data, &launched);
-    if (rc == SRJ_OK && !launched)
-      rc = launch_to_rows_var(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets, out_data,
-                              out_bytes, d_fail_flag, stream, h_col_data, &launched);
+    const int rc = launch_to_rows_var(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, out_offsets,
+                                      out_data, out_bytes, d_fail_flag, stream, h_col_data, &launched);
     if (rc != SRJ_OK) return rc;
     return launch_to_rows_generic(plan, d_col_data, d_masks, d_str_offsets, d_str_chars, row_start, row_count, d_cum_sizes,
                                   out_offsets, out_data, out_bytes, 0, stream, launched ? d_fail_flag : nullptr, false);
