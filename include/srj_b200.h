@@ -221,6 +221,37 @@ SRJ_API int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t n
                           void* stream);
 
 /* ---- multi-GPU configuration (row-range shards + one all-gather of per-column chunks) ---------------- */
+/* ---- Spark HashPartitioning on the device ---------------------------------------------------
+ * The consumer of Hash.murmurHash32: GpuHashPartitioning computes pmod(murmur3_32(42, keys), P) per row and then
+ * partitions the batch (cudf Table.partition) into the P slices shuffle_split takes
+ * (src/main/cpp/src/shuffle_split.hpp:60-189: a table plus exactly these split offsets).
+ *
+ *   srj_partition_workspace_bytes : bytes of the caller-provided workspace of the calls below.
+ *   srj_hash_partition            : d_partition_ids[r] = pmod(murmur3_32(seed, keys of row r), P) (null keys keep the
+ *                                   accumulator, hash/murmur_hash.cu:111-117); then srj_partition_plan.
+ *   srj_partition_plan            : ids -> d_partition_offsets[P + 1] (row index where each partition starts; [P] = rows)
+ *                                   and the STABLE partition maps: d_scatter_map[src] = dest, d_gather_map[dest] = src
+ *                                   (rows of one partition keep their input order).  Ids outside [0, P) are reduced
+ *                                   with Spark's pmod in place.  <= INT32_MAX rows, <= 32768 partitions.
+ *   srj_partition_columns         : moves fixed-width data and null masks into `out`; for STRING columns writes the
+ *                                   output offsets (out.offsets[rows] = the chars the column needs: read it, allocate
+ *                                   out.data, then call srj_partition_strings).  d_null_counts (device int64[ncols],
+ *                                   may be NULL) receives the null count of every column that has a mask.
+ *   srj_partition_strings         : the chars of every STRING column.
+ * All pointers device pointers owned by the caller; asynchronous on `stream`.
+ */
+SRJ_API int64_t srj_partition_workspace_bytes(int64_t num_rows, int32_t num_partitions);
+SRJ_API int srj_hash_partition(const srj_column* keys, int32_t num_keys, int64_t num_rows, uint32_t seed, int32_t num_partitions,
+                               int32_t* d_partition_ids, int32_t* d_partition_offsets, int32_t* d_scatter_map,
+                               int32_t* d_gather_map, void* workspace, void* stream);
+SRJ_API int srj_partition_plan(int32_t* d_partition_ids, int64_t num_rows, int32_t num_partitions, int32_t* d_partition_offsets,
+                               int32_t* d_scatter_map, int32_t* d_gather_map, void* workspace, void* stream);
+SRJ_API int srj_partition_columns(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
+                                  const int32_t* d_scatter_map, const int32_t* d_gather_map, int64_t* d_null_counts,
+                                  void* workspace, void* stream);
+SRJ_API int srj_partition_strings(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
+                                  const int32_t* d_gather_map, void* stream);
+
 /*
  * After the NCCL all-gather of every rank's packed column slab, add to the STRING offsets of rank r's rows the chars
  * the ranks before r hold for that column, so that the gathered chunks form one column.  No reference counterpart

@@ -377,3 +377,43 @@ def to_rows_mt(cols: Sequence[HCol], row_start: int, row_count: int, offsets: np
     _check(lib().orc_to_rows_mt(arr, len(cols), C.c_int64(row_start), C.c_int64(row_count),
                                 C.c_void_p(offsets.ctypes.data), C.c_void_p(out.ctypes.data), int(nthreads)),
            "to_rows_mt")
+
+
+# ---- Spark HashPartitioning: the plugin-side consumer of murmur_hash3_32 -----------------------------
+def spark_pmod(h: np.ndarray, n: int) -> np.ndarray:
+    """Spark's Pmod on int32: r = a % n (truncated, like the JVM); r < 0 ? (r + n) % n : r."""
+    a = h.astype(np.int64)
+    r = np.fmod(a, n)                       # truncated remainder, sign of the dividend
+    return np.where(r < 0, np.fmod(r + n, n), r).astype(np.int32)
+
+
+def partition_ids(keys: Sequence[HCol], num_partitions: int, seed: int = 42) -> np.ndarray:
+    """GpuHashPartitioning: pmod(murmur3_32(seed, keys), numPartitions)."""
+    nested = any(k.type_id in (LIST, STRUCT) for k in keys)
+    h = nested_hash("murmur", keys, seed) if nested else murmur_hash3_32(keys, seed)
+    return spark_pmod(h.astype(np.int32), num_partitions)
+
+
+def take(col: HCol, idx: np.ndarray) -> HCol:
+    """Rows idx of a fixed-width or STRING column (null payload bytes are carried along)."""
+    n = len(idx)
+    mask = None if col.mask is None else pack_mask(col.valid()[idx])
+    if col.type_id == STRING:
+        lens = np.diff(col.offsets.astype(np.int64))[idx]
+        offs = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(lens, out=offs[1:])
+        chars = np.zeros(int(offs[-1]), dtype=np.uint8)
+        for d, s in enumerate(idx):
+            chars[offs[d]:offs[d + 1]] = col.data[col.offsets[s]:col.offsets[s + 1]]
+        return HCol(STRING, chars, mask, offs, col.scale, n)
+    sz = size_of(col.type_id)
+    data = np.ascontiguousarray(col.data).view(np.uint8).reshape(col.size, sz)[idx].reshape(-1).copy()
+    return HCol(col.type_id, data, mask, None, col.scale, n)
+
+
+def stable_partition(cols: Sequence[HCol], ids: np.ndarray, num_partitions: int):
+    """cudf Table.partition with the rows of a partition in input order: (columns, offsets[P + 1], gather map)."""
+    gmap = np.argsort(ids, kind="stable").astype(np.int32)
+    offsets = np.zeros(num_partitions + 1, dtype=np.int32)
+    np.cumsum(np.bincount(ids, minlength=num_partitions), out=offsets[1:])
+    return [take(c, gmap) for c in cols], offsets, gmap

@@ -639,4 +639,99 @@ int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows,
   return hash_any(SRJ_HASH_HIVE, cols, num_columns, num_rows, 0, out, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Spark HashPartitioning: pmod(murmur3_32(seed, keys), P) + stable partition (partition.cu)
+// ---------------------------------------------------------------------------------------------------
+int64_t srj_partition_workspace_bytes(int64_t num_rows, int32_t num_partitions)
+{
+  return std::max(partition_workspace_bytes(num_rows, num_partitions), partition_string_scan_bytes(num_rows));
+}
+
+int srj_partition_plan(int32_t* d_partition_ids, int64_t num_rows, int32_t num_partitions, int32_t* d_partition_offsets,
+                       int32_t* d_scatter_map, int32_t* d_gather_map, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  if (num_rows < 0 || num_partitions <= 0 || !d_partition_offsets || (num_rows > 0 && (!d_partition_ids || !workspace))) {
+    set_error("partition_plan: bad argument");
+    return SRJ_EINVAL;
+  }
+  if (num_rows > INT32_MAX || num_partitions > (1 << 15)) {
+    set_error("partition_plan: %lld rows / %d partitions exceed the int32 row index / 32768 partitions", static_cast<long long>(num_rows), num_partitions);
+    return SRJ_EUNSUPPORTED;
+  }
+  return launch_partition_plan(d_partition_ids, num_rows, num_partitions, d_partition_offsets, d_scatter_map, d_gather_map, workspace,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int srj_hash_partition(const srj_column* keys, int32_t num_keys, int64_t num_rows, uint32_t seed, int32_t num_partitions,
+                       int32_t* d_partition_ids, int32_t* d_partition_offsets, int32_t* d_scatter_map, int32_t* d_gather_map,
+                       void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  if (num_keys <= 0 || !keys) { set_error("hash_partition: no key columns"); return SRJ_EINVAL; }
+  if (num_rows > 0 && !d_partition_ids) { set_error("hash_partition: bad argument"); return SRJ_EINVAL; }
+  // the hashes go where the ids will be: part_ids_kernel turns them into ids in place
+  int rc = hash_any(SRJ_HASH_MURMUR3_32, keys, num_keys, num_rows, seed, d_partition_ids, static_cast<cudaStream_t>(stream));
+  if (rc != SRJ_OK) return rc;
+  return srj_partition_plan(d_partition_ids, num_rows, num_partitions, d_partition_offsets, d_scatter_map, d_gather_map, workspace, stream);
+}
+
+int srj_partition_columns(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
+                          const int32_t* d_scatter_map, const int32_t* d_gather_map, int64_t* d_null_counts, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && (!in || !out))) { set_error("partition_columns: bad argument"); return SRJ_EINVAL; }
+  if (num_rows > 0 && (!d_scatter_map || !d_gather_map)) { set_error("partition_columns: both maps are needed"); return SRJ_EINVAL; }
+  if (d_null_counts && num_columns > 0) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * num_columns, st));
+  for (int32_t c = 0; c < num_columns; ++c) {
+    const srj_column& a = in[c];
+    const srj_column& b = out[c];
+    if (a.type_id != b.type_id || a.size != num_rows || b.size != num_rows) { set_error("partition_columns: column %d: type / size mismatch", c); return SRJ_EINVAL; }
+    int rc = SRJ_OK;
+    if (num_rows == 0) {   // an empty STRING column still has its offsets[0] = 0
+      if (a.type_id == SRJ_STRING && b.offsets) SRJ_CUDA_TRY(cudaMemsetAsync(b.offsets, 0, 4, st));
+      continue;
+    }
+    if (a.type_id == SRJ_STRING) {
+      if (!a.offsets || !b.offsets || !workspace) { set_error("partition_columns: STRING column %d needs offsets and the workspace", c); return SRJ_EINVAL; }
+      rc = launch_partition_string_offsets(a.offsets, b.offsets, d_gather_map, num_rows, workspace, st);
+    } else {
+      const int sz = size_of_type(a.type_id);
+      if (sz <= 0) { set_error("partition_columns: column %d: unsupported type %d", c, a.type_id); return SRJ_EUNSUPPORTED; }
+      if (!a.data || !b.data) { set_error("partition_columns: column %d: NULL data", c); return SRJ_EINVAL; }
+      rc = launch_partition_scatter_fixed(a.data, b.data, sz, d_scatter_map, num_rows, st);
+    }
+    if (rc != SRJ_OK) return rc;
+    if (b.null_mask) {
+      if (a.null_mask) {
+        rc = launch_partition_gather_mask(a.null_mask, b.null_mask, d_gather_map, num_rows,
+                                          d_null_counts ? reinterpret_cast<unsigned long long*>(d_null_counts + c) : nullptr, st);
+        if (rc != SRJ_OK) return rc;
+      } else {
+        SRJ_CUDA_TRY(cudaMemsetAsync(b.null_mask, 0xff, static_cast<size_t>((num_rows + 31) / 32) * 4, st));
+      }
+    } else if (a.null_mask) {
+      set_error("partition_columns: column %d has a null mask but its output has none", c);
+      return SRJ_EINVAL;
+    }
+  }
+  return SRJ_OK;
+}
+
+int srj_partition_strings(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows, const int32_t* d_gather_map,
+                          void* stream)
+{
+  SRJ_API_RANGE();
+  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && (!in || !out))) { set_error("partition_strings: bad argument"); return SRJ_EINVAL; }
+  for (int32_t c = 0; c < num_columns; ++c) {
+    if (in[c].type_id != SRJ_STRING || num_rows == 0) continue;
+    if (!out[c].offsets || !in[c].offsets) { set_error("partition_strings: column %d: NULL offsets", c); return SRJ_EINVAL; }
+    const int rc = launch_partition_gather_chars(static_cast<const uint8_t*>(in[c].data), in[c].offsets, static_cast<uint8_t*>(out[c].data),
+                                                 out[c].offsets, d_gather_map, num_rows, static_cast<cudaStream_t>(stream));
+    if (rc != SRJ_OK) return rc;
+  }
+  return SRJ_OK;
+}
+
 }  // extern "C"

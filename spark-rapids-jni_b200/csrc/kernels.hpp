@@ -70,4 +70,17 @@ int launch_hash_nested(int kind, const srj_column* cols, int32_t num_columns, in
 int launch_hash(int kind, const srj_column* cols, int32_t num_columns, int64_t num_rows, int64_t seed, void* out,
                 cudaStream_t stream);
 
+// ---- partition.cu: Spark HashPartitioning (ids, stable partition maps, moving the columns) ----
+int64_t partition_workspace_bytes(int64_t num_rows, int32_t num_partitions);
+int launch_partition_plan(int32_t* d_ids, int64_t num_rows, int32_t num_partitions, int32_t* d_part_offsets, int32_t* d_scatter_map,
+                          int32_t* d_gather_map, void* workspace, cudaStream_t stream);
+int launch_partition_scatter_fixed(const void* in, void* out, int elem_size, const int32_t* d_scatter_map, int64_t n, cudaStream_t stream);
+int launch_partition_gather_mask(const uint32_t* in, uint32_t* out, const int32_t* d_gather_map, int64_t n, unsigned long long* d_null_count,
+                                 cudaStream_t stream);
+int64_t partition_string_scan_bytes(int64_t n);
+int launch_partition_string_offsets(const int32_t* in_off, int32_t* out_off, const int32_t* d_gather_map, int64_t n, void* scan_ws,
+                                    cudaStream_t stream);
+int launch_partition_gather_chars(const uint8_t* in_chars, const int32_t* in_off, uint8_t* out_chars, const int32_t* out_off,
+                                  const int32_t* d_gather_map, int64_t n, cudaStream_t stream);
+
 }  // namespace srj

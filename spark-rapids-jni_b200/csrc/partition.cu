@@ -1,0 +1,389 @@
+// partition.cu -- Spark HashPartitioning on the device: partition id of every row =
+// pmod(murmur3_32(seed, keys), P), then a STABLE partition of the table's rows by that id (the rows of partition p
+// contiguous, in input order) with the partition offsets a shuffle writer slices at.  The reference repo holds the
+// hash (hash/murmur_hash.cu, Hash.murmurHash32) and the step after (shuffle_split.hpp:60-189 takes the table plus
+// exactly these split offsets); the id + partition step itself sits in the plugin (GpuHashPartitioning ->
+// Table.partition): this file is that step, built on the hashes of hash.cu.
+//
+//   part_ids_kernel   : hash -> id in place (Spark pmod: ((h % P) + P) % P), per-tile histogram in shared memory,
+//                       written partition-major ([P][ntiles]) so that one exclusive scan over the whole matrix yields,
+//                       for every (partition, tile), where that tile's rows of that partition start.
+//   i32 scan          : three-step exclusive scan of the matrix.
+//   part_rank_kernel  : tile = one CTA; warp w owns a contiguous run of the tile's rows.  Per-warp counts of every
+//                       partition (match.any: one leader per distinct id in a 32-row chunk, no atomics), a prefix over
+//                       the warps, then the warp walks its rows again in order: destination = running count of
+//                       (warp, id) + rank of the row among its chunk's rows of the same id.  Writes both maps:
+//                       scatter_map[src] = dest (coalesced) and gather_map[dest] = src.
+//   partition_scatter_*: fixed-width data moves src-ordered (coalesced reads, writes land in runs: the rows a tile sends
+//                       to one partition are contiguous); validity bits and string lengths move dest-ordered through
+//                       gather_map (a mask is n / 8 bytes: L2-resident); chars: a warp per 32 destination rows, lane = byte.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.hpp"
+
+namespace srj {
+
+constexpr int kPartThreads = 1024;
+constexpr int kPartMaxP    = 1 << 15;  // partitions (shared-memory histogram of a tile: 4 P bytes)
+
+__device__ __forceinline__ int32_t spark_pmod(int32_t h, int32_t P)
+{
+  const int32_t r = h % P;  // Spark Pmod: r < 0 ? (r + n) % n : r
+  return r < 0 ? (r + P) % P : r;
+}
+
+// ---- ids + histogram -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPartThreads) part_ids_kernel(int32_t* __restrict__ ids, int64_t n, int32_t P, int32_t tile_rows,
+                                                              int32_t ntiles, int32_t* __restrict__ hist)
+{
+  extern __shared__ int32_t s_hist[];
+  for (int p = threadIdx.x; p < P; p += kPartThreads) s_hist[p] = 0;
+  __syncthreads();
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * tile_rows;
+  const int64_t r1 = tmin<int64_t>(n, r0 + tile_rows);
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += kPartThreads) {
+    const int32_t id = spark_pmod(ids[r], P);
+    ids[r]           = id;
+    atomicAdd(&s_hist[id], 1);
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += kPartThreads) hist[static_cast<int64_t>(p) * ntiles + blockIdx.x] = s_hist[p];
+}
+
+// ---- exclusive scan of int32 (three steps: chunk sums, scan of the sums by one CTA, apply) -----------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPer     = 16;  // elements per thread
+constexpr int kScanChunk   = kScanThreads * kScanPer;
+
+__device__ __forceinline__ int32_t block_exclusive_scan(int32_t v, int32_t* s_warp, int32_t& total)
+{
+  const int lane = lane_id(), w = warp_id();
+  int32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_warp[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int32_t t = lane < kScanThreads / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    s_warp[lane] = t;  // inclusive over the warps (entries past the last warp repeat the total)
+  }
+  __syncthreads();
+  total              = s_warp[kScanThreads / 32 - 1];
+  const int32_t base = w > 0 ? s_warp[w - 1] : 0;
+  __syncthreads();
+  return base + x - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) i32_chunk_sums_kernel(const int32_t* __restrict__ v, int64_t n, int32_t* __restrict__ sums)
+{
+  __shared__ int32_t s_warp[32];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk;
+  int32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    const int64_t i = base + k * kScanThreads + threadIdx.x;
+    if (i < n) acc += v[i];
+  }
+  int32_t total;
+  block_exclusive_scan(acc, s_warp, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) i32_scan_sums_kernel(int32_t* sums, int32_t nchunks)
+{
+  __shared__ int32_t s_warp[32];
+  int32_t carry = 0;
+  for (int32_t b = 0; b < nchunks; b += kScanThreads) {
+    const int32_t i = b + threadIdx.x;
+    const int32_t v = i < nchunks ? sums[i] : 0;
+    int32_t total;
+    const int32_t ex = block_exclusive_scan(v, s_warp, total);
+    if (i < nchunks) sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+// exclusive scan in place; element i of `tail` (when given) receives the grand total
+__global__ void __launch_bounds__(kScanThreads) i32_scan_apply_kernel(int32_t* __restrict__ v, int64_t n, const int32_t* __restrict__ sums,
+                                                                     int32_t* __restrict__ tail)
+{
+  __shared__ int32_t s_warp[32];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kScanChunk + static_cast<int64_t>(threadIdx.x) * kScanPer;
+  int32_t x[kScanPer];
+  int32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    x[k] = base + k < n ? v[base + k] : 0;
+    acc += x[k];
+  }
+  int32_t total;
+  int32_t run = sums[blockIdx.x] + block_exclusive_scan(acc, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) {
+    if (base + k < n) v[base + k] = run;
+    run += x[k];
+  }
+  if (tail && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *tail = run;
+}
+
+static int64_t i32_scan_nchunks(int64_t n) { return (n + kScanChunk - 1) / kScanChunk; }
+
+static int launch_i32_exclusive_scan(int32_t* v, int64_t n, int32_t* sums /* nchunks ints */, int32_t* tail, cudaStream_t stream)
+{
+  if (n <= 0) return SRJ_OK;
+  const int64_t nchunks = i32_scan_nchunks(n);
+  i32_chunk_sums_kernel<<<static_cast<unsigned>(nchunks), kScanThreads, 0, stream>>>(v, n, sums);
+  i32_scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(sums, static_cast<int32_t>(nchunks));
+  i32_scan_apply_kernel<<<static_cast<unsigned>(nchunks), kScanThreads, 0, stream>>>(v, n, sums, tail);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+// ---- stable ranks ------------------------------------------------------------------------------------------------------
+struct RankParams {
+  const int32_t* ids;
+  const int32_t* base;  // scanned histogram [P][ntiles]
+  int64_t n;
+  int32_t P, tile_rows, ntiles, nwarps;
+  int32_t* scatter_map;  // [n] or NULL
+  int32_t* gather_map;   // [n] or NULL
+  int32_t* part_offsets; // [P + 1]
+};
+
+__global__ void __launch_bounds__(kPartThreads) part_rank_kernel(const __grid_constant__ RankParams p)
+{
+  extern __shared__ int32_t s_cnt[];  // [nwarps][P]
+  const int W = p.nwarps, P = p.P;
+  const int lane = lane_id(), w = warp_id();
+  for (int i = threadIdx.x; i < W * P; i += blockDim.x) s_cnt[i] = 0;
+  if (blockIdx.x == 0)
+    for (int q = threadIdx.x; q <= P; q += blockDim.x)
+      p.part_offsets[q] = q < P ? p.base[static_cast<int64_t>(q) * p.ntiles] : static_cast<int32_t>(p.n);
+  __syncthreads();
+  const int64_t t0  = static_cast<int64_t>(blockIdx.x) * p.tile_rows;
+  const int rows_t  = static_cast<int>(tmin<int64_t>(p.tile_rows, p.n - t0));
+  const int per_w   = ((p.tile_rows / W) + 31) & ~31;  // rows of a warp: whole 32-row chunks
+  const int b0      = tmin(rows_t, w * per_w), b1 = tmin(rows_t, b0 + per_w);
+  int32_t* cnt      = s_cnt + w * P;
+  // A: this warp's rows per partition
+  if (w < W)
+    for (int c = b0; c < b1; c += 32) {
+      const bool on    = c + lane < b1;
+      const int32_t id = on ? p.ids[t0 + c + lane] : -1;
+      const unsigned m = __match_any_sync(0xffffffffu, id);
+      if (on && (m & ((1u << lane) - 1)) == 0) cnt[id] += __popc(m);  // one leader per distinct id of the chunk
+      __syncwarp();
+    }
+  __syncthreads();
+  // B: where (warp, partition) starts: the tile's base of the partition + the counts of the warps before
+  for (int q = threadIdx.x; q < P; q += blockDim.x) {
+    int32_t run = p.base[static_cast<int64_t>(q) * p.ntiles + blockIdx.x];
+    for (int k = 0; k < W; ++k) {
+      const int32_t c  = s_cnt[k * P + q];
+      s_cnt[k * P + q] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // C: destinations, in row order
+  if (w < W)
+    for (int c = b0; c < b1; c += 32) {
+      const bool on    = c + lane < b1;
+      const int32_t id = on ? p.ids[t0 + c + lane] : -1;
+      const unsigned m = __match_any_sync(0xffffffffu, id);
+      if (on) {
+        const int32_t dest = cnt[id] + __popc(m & ((1u << lane) - 1));
+        const int64_t src  = t0 + c + lane;
+        if (p.scatter_map) p.scatter_map[src] = dest;
+        if (p.gather_map) p.gather_map[dest] = static_cast<int32_t>(src);
+      }
+      __syncwarp();
+      if (on && (m & ((1u << lane) - 1)) == 0) cnt[id] += __popc(m);
+      __syncwarp();
+    }
+}
+
+// tile of a partitioning job: large enough that the histogram matrix stays small (P x ntiles ints)
+static int32_t part_tile_rows(int32_t P)
+{
+  int32_t t = 4096;
+  while (t < 8 * P) t <<= 1;
+  return t;
+}
+
+int64_t partition_workspace_bytes(int64_t num_rows, int32_t P)
+{
+  if (num_rows <= 0 || P <= 0) return 0;
+  const int64_t ntiles = (num_rows + part_tile_rows(P) - 1) / part_tile_rows(P);
+  const int64_t hist   = static_cast<int64_t>(P) * ntiles;
+  return ((hist + i32_scan_nchunks(hist) + 64) * 4 + 255) & ~int64_t{255};
+}
+
+int launch_partition_plan(int32_t* d_ids /* in: hashes, out: partition ids */, int64_t num_rows, int32_t P, int32_t* d_part_offsets,
+                          int32_t* d_scatter_map, int32_t* d_gather_map, void* workspace, cudaStream_t stream)
+{
+  if (P <= 0 || P > kPartMaxP || num_rows < 0 || num_rows > INT32_MAX) return SRJ_EINVAL;
+  if (num_rows == 0) {
+    SRJ_CUDA_TRY(cudaMemsetAsync(d_part_offsets, 0, (static_cast<size_t>(P) + 1) * 4, stream));
+    return SRJ_OK;
+  }
+  const int32_t tile   = part_tile_rows(P);
+  const int32_t ntiles = static_cast<int32_t>((num_rows + tile - 1) / tile);
+  const int64_t hist_n = static_cast<int64_t>(P) * ntiles;
+  int32_t* hist        = static_cast<int32_t*>(workspace);
+  int32_t* sums        = hist + hist_n;
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(part_ids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPartMaxP * 4));
+  part_ids_kernel<<<ntiles, kPartThreads, static_cast<size_t>(P) * 4, stream>>>(d_ids, num_rows, P, tile, ntiles, hist);
+  const int rc = launch_i32_exclusive_scan(hist, hist_n, sums, nullptr, stream);
+  if (rc != SRJ_OK) return rc;
+  RankParams rp{};
+  rp.ids          = d_ids;
+  rp.base         = hist;
+  rp.n            = num_rows;
+  rp.P            = P;
+  rp.tile_rows    = tile;
+  rp.ntiles       = ntiles;
+  rp.nwarps       = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(kPartThreads / 32, (200 * 1024) / (static_cast<int64_t>(P) * 4))));
+  rp.scatter_map  = d_scatter_map;
+  rp.gather_map   = d_gather_map;
+  rp.part_offsets = d_part_offsets;
+  const size_t smem = static_cast<size_t>(rp.nwarps) * P * 4;
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(part_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  part_rank_kernel<<<ntiles, kPartThreads, smem, stream>>>(rp);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+// ---- moving the columns ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_fixed_kernel(const T* __restrict__ in, T* __restrict__ out, const int32_t* __restrict__ smap, int64_t n)
+{
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; r < n; r += static_cast<int64_t>(gridDim.x) * 256) out[smap[r]] = in[r];
+}
+
+// dest-ordered: validity bit of every destination row (one word per warp iteration)
+__global__ void __launch_bounds__(256) gather_mask_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const int32_t* __restrict__ gmap,
+                                                         int64_t n, unsigned long long* __restrict__ null_count)
+{
+  const int lane = lane_id();
+  int nulls      = 0;
+  for (int64_t d0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp_id()) * 32; d0 < n; d0 += static_cast<int64_t>(gridDim.x) * 256) {
+    const int64_t d = d0 + lane;
+    bool bit        = false;
+    if (d < n) {
+      const int32_t s = gmap[d];
+      bit             = (in[s >> 5] >> (s & 31)) & 1u;
+      nulls += !bit;
+    }
+    const unsigned word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) out[d0 >> 5] = word;
+  }
+  if (null_count) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nulls += __shfl_down_sync(0xffffffffu, nulls, o);
+    if (lane == 0 && nulls) atomicAdd(null_count, static_cast<unsigned long long>(nulls));
+  }
+}
+
+// dest-ordered: out_offsets[d + 1] = length of the destination row's string (scanned afterwards); out_offsets[0] = 0
+__global__ void __launch_bounds__(256) gather_lengths_kernel(const int32_t* __restrict__ in_off, int32_t* __restrict__ out_off,
+                                                            const int32_t* __restrict__ gmap, int64_t n)
+{
+  for (int64_t d = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; d < n; d += static_cast<int64_t>(gridDim.x) * 256) {
+    const int32_t s = gmap[d];
+    out_off[d]      = in_off[s + 1] - in_off[s];  // exclusive scan in place turns element d into the start of string d
+  }
+}
+
+// chars: a warp per 32 destination rows; lane = destination byte, its row by a shuffle search over the 32 starts
+__global__ void __launch_bounds__(256) gather_chars_kernel(const uint8_t* __restrict__ in_chars, const int32_t* __restrict__ in_off,
+                                                          uint8_t* __restrict__ out_chars, const int32_t* __restrict__ out_off,
+                                                          const int32_t* __restrict__ gmap, int64_t n)
+{
+  const int lane = lane_id();
+  for (int64_t d0 = (static_cast<int64_t>(blockIdx.x) * 8 + warp_id()) * 32; d0 < n; d0 += static_cast<int64_t>(gridDim.x) * 256) {
+    const int last   = static_cast<int>(tmin<int64_t>(32, n - d0)) - 1;
+    const int64_t d  = tmin<int64_t>(d0 + lane, n - 1);
+    const int32_t ob = out_off[d0];
+    const int32_t pe = out_off[d] - ob;              // where this lane's string starts among the tile's bytes
+    const int32_t so = in_off[gmap[d]];              // ... and where it comes from
+    const int32_t T  = out_off[d0 + last + 1] - ob;  // bytes of the 32 strings
+    for (int32_t q = lane; q < ((T + 31) & ~31); q += 32) {
+      int j = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand  = j + step;
+        const int32_t v = __shfl_sync(0xffffffffu, pe, cand & 31);
+        if (cand <= last && v <= q) j = cand;
+      }
+      const int32_t pj = __shfl_sync(0xffffffffu, pe, j);
+      const int32_t sj = __shfl_sync(0xffffffffu, so, j);
+      if (q < T) out_chars[ob + q] = in_chars[sj + (q - pj)];
+    }
+  }
+}
+
+static unsigned grid_for(int64_t n, int per_block)
+{
+  return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + per_block - 1) / per_block, 148 * 16)));
+}
+
+int launch_partition_scatter_fixed(const void* in, void* out, int elem_size, const int32_t* d_scatter_map, int64_t n, cudaStream_t stream)
+{
+  if (n == 0) return SRJ_OK;
+  const unsigned g = grid_for(n, 256);
+  switch (elem_size) {
+    case 1: scatter_fixed_kernel<uint8_t><<<g, 256, 0, stream>>>(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), d_scatter_map, n); break;
+    case 2: scatter_fixed_kernel<uint16_t><<<g, 256, 0, stream>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), d_scatter_map, n); break;
+    case 4: scatter_fixed_kernel<uint32_t><<<g, 256, 0, stream>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), d_scatter_map, n); break;
+    case 8: scatter_fixed_kernel<uint2><<<g, 256, 0, stream>>>(static_cast<const uint2*>(in), static_cast<uint2*>(out), d_scatter_map, n); break;
+    case 16: scatter_fixed_kernel<uint4><<<g, 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), d_scatter_map, n); break;
+    default: return SRJ_EUNSUPPORTED;
+  }
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+int launch_partition_gather_mask(const uint32_t* in, uint32_t* out, const int32_t* d_gather_map, int64_t n, unsigned long long* d_null_count,
+                                 cudaStream_t stream)
+{
+  if (n == 0) return SRJ_OK;
+  gather_mask_kernel<<<grid_for(n, 256), 256, 0, stream>>>(in, out, d_gather_map, n, d_null_count);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+int64_t partition_string_scan_bytes(int64_t n) { return (i32_scan_nchunks(n + 1) + 64) * 4; }
+
+// out_off[0 .. n] <- offsets of the partitioned column; *d_total (device int32, = out_off[n]) the chars it needs
+int launch_partition_string_offsets(const int32_t* in_off, int32_t* out_off, const int32_t* d_gather_map, int64_t n, void* scan_ws,
+                                    cudaStream_t stream)
+{
+  if (n == 0) {
+    SRJ_CUDA_TRY(cudaMemsetAsync(out_off, 0, 4, stream));
+    return SRJ_OK;
+  }
+  gather_lengths_kernel<<<grid_for(n, 256), 256, 0, stream>>>(in_off, out_off, d_gather_map, n);
+  // exclusive scan of the n lengths in place; the grand total lands in out_off[n]
+  return launch_i32_exclusive_scan(out_off, n, static_cast<int32_t*>(scan_ws), out_off + n, stream);
+}
+
+int launch_partition_gather_chars(const uint8_t* in_chars, const int32_t* in_off, uint8_t* out_chars, const int32_t* out_off,
+                                  const int32_t* d_gather_map, int64_t n, cudaStream_t stream)
+{
+  if (n == 0) return SRJ_OK;
+  gather_chars_kernel<<<grid_for(n, 256), 256, 0, stream>>>(in_chars, in_off, out_chars, out_off, d_gather_map, n);
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
+}  // namespace srj
