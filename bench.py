@@ -64,6 +64,11 @@ WORKLOADS = {
     "nvbench_var": dict(name="nvbench 'Fixed or Variable Width', include strings: 155 cols cycling [...,BOOL8,STRING,UINT16,...], "
                              "strings ~N(16,8) in [0,32] B (benchmarks/row_conversion.cpp:66-147)",
                         types=cycle(NVB_CYCLE_STR, 155), rows=1 << 20, null_frac=0.0, nvbench=True),
+    # the consumer of the row hashes -- Spark HashPartitioning of a device-resident store_sales batch
+    "partition": dict(name="hash partition: TPC-DS store_sales (23 cols, 96 data B/row), pmod(murmur3_32(42, ss_item_sk, ss_ticket_number), 200) "
+                           "+ stable partition of every column",
+                      types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, hash_keys=[1, 9], partitions=200,
+                      partition=True),
     "c3": dict(name="C3: 100M rows x 256 mixed cols ([INT32,INT64,DECIMAL128,STRING]x64, 20% nulls, strings ~N(16,8) in [0,32] B) "
                     "convert_from_rows, streamed as 200 batches of 500K rows (<=2 GiB each)",
                types=[INT32, INT64, DEC128, STRING] * 64, rows=100_000_000, null_frac=0.2, batch_rows=500_000, pool=4),
@@ -934,6 +939,74 @@ def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthre
             "ms_per_pass": sec * 1e3}
 
 
+def run_partition(args, wl, rank, world):
+    """Spark HashPartitioning step on one GPU: ids + stable partition maps + moving every column, inputs resident in HBM."""
+    import ctypes as C
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "spark-rapids-jni_b200"))
+    import srj_b200 as S
+    from srj_b200 import _native as N
+    torch.cuda.set_device(0)
+    types, n, P = wl["types"], args.rows or wl["rows"], wl["partitions"]
+    cols = synth_columns_gpu(torch, S, types, n, wl["null_frac"], 42)
+    keys = [cols[i] for i in wl["hash_keys"]]
+    words = (n + 31) // 32
+    outs = [S.ColumnVector(c.dtype, n, torch.empty_like(c.data), torch.empty(words, dtype=torch.int32, device="cuda")) for c in cols]
+    lib = N.lib()
+    ws = torch.empty(lib.srj_partition_workspace_bytes(n, P), dtype=torch.uint8, device="cuda")
+    ids = torch.empty(n, dtype=torch.int32, device="cuda")
+    offs = torch.empty(P + 1, dtype=torch.int32, device="cuda")
+    smap = torch.empty(n, dtype=torch.int32, device="cuda")
+    gmap = torch.empty(n, dtype=torch.int32, device="cuda")
+    nulls = torch.zeros(len(cols), dtype=torch.int64, device="cuda")
+    karr = (N.SrjColumn * len(keys))(*[k._c() for k in keys])
+    cin = (N.SrjColumn * len(cols))(*[c._c() for c in cols])
+    cout = (N.SrjColumn * len(cols))(*[c._c() for c in outs])
+    stream = torch.cuda.current_stream()
+    st = int(stream.cuda_stream)
+
+    def plan_step():
+        N.check(lib.srj_hash_partition(karr, len(keys), n, C.c_uint32(42), P, ids.data_ptr(), offs.data_ptr(), smap.data_ptr(), gmap.data_ptr(),
+                                       ws.data_ptr(), st))
+
+    def step():
+        plan_step()
+        N.check(lib.srj_partition_columns(cin, cout, len(cols), n, P, smap.data_ptr(), gmap.data_ptr(), nulls.data_ptr(), ws.data_ptr(), st))
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # size-independent check: the output is the input permuted by the gather map, partition by partition
+    k0 = cols[9].data.view(torch.int64)
+    assert torch.equal(outs[9].data.view(torch.int64), k0[gmap.long()]) and int(offs[P]) == n
+    sampler = ClockSampler(0)
+    sampler.start()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record(stream)
+    for _ in range(args.steps):
+        plan_step()
+    e[1].record(stream)
+    for _ in range(args.steps):
+        step()
+    e[2].record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    plan_ms = e[0].elapsed_time(e[1]) / args.steps
+    ms = e[1].elapsed_time(e[2]) / args.steps
+    peak, peak_src = load_peaks()
+    data_b = sum(SIZE[t] for t in types)
+    bpr = 2 * (data_b + len(types) / 8.0) + 4          # read the table + write it partitioned + the ids
+    gbs = bpr * n / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": "rows_per_sec_hash_partition", "value": n / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": wl["name"], "rows": n, "partitions": P, "l2": "inputs 9.6 GB >> 126 MB L2"},
+                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                                   "traffic": None, "kernel": "whole step: murmur3 + ids/histogram + scan + ranks + 23 column scatters + 23 mask gathers",
+                                   "algorithmic_bytes_per_row": bpr, "peak_source": peak_src, "plan_only_ms": plan_ms},
+                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the CPU implementation of the path on the host cores (oracle port: the reference's own
     code needs a JVM + libcudf, neither exists here).  Rank 0 only."""
@@ -1028,6 +1101,9 @@ def main():
     elif wl.get("nvbench"):
         if rank == 0:
             run_nvbench(args, wl, rank, world)
+    elif wl.get("partition"):
+        if rank == 0:
+            run_partition(args, wl, rank, world)
     elif args.workload == "c3":
         run_c3(args, wl, rank, world)
     else:

@@ -232,8 +232,10 @@ SRJ_API int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t n
  *   srj_partition_plan            : ids -> d_partition_offsets[P + 1] (row index where each partition starts; [P] = rows)
  *                                   and the STABLE partition maps: d_scatter_map[src] = dest, d_gather_map[dest] = src
  *                                   (rows of one partition keep their input order).  Ids outside [0, P) are reduced
- *                                   with Spark's pmod in place.  <= INT32_MAX rows, <= 32768 partitions.
- *   srj_partition_columns         : moves fixed-width data and null masks into `out`; for STRING columns writes the
+ *                                   with Spark's pmod in place.  <= INT32_MAX rows, <= 16384 partitions.  The workspace
+ *                                   keeps the plan's tile order: pass it, unmodified, to srj_partition_columns.
+ *   srj_partition_columns         : (same num_partitions, maps and workspace as the plan) moves fixed-width data and
+ *                                   null masks into `out`; for STRING columns writes the
  *                                   output offsets (out.offsets[rows] = the chars the column needs: read it, allocate
  *                                   out.data, then call srj_partition_strings).  d_null_counts (device int64[ncols],
  *                                   may be NULL) receives the null count of every column that has a mask.
@@ -247,10 +249,38 @@ SRJ_API int srj_hash_partition(const srj_column* keys, int32_t num_keys, int64_t
 SRJ_API int srj_partition_plan(int32_t* d_partition_ids, int64_t num_rows, int32_t num_partitions, int32_t* d_partition_offsets,
                                int32_t* d_scatter_map, int32_t* d_gather_map, void* workspace, void* stream);
 SRJ_API int srj_partition_columns(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
-                                  const int32_t* d_scatter_map, const int32_t* d_gather_map, int64_t* d_null_counts,
-                                  void* workspace, void* stream);
+                                  int32_t num_partitions, const int32_t* d_scatter_map, const int32_t* d_gather_map,
+                                  int64_t* d_null_counts, void* workspace, void* stream);
 SRJ_API int srj_partition_strings(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
                                   const int32_t* d_gather_map, void* stream);
+
+/* ---- Apache Spark UnsafeRow codec -----------------------------------------------------------
+ * The row format Spark's own operators consume (org.apache.spark.sql.catalyst.expressions.UnsafeRow /
+ * codegen.UnsafeRowWriter); the reference speaks only JCUDF (RowConversion.java:44-117) and leaves the adaptation to
+ * the plugin's CudfUnsafeRow.  Row = null bitset (ceil(n/64) 8-byte words, bit SET = NULL) | one 8-byte slot per
+ * field | variable region (strings: (offset << 32) | length, padded to 8; DECIMAL128: 16 bytes always reserved,
+ * BigInteger.toByteArray() big-endian minimal bytes, slot (offset << 32) | byte count).  DECIMAL32/64 are longs.
+ * Supported: the fixed-width types of the row path, STRING, DECIMAL32/64/128; <= 256 columns; rows 8-byte aligned.
+ *
+ *   srj_unsafe_row_layout   : bitset bytes and the size of a row without its strings.
+ *   srj_unsafe_row_sizes    : d_row_offsets[rows + 1] (byte offset of every row) and *total_bytes (host; the call
+ *                             synchronises the stream once); SRJ_EOVERFLOW beyond INT32_MAX bytes.
+ *   srj_convert_to_unsafe_rows   : columns -> rows (d_row_offsets may be NULL for tables without STRING columns:
+ *                                  rows are then fixed_bytes apart).
+ *   srj_convert_from_unsafe_rows : rows -> fixed-width / decimal values, null masks (+ counts), and for STRING
+ *                                  columns the output offsets (out.offsets[rows] = chars needed: read it, allocate
+ *                                  out.data, then call srj_convert_from_unsafe_rows_strings).
+ */
+SRJ_API int srj_unsafe_row_layout(const int32_t* type_ids, int32_t num_columns, int32_t* bitset_bytes, int32_t* fixed_bytes);
+SRJ_API int64_t srj_unsafe_row_workspace_bytes(int32_t num_columns, int64_t num_rows);
+SRJ_API int srj_unsafe_row_sizes(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* d_row_offsets,
+                                 int64_t* total_bytes, void* workspace, void* stream);
+SRJ_API int srj_convert_to_unsafe_rows(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_row_offsets,
+                                       uint8_t* rows, void* workspace, void* stream);
+SRJ_API int srj_convert_from_unsafe_rows(const uint8_t* rows, const int32_t* d_row_offsets, int64_t num_rows, const srj_column* out,
+                                         int32_t num_columns, int64_t* d_null_counts, void* workspace, void* stream);
+SRJ_API int srj_convert_from_unsafe_rows_strings(const uint8_t* rows, const int32_t* d_row_offsets, int64_t num_rows,
+                                                 const srj_column* out, int32_t num_columns, void* stream);
 
 /*
  * After the NCCL all-gather of every rank's packed column slab, add to the STRING offsets of rank r's rows the chars

@@ -644,7 +644,7 @@ int srj_hive_hash(const srj_column* cols, int32_t num_columns, int64_t num_rows,
 // ---------------------------------------------------------------------------------------------------
 int64_t srj_partition_workspace_bytes(int64_t num_rows, int32_t num_partitions)
 {
-  return std::max(partition_workspace_bytes(num_rows, num_partitions), partition_string_scan_bytes(num_rows));
+  return partition_workspace_bytes(num_rows, num_partitions);
 }
 
 int srj_partition_plan(int32_t* d_partition_ids, int64_t num_rows, int32_t num_partitions, int32_t* d_partition_offsets,
@@ -655,8 +655,8 @@ int srj_partition_plan(int32_t* d_partition_ids, int64_t num_rows, int32_t num_p
     set_error("partition_plan: bad argument");
     return SRJ_EINVAL;
   }
-  if (num_rows > INT32_MAX || num_partitions > (1 << 15)) {
-    set_error("partition_plan: %lld rows / %d partitions exceed the int32 row index / 32768 partitions", static_cast<long long>(num_rows), num_partitions);
+  if (num_rows > INT32_MAX || num_partitions > (1 << 14)) {
+    set_error("partition_plan: %lld rows / %d partitions exceed the int32 row index / 16384 partitions", static_cast<long long>(num_rows), num_partitions);
     return SRJ_EUNSUPPORTED;
   }
   return launch_partition_plan(d_partition_ids, num_rows, num_partitions, d_partition_offsets, d_scatter_map, d_gather_map, workspace,
@@ -676,45 +676,52 @@ int srj_hash_partition(const srj_column* keys, int32_t num_keys, int64_t num_row
   return srj_partition_plan(d_partition_ids, num_rows, num_partitions, d_partition_offsets, d_scatter_map, d_gather_map, workspace, stream);
 }
 
-int srj_partition_columns(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
+int srj_partition_columns(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows, int32_t num_partitions,
                           const int32_t* d_scatter_map, const int32_t* d_gather_map, int64_t* d_null_counts, void* workspace, void* stream)
 {
   SRJ_API_RANGE();
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (num_columns < 0 || num_rows < 0 || (num_columns > 0 && (!in || !out))) { set_error("partition_columns: bad argument"); return SRJ_EINVAL; }
-  if (num_rows > 0 && (!d_scatter_map || !d_gather_map)) { set_error("partition_columns: both maps are needed"); return SRJ_EINVAL; }
+  if (num_columns < 0 || num_rows < 0 || num_partitions <= 0 || (num_columns > 0 && (!in || !out))) { set_error("partition_columns: bad argument"); return SRJ_EINVAL; }
+  if (num_rows > 0 && (!d_scatter_map || !d_gather_map || !workspace)) { set_error("partition_columns: the maps and the plan's workspace are needed"); return SRJ_EINVAL; }
   if (d_null_counts && num_columns > 0) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * num_columns, st));
+  std::vector<int> esz(static_cast<size_t>(num_columns), 0);
   for (int32_t c = 0; c < num_columns; ++c) {
     const srj_column& a = in[c];
     const srj_column& b = out[c];
     if (a.type_id != b.type_id || a.size != num_rows || b.size != num_rows) { set_error("partition_columns: column %d: type / size mismatch", c); return SRJ_EINVAL; }
-    int rc = SRJ_OK;
-    if (num_rows == 0) {   // an empty STRING column still has its offsets[0] = 0
-      if (a.type_id == SRJ_STRING && b.offsets) SRJ_CUDA_TRY(cudaMemsetAsync(b.offsets, 0, 4, st));
+    if (a.type_id == SRJ_STRING) {
+      if (!a.offsets || !b.offsets) { set_error("partition_columns: STRING column %d needs offsets", c); return SRJ_EINVAL; }
+    } else {
+      esz[c] = size_of_type(a.type_id);
+      if (esz[c] <= 0) { set_error("partition_columns: column %d: unsupported type %d", c, a.type_id); return SRJ_EUNSUPPORTED; }
+      if (num_rows > 0 && (!a.data || !b.data)) { set_error("partition_columns: column %d: NULL data", c); return SRJ_EINVAL; }
+    }
+    if (a.null_mask && !b.null_mask) { set_error("partition_columns: column %d has a null mask but its output has none", c); return SRJ_EINVAL; }
+    if (!a.null_mask && b.null_mask && num_rows > 0) SRJ_CUDA_TRY(cudaMemsetAsync(b.null_mask, 0xff, static_cast<size_t>((num_rows + 31) / 32) * 4, st));
+  }
+  // fixed-width data and every null mask: tile by tile, staged in destination order (plans of <= 1024 partitions) ...
+  int rc = launch_partition_move_tiles(in, out, esz.data(), num_columns, num_rows, num_partitions, d_scatter_map, workspace,
+                                       reinterpret_cast<unsigned long long*>(d_null_counts), st);
+  if (rc == SRJ_EUNSUPPORTED) {
+    // ... or row by row
+    rc = SRJ_OK;
+    for (int32_t c = 0; c < num_columns && rc == SRJ_OK && num_rows > 0; ++c) {
+      if (esz[c] > 0) rc = launch_partition_scatter_fixed(in[c].data, out[c].data, esz[c], d_scatter_map, num_rows, st);
+      if (rc == SRJ_OK && in[c].null_mask)
+        rc = launch_partition_gather_mask(in[c].null_mask, out[c].null_mask, d_gather_map, num_rows,
+                                          d_null_counts ? reinterpret_cast<unsigned long long*>(d_null_counts + c) : nullptr, st);
+    }
+  }
+  if (rc != SRJ_OK) return rc;
+  // STRING columns: the output offsets (lengths through the gather map, then a scan; partials behind the plan's tile order)
+  for (int32_t c = 0; c < num_columns; ++c) {
+    if (in[c].type_id != SRJ_STRING) continue;
+    if (num_rows == 0) {
+      SRJ_CUDA_TRY(cudaMemsetAsync(out[c].offsets, 0, 4, st));   // an empty STRING column still has its offsets[0] = 0
       continue;
     }
-    if (a.type_id == SRJ_STRING) {
-      if (!a.offsets || !b.offsets || !workspace) { set_error("partition_columns: STRING column %d needs offsets and the workspace", c); return SRJ_EINVAL; }
-      rc = launch_partition_string_offsets(a.offsets, b.offsets, d_gather_map, num_rows, workspace, st);
-    } else {
-      const int sz = size_of_type(a.type_id);
-      if (sz <= 0) { set_error("partition_columns: column %d: unsupported type %d", c, a.type_id); return SRJ_EUNSUPPORTED; }
-      if (!a.data || !b.data) { set_error("partition_columns: column %d: NULL data", c); return SRJ_EINVAL; }
-      rc = launch_partition_scatter_fixed(a.data, b.data, sz, d_scatter_map, num_rows, st);
-    }
+    rc = launch_partition_string_offsets(in[c].offsets, out[c].offsets, d_gather_map, num_rows, static_cast<int32_t*>(workspace) + num_rows, st);
     if (rc != SRJ_OK) return rc;
-    if (b.null_mask) {
-      if (a.null_mask) {
-        rc = launch_partition_gather_mask(a.null_mask, b.null_mask, d_gather_map, num_rows,
-                                          d_null_counts ? reinterpret_cast<unsigned long long*>(d_null_counts + c) : nullptr, st);
-        if (rc != SRJ_OK) return rc;
-      } else {
-        SRJ_CUDA_TRY(cudaMemsetAsync(b.null_mask, 0xff, static_cast<size_t>((num_rows + 31) / 32) * 4, st));
-      }
-    } else if (a.null_mask) {
-      set_error("partition_columns: column %d has a null mask but its output has none", c);
-      return SRJ_EINVAL;
-    }
   }
   return SRJ_OK;
 }
@@ -732,6 +739,81 @@ int srj_partition_strings(const srj_column* in, const srj_column* out, int32_t n
     if (rc != SRJ_OK) return rc;
   }
   return SRJ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Apache Spark UnsafeRow codec (unsafe_row.cu)
+// ---------------------------------------------------------------------------------------------------
+int srj_unsafe_row_layout(const int32_t* type_ids, int32_t num_columns, int32_t* bitset_bytes, int32_t* fixed_bytes)
+{
+  if (!type_ids || !bitset_bytes || !fixed_bytes) { set_error("unsafe_row_layout: bad argument"); return SRJ_EINVAL; }
+  int32_t ndec = 0, nstr = 0, fb = 0;
+  const int rc = unsafe_row_layout(type_ids, num_columns, bitset_bytes, &fb, &ndec, &nstr);
+  if (rc != SRJ_OK) { set_error("unsafe_row_layout: 1..256 columns of fixed-width, decimal or STRING type"); return rc; }
+  *fixed_bytes = fb + 16 * ndec;   // every DECIMAL128 field reserves 16 bytes of the variable region
+  return SRJ_OK;
+}
+
+int64_t srj_unsafe_row_workspace_bytes(int32_t num_columns, int64_t num_rows) { return unsafe_row_workspace_bytes(num_columns, std::max<int64_t>(0, num_rows)); }
+
+static int ur_check(const char* what, const srj_column* cols, int32_t ncols, int64_t n, const void* workspace)
+{
+  if (ncols <= 0 || n < 0 || !cols || !workspace) { set_error("%s: bad argument", what); return SRJ_EINVAL; }
+  if (n > INT32_MAX) { set_error("%s: more than INT32_MAX rows", what); return SRJ_EOVERFLOW; }
+  for (int32_t c = 0; c < ncols; ++c)
+    if (cols[c].size != n) { set_error("%s: column %d has %lld rows, expected %lld", what, c, static_cast<long long>(cols[c].size), static_cast<long long>(n)); return SRJ_EINVAL; }
+  return SRJ_OK;
+}
+
+int srj_unsafe_row_sizes(const srj_column* cols, int32_t num_columns, int64_t num_rows, int32_t* d_row_offsets, int64_t* total_bytes,
+                         void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = ur_check("unsafe_row_sizes", cols, num_columns, num_rows, workspace);
+  if (rc != SRJ_OK) return rc;
+  if (!d_row_offsets || !total_bytes) { set_error("unsafe_row_sizes: bad argument"); return SRJ_EINVAL; }
+  rc = launch_unsafe_row_sizes(cols, num_columns, num_rows, d_row_offsets, workspace, total_bytes, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EOVERFLOW) set_error("unsafe_row_sizes: %lld bytes of rows exceed one LIST<INT8> column (INT32_MAX): convert fewer rows per call", static_cast<long long>(*total_bytes));
+  else if (rc == SRJ_EUNSUPPORTED) set_error("unsafe_row_sizes: unsupported column type or more than 256 columns");
+  return rc;
+}
+
+int srj_convert_to_unsafe_rows(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_row_offsets, uint8_t* rows,
+                               void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = ur_check("convert_to_unsafe_rows", cols, num_columns, num_rows, workspace);
+  if (rc != SRJ_OK) return rc;
+  if ((num_rows > 0 && !rows) || (reinterpret_cast<uintptr_t>(rows) & 7)) { set_error("convert_to_unsafe_rows: rows must be 8-byte aligned"); return SRJ_EINVAL; }
+  if (!d_row_offsets)
+    for (int32_t c = 0; c < num_columns; ++c)
+      if (cols[c].type_id == SRJ_STRING) { set_error("convert_to_unsafe_rows: STRING columns need the row offsets of srj_unsafe_row_sizes"); return SRJ_EINVAL; }
+  rc = launch_unsafe_to_rows(cols, num_columns, num_rows, d_row_offsets, rows, workspace, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EUNSUPPORTED) set_error("convert_to_unsafe_rows: unsupported column type or more than 256 columns");
+  return rc;
+}
+
+int srj_convert_from_unsafe_rows(const uint8_t* rows, const int32_t* d_row_offsets, int64_t num_rows, const srj_column* out, int32_t num_columns,
+                                 int64_t* d_null_counts, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = ur_check("convert_from_unsafe_rows", out, num_columns, num_rows, workspace);
+  if (rc != SRJ_OK) return rc;
+  if ((num_rows > 0 && !rows) || (reinterpret_cast<uintptr_t>(rows) & 7)) { set_error("convert_from_unsafe_rows: rows must be 8-byte aligned"); return SRJ_EINVAL; }
+  if (!d_row_offsets)
+    for (int32_t c = 0; c < num_columns; ++c)
+      if (out[c].type_id == SRJ_STRING) { set_error("convert_from_unsafe_rows: variable-width rows need their offsets"); return SRJ_EINVAL; }
+  rc = launch_unsafe_from_rows(out, num_columns, num_rows, rows, d_row_offsets, d_null_counts, workspace, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EUNSUPPORTED) set_error("convert_from_unsafe_rows: unsupported column type or more than 256 columns");
+  return rc;
+}
+
+int srj_convert_from_unsafe_rows_strings(const uint8_t* rows, const int32_t* d_row_offsets, int64_t num_rows, const srj_column* out,
+                                         int32_t num_columns, void* stream)
+{
+  SRJ_API_RANGE();
+  if (num_columns <= 0 || num_rows < 0 || !out || (num_rows > 0 && (!rows || !d_row_offsets))) { set_error("convert_from_unsafe_rows_strings: bad argument"); return SRJ_EINVAL; }
+  return launch_unsafe_from_rows_strings(out, num_columns, num_rows, rows, d_row_offsets, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -77,10 +77,27 @@ int launch_partition_plan(int32_t* d_ids, int64_t num_rows, int32_t num_partitio
 int launch_partition_scatter_fixed(const void* in, void* out, int elem_size, const int32_t* d_scatter_map, int64_t n, cudaStream_t stream);
 int launch_partition_gather_mask(const uint32_t* in, uint32_t* out, const int32_t* d_gather_map, int64_t n, unsigned long long* d_null_count,
                                  cudaStream_t stream);
-int64_t partition_string_scan_bytes(int64_t n);
+int launch_partition_move_tiles(const srj_column* in, const srj_column* out, const int* elem_size, int32_t ncols, int64_t n, int32_t P,
+                                const int32_t* d_scatter_map, const void* workspace, unsigned long long* d_null_counts, cudaStream_t stream);
 int launch_partition_string_offsets(const int32_t* in_off, int32_t* out_off, const int32_t* d_gather_map, int64_t n, void* scan_ws,
                                     cudaStream_t stream);
 int launch_partition_gather_chars(const uint8_t* in_chars, const int32_t* in_off, uint8_t* out_chars, const int32_t* out_off,
                                   const int32_t* d_gather_map, int64_t n, cudaStream_t stream);
+
+// exclusive scan of int32 in place (partition.cu); `sums` = i32_scan_nchunks(n) ints of scratch; *tail (may be NULL) <- grand total
+int64_t i32_scan_nchunks(int64_t n);
+int launch_i32_exclusive_scan(int32_t* v, int64_t n, int32_t* sums, int32_t* tail, cudaStream_t stream);
+
+// ---- unsafe_row.cu: columns <-> Apache Spark UnsafeRow ----
+int unsafe_row_layout(const int32_t* type_ids, int32_t ncols, int32_t* bitset_bytes, int32_t* fixed_bytes, int32_t* ndec, int32_t* nstr);
+int64_t unsafe_row_workspace_bytes(int32_t ncols, int64_t n);
+int launch_unsafe_row_sizes(const srj_column* cols, int32_t ncols, int64_t n, int32_t* d_row_offsets, void* workspace, int64_t* h_total,
+                            cudaStream_t stream);
+int launch_unsafe_to_rows(const srj_column* cols, int32_t ncols, int64_t n, const int32_t* d_row_offsets, uint8_t* rows, void* workspace,
+                          cudaStream_t stream);
+int launch_unsafe_from_rows(const srj_column* out, int32_t ncols, int64_t n, const uint8_t* rows, const int32_t* d_row_offsets,
+                            int64_t* d_null_counts, void* workspace, cudaStream_t stream);
+int launch_unsafe_from_rows_strings(const srj_column* out, int32_t ncols, int64_t n, const uint8_t* rows, const int32_t* d_row_offsets,
+                                    cudaStream_t stream);
 
 }  // namespace srj

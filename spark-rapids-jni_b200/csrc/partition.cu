@@ -25,7 +25,7 @@
 namespace srj {
 
 constexpr int kPartThreads = 1024;
-constexpr int kPartMaxP    = 1 << 15;  // partitions (shared-memory histogram of a tile: 4 P bytes)
+constexpr int kPartMaxP    = 1 << 14;  // partitions (shared memory of the rank kernel: (warps + 1) x P ints)
 
 __device__ __forceinline__ int32_t spark_pmod(int32_t h, int32_t P)
 {
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(kScanThreads) i32_scan_apply_kernel(int32_t* _
   if (tail && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *tail = run;
 }
 
-static int64_t i32_scan_nchunks(int64_t n) { return (n + kScanChunk - 1) / kScanChunk; }
+int64_t i32_scan_nchunks(int64_t n) { return (n + kScanChunk - 1) / kScanChunk; }
 
-static int launch_i32_exclusive_scan(int32_t* v, int64_t n, int32_t* sums /* nchunks ints */, int32_t* tail, cudaStream_t stream)
+int launch_i32_exclusive_scan(int32_t* v, int64_t n, int32_t* sums /* nchunks ints */, int32_t* tail, cudaStream_t stream)
 {
   if (n <= 0) return SRJ_OK;
   const int64_t nchunks = i32_scan_nchunks(n);
@@ -156,13 +156,16 @@ struct RankParams {
   int32_t P, tile_rows, ntiles, nwarps;
   int32_t* scatter_map;  // [n] or NULL
   int32_t* gather_map;   // [n] or NULL
+  int32_t* local_pos;    // [n]: rank of the row among its tile's rows ordered by destination (the tile kernel's staging order)
   int32_t* part_offsets; // [P + 1]
 };
 
 __global__ void __launch_bounds__(kPartThreads) part_rank_kernel(const __grid_constant__ RankParams p)
 {
-  extern __shared__ int32_t s_cnt[];  // [nwarps][P]
+  extern __shared__ int32_t s_cnt[];  // [nwarps][P], then s_delta[P]
+  __shared__ int32_t s_scan[32];
   const int W = p.nwarps, P = p.P;
+  int32_t* s_delta = s_cnt + W * P;     // (rows of the tile in the partitions before p) - (where the tile's rows of p start)
   const int lane = lane_id(), w = warp_id();
   for (int i = threadIdx.x; i < W * P; i += blockDim.x) s_cnt[i] = 0;
   if (blockIdx.x == 0)
@@ -184,13 +187,46 @@ __global__ void __launch_bounds__(kPartThreads) part_rank_kernel(const __grid_co
       __syncwarp();
     }
   __syncthreads();
-  // B: where (warp, partition) starts: the tile's base of the partition + the counts of the warps before
-  for (int q = threadIdx.x; q < P; q += blockDim.x) {
-    int32_t run = p.base[static_cast<int64_t>(q) * p.ntiles + blockIdx.x];
-    for (int k = 0; k < W; ++k) {
-      const int32_t c  = s_cnt[k * P + q];
-      s_cnt[k * P + q] = run;
-      run += c;
+  // B: where (warp, partition) starts: the tile's base of the partition + the counts of the warps before; and the
+  // exclusive prefix of the tile's own counts over the partitions (the tile-local order of its rows)
+  {
+    int32_t carry = 0;
+    for (int q0 = 0; q0 < P; q0 += blockDim.x) {   // blockDim.x partitions per round
+      const int q = q0 + threadIdx.x;
+      int32_t tile_cnt = 0, b = 0;
+      if (q < P) {
+        b           = p.base[static_cast<int64_t>(q) * p.ntiles + blockIdx.x];
+        int32_t run = b;
+        for (int k = 0; k < W; ++k) {
+          const int32_t c  = s_cnt[k * P + q];
+          s_cnt[k * P + q] = run;
+          run += c;
+        }
+        tile_cnt = run - b;
+      }
+      // block-wide exclusive scan of tile_cnt
+      int32_t x = tile_cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_scan[w] = x;
+      __syncthreads();
+      if (w == 0) {
+        int32_t t = s_scan[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
+          if (lane >= o) t += y;
+        }
+        s_scan[lane] = t;
+      }
+      __syncthreads();
+      const int32_t before = carry + (w > 0 ? s_scan[w - 1] : 0) + x - tile_cnt;
+      if (q < P) s_delta[q] = before - b;
+      carry += s_scan[31];
+      __syncthreads();
     }
   }
   __syncthreads();
@@ -205,6 +241,7 @@ __global__ void __launch_bounds__(kPartThreads) part_rank_kernel(const __grid_co
         const int64_t src  = t0 + c + lane;
         if (p.scatter_map) p.scatter_map[src] = dest;
         if (p.gather_map) p.gather_map[dest] = static_cast<int32_t>(src);
+        if (p.local_pos) p.local_pos[src] = static_cast<int32_t>(t0) + dest + s_delta[id];
       }
       __syncwarp();
       if (on && (m & ((1u << lane) - 1)) == 0) cnt[id] += __popc(m);
@@ -220,12 +257,14 @@ static int32_t part_tile_rows(int32_t P)
   return t;
 }
 
+// workspace: [local_pos: n ints | histogram matrix + scan partials (later: the string scans' partials)]
 int64_t partition_workspace_bytes(int64_t num_rows, int32_t P)
 {
-  if (num_rows <= 0 || P <= 0) return 0;
+  if (num_rows <= 0 || P <= 0) return 256;
   const int64_t ntiles = (num_rows + part_tile_rows(P) - 1) / part_tile_rows(P);
   const int64_t hist   = static_cast<int64_t>(P) * ntiles;
-  return ((hist + i32_scan_nchunks(hist) + 64) * 4 + 255) & ~int64_t{255};
+  const int64_t tail   = std::max(hist + i32_scan_nchunks(hist), i32_scan_nchunks(num_rows + 1)) + 64;
+  return ((num_rows + tail) * 4 + 255) & ~int64_t{255};
 }
 
 int launch_partition_plan(int32_t* d_ids /* in: hashes, out: partition ids */, int64_t num_rows, int32_t P, int32_t* d_part_offsets,
@@ -239,7 +278,8 @@ int launch_partition_plan(int32_t* d_ids /* in: hashes, out: partition ids */, i
   const int32_t tile   = part_tile_rows(P);
   const int32_t ntiles = static_cast<int32_t>((num_rows + tile - 1) / tile);
   const int64_t hist_n = static_cast<int64_t>(P) * ntiles;
-  int32_t* hist        = static_cast<int32_t*>(workspace);
+  int32_t* local_pos   = static_cast<int32_t*>(workspace);
+  int32_t* hist        = local_pos + num_rows;
   int32_t* sums        = hist + hist_n;
   SRJ_CUDA_TRY(cudaFuncSetAttribute(part_ids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPartMaxP * 4));
   part_ids_kernel<<<ntiles, kPartThreads, static_cast<size_t>(P) * 4, stream>>>(d_ids, num_rows, P, tile, ntiles, hist);
@@ -252,11 +292,12 @@ int launch_partition_plan(int32_t* d_ids /* in: hashes, out: partition ids */, i
   rp.P            = P;
   rp.tile_rows    = tile;
   rp.ntiles       = ntiles;
-  rp.nwarps       = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(kPartThreads / 32, (200 * 1024) / (static_cast<int64_t>(P) * 4))));
+  rp.nwarps       = static_cast<int32_t>(std::max<int64_t>(1, std::min<int64_t>(kPartThreads / 32, (200 * 1024) / (static_cast<int64_t>(P) * 4) - 1)));
   rp.scatter_map  = d_scatter_map;
   rp.gather_map   = d_gather_map;
+  rp.local_pos    = local_pos;
   rp.part_offsets = d_part_offsets;
-  const size_t smem = static_cast<size_t>(rp.nwarps) * P * 4;
+  const size_t smem = (static_cast<size_t>(rp.nwarps) + 1) * P * 4;
   SRJ_CUDA_TRY(cudaFuncSetAttribute(part_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   part_rank_kernel<<<ntiles, kPartThreads, smem, stream>>>(rp);
   SRJ_CUDA_TRY(cudaGetLastError());
@@ -332,6 +373,139 @@ __global__ void __launch_bounds__(256) gather_chars_kernel(const uint8_t* __rest
   }
 }
 
+// ---- moving the columns, tile by tile ------------------------------------------------------------------------------------
+// One CTA per tile of the plan.  The tile's rows are staged in shared memory in destination order (local_pos), so that
+// consecutive threads then write consecutive destinations: the rows a tile sends to one partition leave as one run
+// instead of one 4-byte transaction per row.  The destination of every staged position is kept in shared memory for
+// the whole column loop; validity bits travel the same way and reach the output words through one atomicOr per
+// (warp, word).
+constexpr int kMoveCols = 48;  // columns per launch (descriptor table in the kernel parameters)
+struct MoveParams {
+  const int32_t* smap;
+  const int32_t* local_pos;
+  int64_t n;
+  int32_t tile_rows, ncols;
+  unsigned long long* null_counts;  // [ncols of the launch] or NULL
+  const void* in[kMoveCols];
+  void* out[kMoveCols];
+  const uint32_t* in_mask[kMoveCols];
+  uint32_t* out_mask[kMoveCols];    // zeroed by the caller
+  uint8_t width[kMoveCols];         // 0: no data (STRING: mask only)
+};
+
+template <typename T>
+__device__ __forceinline__ void move_column(const T* __restrict__ in, T* __restrict__ out, T* s_val, const int32_t* s_dest, int64_t t0, int rows_t,
+                                            const int32_t* lp, int rpt)
+{
+  for (int k = 0; k < rpt; ++k) {
+    const int i = k * kPartThreads + threadIdx.x;
+    if (i < rows_t) s_val[lp[k]] = in[t0 + i];
+  }
+  __syncthreads();
+  for (int k = 0; k < rpt; ++k) {
+    const int i = k * kPartThreads + threadIdx.x;
+    if (i < rows_t) out[s_dest[i]] = s_val[i];
+  }
+  __syncthreads();
+}
+
+constexpr int kMoveMaxRpt = 8;  // tile_rows <= 8 x 1024
+
+__global__ void __launch_bounds__(kPartThreads) partition_move_tile_kernel(const __grid_constant__ MoveParams p)
+{
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  int32_t* s_dest = reinterpret_cast<int32_t*>(s_raw);                     // [tile_rows]
+  uint8_t* s_val  = s_raw + static_cast<size_t>(p.tile_rows) * 4;         // [tile_rows] x 16 bytes
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x) * p.tile_rows;
+  const int rows_t = static_cast<int>(tmin<int64_t>(p.tile_rows, p.n - t0));
+  const int rpt    = p.tile_rows / kPartThreads;
+  const int lane   = lane_id();
+  int32_t lp[kMoveMaxRpt];
+#pragma unroll
+  for (int k = 0; k < kMoveMaxRpt; ++k) {
+    lp[k]       = 0;
+    const int i = k * kPartThreads + threadIdx.x;
+    if (k < rpt && i < rows_t) {
+      lp[k]         = p.local_pos[t0 + i] - static_cast<int32_t>(t0);   // (see part_rank_kernel: rank inside the tile)
+      s_dest[lp[k]] = p.smap[t0 + i];
+    }
+  }
+  __syncthreads();
+  for (int c = 0; c < p.ncols; ++c) {
+    switch (p.width[c]) {
+      case 1: move_column(static_cast<const uint8_t*>(p.in[c]), static_cast<uint8_t*>(p.out[c]), s_val, s_dest, t0, rows_t, lp, rpt); break;
+      case 2: move_column(static_cast<const uint16_t*>(p.in[c]), static_cast<uint16_t*>(p.out[c]), reinterpret_cast<uint16_t*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
+      case 4: move_column(static_cast<const uint32_t*>(p.in[c]), static_cast<uint32_t*>(p.out[c]), reinterpret_cast<uint32_t*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
+      case 8: move_column(static_cast<const uint2*>(p.in[c]), static_cast<uint2*>(p.out[c]), reinterpret_cast<uint2*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
+      case 16: move_column(static_cast<const uint4*>(p.in[c]), static_cast<uint4*>(p.out[c]), reinterpret_cast<uint4*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
+      default: break;
+    }
+    const uint32_t* im = p.in_mask[c];
+    uint32_t* om       = p.out_mask[c];
+    if (im && om) {   // CTA-uniform
+      for (int k = 0; k < rpt; ++k) {
+        const int i = k * kPartThreads + threadIdx.x;
+        if (i < rows_t) s_val[lp[k]] = static_cast<uint8_t>((im[(t0 + i) >> 5] >> ((t0 + i) & 31)) & 1u);
+      }
+      __syncthreads();
+      int nulls = 0;
+      for (int k = 0; k < rpt; ++k) {
+        const int i       = k * kPartThreads + threadIdx.x;
+        const bool on     = i < rows_t;
+        const int32_t d   = on ? s_dest[i] : -1;
+        const uint32_t b  = on ? s_val[i] : 0;
+        nulls += on && !b;
+        const int32_t key = on ? (d >> 5) : -1;
+        const unsigned m  = __match_any_sync(0xffffffffu, key);
+        const uint32_t wd = __reduce_or_sync(m, b << (d & 31));
+        if (on && wd && (m & ((1u << lane) - 1)) == 0) atomicOr(om + key, wd);
+      }
+      if (p.null_counts) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nulls += __shfl_down_sync(0xffffffffu, nulls, o);
+        if (lane == 0 && nulls) atomicAdd(p.null_counts + c, static_cast<unsigned long long>(nulls));
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// local_pos as written by part_rank_kernel is an ABSOLUTE position (tile start + rank inside the tile); every column
+// (data of fixed-width columns, null masks of all) of `in` moves to `out`.  Returns SRJ_EUNSUPPORTED when the plan's
+// tiles do not fit the staging buffers (more than 1024 partitions): the caller then uses the per-row kernels.
+int launch_partition_move_tiles(const srj_column* in, const srj_column* out, const int* elem_size, int32_t ncols, int64_t n, int32_t P,
+                                const int32_t* d_scatter_map, const void* workspace, unsigned long long* d_null_counts, cudaStream_t stream)
+{
+  const int32_t tile = part_tile_rows(P);
+  if (tile > kMoveMaxRpt * kPartThreads) return SRJ_EUNSUPPORTED;
+  if (n == 0 || ncols == 0) return SRJ_OK;
+  const int32_t ntiles = static_cast<int32_t>((n + tile - 1) / tile);
+  const size_t smem    = static_cast<size_t>(tile) * 20;
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(partition_move_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMoveMaxRpt * kPartThreads * 20));
+  for (int32_t c0 = 0; c0 < ncols; c0 += kMoveCols) {
+    MoveParams mp{};
+    mp.smap        = d_scatter_map;
+    mp.local_pos   = static_cast<const int32_t*>(workspace);
+    mp.n           = n;
+    mp.tile_rows   = tile;
+    mp.ncols       = std::min(kMoveCols, ncols - c0);
+    mp.null_counts = d_null_counts ? d_null_counts + c0 : nullptr;
+    for (int k = 0; k < mp.ncols; ++k) {
+      const srj_column& a = in[c0 + k];
+      const srj_column& b = out[c0 + k];
+      mp.width[k]    = static_cast<uint8_t>(elem_size[c0 + k]);
+      mp.in[k]       = a.data;
+      mp.out[k]      = b.data;
+      mp.in_mask[k]  = a.null_mask;
+      mp.out_mask[k] = a.null_mask ? b.null_mask : nullptr;
+      if (a.null_mask && b.null_mask) SRJ_CUDA_TRY(cudaMemsetAsync(b.null_mask, 0, static_cast<size_t>((n + 31) / 32) * 4, stream));
+    }
+    partition_move_tile_kernel<<<ntiles, kPartThreads, smem, stream>>>(mp);
+  }
+  SRJ_CUDA_TRY(cudaGetLastError());
+  return SRJ_OK;
+}
+
 static unsigned grid_for(int64_t n, int per_block)
 {
   return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + per_block - 1) / per_block, 148 * 16)));
@@ -361,8 +535,6 @@ int launch_partition_gather_mask(const uint32_t* in, uint32_t* out, const int32_
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }
-
-int64_t partition_string_scan_bytes(int64_t n) { return (i32_scan_nchunks(n + 1) + 64) * 4; }
 
 // out_off[0 .. n] <- offsets of the partitioned column; *d_total (device int32, = out_off[n]) the chars it needs
 int launch_partition_string_offsets(const int32_t* in_off, int32_t* out_off, const int32_t* d_gather_map, int64_t n, void* scan_ws,

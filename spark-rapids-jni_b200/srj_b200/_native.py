@@ -68,9 +68,16 @@ SYMBOLS = {
     "srj_hash_partition": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "srj_partition_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "srj_partition_columns": (C.c_int, [C.POINTER(SrjColumn), C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+    "srj_partition_columns": (C.c_int, [C.POINTER(SrjColumn), C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "srj_partition_strings": (C.c_int, [C.POINTER(SrjColumn), C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "srj_unsafe_row_layout": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "srj_unsafe_row_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64]),
+    "srj_unsafe_row_sizes": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "srj_convert_to_unsafe_rows": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "srj_convert_from_unsafe_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]),
+    "srj_convert_from_unsafe_rows_strings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_int32, C.c_void_p]),
     "srj_shard_rebase_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]),
     "srj_convert_from_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(SrjColumn),

@@ -67,7 +67,7 @@ def _partition(table: Table, ids: torch.Tensor, num_partitions: int, hash_keys: 
                 raise ValueError(f"partition: unsupported column type {c.dtype}")
         nulls = torch.zeros(max(1, len(cols)), dtype=torch.int64, device=dev)
         cin, cout = _carray(cols), _carray(outs)
-        N.check(lib.srj_partition_columns(cin, cout, len(cols), n, smap.data_ptr(), gmap.data_ptr(), nulls.data_ptr(), ws.data_ptr(), st),
+        N.check(lib.srj_partition_columns(cin, cout, len(cols), n, num_partitions, smap.data_ptr(), gmap.data_ptr(), nulls.data_ptr(), ws.data_ptr(), st),
                 "partition")
         sidx = [i for i, c in enumerate(cols) if c.dtype.type_id == DType.STRING]
         if sidx:
