@@ -394,26 +394,29 @@ struct MoveParams {
 };
 
 template <typename T>
-__device__ __forceinline__ void move_column(const T* __restrict__ in, T* __restrict__ out, T* s_val, const int32_t* s_dest, int64_t t0, int rows_t,
-                                            const int32_t* lp, int rpt)
+__device__ __forceinline__ void move_stage(const T* __restrict__ in, T* s_val, int64_t t0, int rows_t, const int32_t* lp, int rpt)
 {
   for (int k = 0; k < rpt; ++k) {
     const int i = k * kPartThreads + threadIdx.x;
     if (i < rows_t) s_val[lp[k]] = in[t0 + i];
   }
-  __syncthreads();
+}
+template <typename T>
+__device__ __forceinline__ void move_write(T* __restrict__ out, const T* s_val, const int32_t* s_dest, int rows_t, int rpt)
+{
   for (int k = 0; k < rpt; ++k) {
     const int i = k * kPartThreads + threadIdx.x;
     if (i < rows_t) out[s_dest[i]] = s_val[i];
   }
-  __syncthreads();
 }
 
-constexpr int kMoveMaxRpt = 8;  // tile_rows <= 8 x 1024
+constexpr int kMoveMaxRpt = 8;    // tile_rows <= 8 x 1024
+constexpr int kMoveGroupB = 16;   // bytes per row staged between two CTA barriers: columns move in groups of <= 16 bytes
 
 __global__ void __launch_bounds__(kPartThreads) partition_move_tile_kernel(const __grid_constant__ MoveParams p)
 {
   extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ int s_nulls[kMoveGroupB];
   int32_t* s_dest = reinterpret_cast<int32_t*>(s_raw);                     // [tile_rows]
   uint8_t* s_val  = s_raw + static_cast<size_t>(p.tile_rows) * 4;         // [tile_rows] x 16 bytes
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * p.tile_rows;
@@ -431,42 +434,75 @@ __global__ void __launch_bounds__(kPartThreads) partition_move_tile_kernel(const
     }
   }
   __syncthreads();
-  for (int c = 0; c < p.ncols; ++c) {
-    switch (p.width[c]) {
-      case 1: move_column(static_cast<const uint8_t*>(p.in[c]), static_cast<uint8_t*>(p.out[c]), s_val, s_dest, t0, rows_t, lp, rpt); break;
-      case 2: move_column(static_cast<const uint16_t*>(p.in[c]), static_cast<uint16_t*>(p.out[c]), reinterpret_cast<uint16_t*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
-      case 4: move_column(static_cast<const uint32_t*>(p.in[c]), static_cast<uint32_t*>(p.out[c]), reinterpret_cast<uint32_t*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
-      case 8: move_column(static_cast<const uint2*>(p.in[c]), static_cast<uint2*>(p.out[c]), reinterpret_cast<uint2*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
-      case 16: move_column(static_cast<const uint4*>(p.in[c]), static_cast<uint4*>(p.out[c]), reinterpret_cast<uint4*>(s_val), s_dest, t0, rows_t, lp, rpt); break;
-      default: break;
-    }
-    const uint32_t* im = p.in_mask[c];
-    uint32_t* om       = p.out_mask[c];
-    if (im && om) {   // CTA-uniform
-      for (int k = 0; k < rpt; ++k) {
-        const int i = k * kPartThreads + threadIdx.x;
-        if (i < rows_t) s_val[lp[k]] = static_cast<uint8_t>((im[(t0 + i) >> 5] >> ((t0 + i) & 31)) & 1u);
-      }
-      __syncthreads();
-      int nulls = 0;
-      for (int k = 0; k < rpt; ++k) {
-        const int i       = k * kPartThreads + threadIdx.x;
-        const bool on     = i < rows_t;
-        const int32_t d   = on ? s_dest[i] : -1;
-        const uint32_t b  = on ? s_val[i] : 0;
-        nulls += on && !b;
-        const int32_t key = on ? (d >> 5) : -1;
-        const unsigned m  = __match_any_sync(0xffffffffu, key);
-        const uint32_t wd = __reduce_or_sync(m, b << (d & 31));
-        if (on && wd && (m & ((1u << lane) - 1)) == 0) atomicOr(om + key, wd);
-      }
-      if (p.null_counts) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nulls += __shfl_down_sync(0xffffffffu, nulls, o);
-        if (lane == 0 && nulls) atomicAdd(p.null_counts + c, static_cast<unsigned long long>(nulls));
+  // ---- data: groups of columns whose widths add up to <= 16 bytes share one stage / write round ----
+  for (int c0 = 0; c0 < p.ncols;) {
+    int c1 = c0, acc = 0;
+    while (c1 < p.ncols && acc + p.width[c1] <= kMoveGroupB) acc += p.width[c1++];
+    for (int pass = 0; pass < 2; ++pass) {
+      int at = 0;
+      for (int c = c0; c < c1; ++c) {
+        const int W = p.width[c];
+        uint8_t* area = s_val + static_cast<size_t>(at) * p.tile_rows;   // every area starts 16-byte aligned: tile_rows is a multiple of 1024
+        at += W;
+        switch (W) {
+          case 1: pass == 0 ? move_stage(static_cast<const uint8_t*>(p.in[c]), area, t0, rows_t, lp, rpt) : move_write(static_cast<uint8_t*>(p.out[c]), area, s_dest, rows_t, rpt); break;
+          case 2: pass == 0 ? move_stage(static_cast<const uint16_t*>(p.in[c]), reinterpret_cast<uint16_t*>(area), t0, rows_t, lp, rpt) : move_write(static_cast<uint16_t*>(p.out[c]), reinterpret_cast<uint16_t*>(area), s_dest, rows_t, rpt); break;
+          case 4: pass == 0 ? move_stage(static_cast<const uint32_t*>(p.in[c]), reinterpret_cast<uint32_t*>(area), t0, rows_t, lp, rpt) : move_write(static_cast<uint32_t*>(p.out[c]), reinterpret_cast<uint32_t*>(area), s_dest, rows_t, rpt); break;
+          case 8: pass == 0 ? move_stage(static_cast<const uint2*>(p.in[c]), reinterpret_cast<uint2*>(area), t0, rows_t, lp, rpt) : move_write(static_cast<uint2*>(p.out[c]), reinterpret_cast<uint2*>(area), s_dest, rows_t, rpt); break;
+          case 16: pass == 0 ? move_stage(static_cast<const uint4*>(p.in[c]), reinterpret_cast<uint4*>(area), t0, rows_t, lp, rpt) : move_write(static_cast<uint4*>(p.out[c]), reinterpret_cast<uint4*>(area), s_dest, rows_t, rpt); break;
+          default: break;
+        }
       }
       __syncthreads();
     }
+    c0 = c1 > c0 ? c1 : c0 + 1;
+  }
+  // ---- null masks: up to 16 columns' validity bits per round, one byte per (row, column) ----
+  for (int c0 = 0; c0 < p.ncols; c0 += kMoveGroupB) {
+    const int c1 = tmin(p.ncols, c0 + kMoveGroupB);
+    bool any = false;
+    for (int c = c0; c < c1; ++c) any |= p.in_mask[c] && p.out_mask[c];
+    if (!any) continue;   // CTA-uniform
+    if (threadIdx.x < kMoveGroupB) s_nulls[threadIdx.x] = 0;
+    for (int k = 0; k < rpt; ++k) {
+      const int i = k * kPartThreads + threadIdx.x;
+      if (i < rows_t)
+        for (int c = c0; c < c1; ++c) {
+          const uint32_t* im = p.in_mask[c];
+          if (im && p.out_mask[c]) s_val[static_cast<size_t>(c - c0) * p.tile_rows + lp[k]] = static_cast<uint8_t>((im[(t0 + i) >> 5] >> ((t0 + i) & 31)) & 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < rpt; ++k) {
+      const int i     = k * kPartThreads + threadIdx.x;
+      const bool on   = i < rows_t;
+      const int32_t d = on ? s_dest[i] : -2;
+      // lanes whose destinations are consecutive and fall into one output word form a segment; its head ORs the
+      // segment's bits into that word with one atomic
+      const int32_t dprev  = __shfl_up_sync(0xffffffffu, d, 1);
+      const bool head      = on && (lane == 0 || d != dprev + 1 || (d & 31) == 0);
+      const unsigned heads = __ballot_sync(0xffffffffu, head || !on);
+      const unsigned later = lane < 31 ? heads >> (lane + 1) : 0u;
+      const int seg_len    = later ? __ffs(later) : 32 - lane;   // lanes up to the next head (or the end of the warp)
+      const unsigned seg   = (seg_len >= 32 ? 0xffffffffu : ((1u << seg_len) - 1u)) << lane;
+      for (int c = c0; c < c1; ++c) {
+        uint32_t* om = p.out_mask[c];
+        if (!p.in_mask[c] || !om) continue;
+        const uint32_t b     = on ? s_val[static_cast<size_t>(c - c0) * p.tile_rows + i] : 0u;
+        const unsigned valid = __ballot_sync(0xffffffffu, b != 0);
+        if (head) {
+          const uint32_t wd = ((valid & seg) >> lane) << (d & 31);
+          if (wd) atomicOr(om + (d >> 5), wd);
+        }
+        if (p.null_counts) {   // per CTA in shared memory first: one global atomic per (tile, column)
+          const int nulls = __popc(__ballot_sync(0xffffffffu, on) & ~valid);
+          if (lane == 0 && nulls) atomicAdd(&s_nulls[c - c0], nulls);
+        }
+      }
+    }
+    __syncthreads();
+    if (p.null_counts && threadIdx.x < c1 - c0 && s_nulls[threadIdx.x]) atomicAdd(p.null_counts + c0 + threadIdx.x, static_cast<unsigned long long>(s_nulls[threadIdx.x]));
+    __syncthreads();
   }
 }
 
