@@ -17,6 +17,8 @@ cannot run).
 from __future__ import annotations
 
 import argparse
+import ctypes
+from ctypes import c_int32 as C_int32
 import json
 import os
 import subprocess
@@ -69,6 +71,10 @@ WORKLOADS = {
                            "+ stable partition of every column",
                       types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, hash_keys=[1, 9], partitions=200,
                       partition=True),
+    # the same C2 table through Apache Spark's UnsafeRow format (264 B rows: 8 B bitset + 32 slots)
+    "unsafe_c2": dict(name="UnsafeRow codec: 50M rows x 32 fixed-width cols ([INT8,INT16,INT32,INT64,FLOAT32,FLOAT64,BOOL8,TIMESTAMP_US]x4), "
+                           "264 B UnsafeRows, 20% nulls", types=[INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US] * 4,
+                      rows=50_000_000, null_frac=0.2, unsafe=True),
     "c3": dict(name="C3: 100M rows x 256 mixed cols ([INT32,INT64,DECIMAL128,STRING]x64, 20% nulls, strings ~N(16,8) in [0,32] B) "
                     "convert_from_rows, streamed as 200 batches of 500K rows (<=2 GiB each)",
                types=[INT32, INT64, DEC128, STRING] * 64, rows=100_000_000, null_frac=0.2, batch_rows=500_000, pool=4),
@@ -1007,6 +1013,72 @@ def run_partition(args, wl, rank, world):
                       "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
 
 
+def run_unsafe(args, wl, rank, world):
+    """columns <-> UnsafeRow on one GPU, inputs resident in HBM; --direction picks the timed side."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "spark-rapids-jni_b200"))
+    import srj_b200 as S
+    from srj_b200 import _native as N
+    torch.cuda.set_device(0)
+    types, n = wl["types"], args.rows or wl["rows"]
+    cols = synth_columns_gpu(torch, S, types, n, wl["null_frac"], 42)
+    lib = N.lib()
+    ids = (C_int32 * len(types))(*types)
+    a, b = C_int32(0), C_int32(0)
+    N.check(lib.srj_unsafe_row_layout(ids, len(types), ctypes.byref(a), ctypes.byref(b)))
+    row_bytes = b.value
+    st = int(torch.cuda.current_stream().cuda_stream)
+    ws = torch.empty(lib.srj_unsafe_row_workspace_bytes(len(types), n), dtype=torch.uint8, device="cuda")
+    rows = torch.empty(n * row_bytes, dtype=torch.uint8, device="cuda")
+    words = (n + 31) // 32
+    outs = [S.ColumnVector(c.dtype, n, torch.empty_like(c.data), torch.empty(words, dtype=torch.int32, device="cuda")) for c in cols]
+    nulls = torch.zeros(len(cols), dtype=torch.int64, device="cuda")
+    cin = (N.SrjColumn * len(cols))(*[c._c() for c in cols])
+    cout = (N.SrjColumn * len(cols))(*[c._c() for c in outs])
+
+    def to_rows():
+        N.check(lib.srj_convert_to_unsafe_rows(cin, len(cols), n, None, rows.data_ptr(), ws.data_ptr(), st))
+
+    def from_rows():
+        N.check(lib.srj_convert_from_unsafe_rows(rows.data_ptr(), None, n, cout, len(cols), nulls.data_ptr(), ws.data_ptr(), st))
+
+    to_rows()
+    from_rows()
+    torch.cuda.synchronize()
+    # round trip identity on the valid values of two columns + the null counts
+    for i in (3, 5):
+        m = cols[i].mask
+        valid = ((m[torch.arange(n, device="cuda") // 32] >> (torch.arange(n, device="cuda") % 32)) & 1).bool()
+        assert torch.equal(outs[i].data.view(torch.int64)[valid], cols[i].data.view(torch.int64)[valid])
+        assert int(nulls[i]) == int((~valid).sum())
+    step = to_rows if args.direction == "to_rows" else from_rows
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, peak_src = load_peaks()
+    bpr = row_bytes + sum(SIZE[t] for t in types) + len(types) / 8.0
+    gbs = bpr * n / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": f"rows_per_sec_convert_{'to' if args.direction == 'to_rows' else 'from'}_unsafe_rows", "value": n / (ms * 1e-3),
+                      "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": wl["name"], "rows": n, "row_bytes": row_bytes, "direction": args.direction,
+                                 "l2": "rows 13.2 GB + columns 7.2 GB >> 126 MB L2"},
+                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                                   "traffic": None, "kernel": "ur_to_rows_kernel" if args.direction == "to_rows" else "ur_from_rows_kernel",
+                                   "algorithmic_bytes_per_row": bpr, "peak_source": peak_src},
+                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the CPU implementation of the path on the host cores (oracle port: the reference's own
     code needs a JVM + libcudf, neither exists here).  Rank 0 only."""
@@ -1104,6 +1176,9 @@ def main():
     elif wl.get("partition"):
         if rank == 0:
             run_partition(args, wl, rank, world)
+    elif wl.get("unsafe"):
+        if rank == 0:
+            run_unsafe(args, wl, rank, world)
     elif args.workload == "c3":
         run_c3(args, wl, rank, world)
     else:

@@ -31,6 +31,8 @@
 
 namespace srj {
 
+constexpr int kUrStage   = 12 * 1024;  // shared-memory stage of a warp: its 32 rows when they are <= 384 bytes on average
+constexpr int kUrBatch   = 16;         // fields whose column loads are in flight together (to_rows)
 constexpr int kUrMaxCols = 256;  // fields of an UnsafeRow schema handled here (descriptor table in constant kernel parameters)
 
 enum UrKind : int32_t { kUrFixed = 0, kUrString = 1, kUrDec128 = 2 };
@@ -99,18 +101,54 @@ __global__ void __launch_bounds__(256) ur_sizes_kernel(const UrTable t, int64_t 
 __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_t n, const int32_t* __restrict__ row_offsets, int64_t row_stride,
                                                         uint8_t* __restrict__ rows)
 {
-  const int64_t r = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (r >= n) return;
-  uint8_t* row      = rows + (row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride);
-  uint64_t* slots   = reinterpret_cast<uint64_t*>(row + t.bitset_bytes);
+  // The 32 rows of a warp are one contiguous byte range of the output: when it fits the warp's shared-memory stage the
+  // rows are assembled there (a thread walking its row touches shared memory, not 32 scattered sectors per instruction)
+  // and leave with coalesced 8-byte stores; larger ranges are written in place.
+  extern __shared__ __align__(16) uint8_t s_stage[];
+  UrCol* s_cols = reinterpret_cast<UrCol*>(s_stage + 8 * kUrStage);       // the column descriptors, once per CTA
+  for (int i = threadIdx.x; i < t.ncols; i += 256) s_cols[i] = t.cols[i];
+  __syncthreads();
+  const int lane = lane_id();
+  for (int64_t blk = blockIdx.x; blk * 256 < n; blk += gridDim.x) {
+  const int64_t r     = blk * 256 + threadIdx.x;
+  const int64_t rw0   = r - lane;                                          // first row of the warp
+  if (rw0 >= n) continue;
+  __syncwarp();
+  const int64_t rw1   = tmin<int64_t>(n, rw0 + 32);
+  const int64_t b0    = row_offsets ? static_cast<int64_t>(row_offsets[rw0]) : rw0 * row_stride;
+  const int64_t b1    = row_offsets ? static_cast<int64_t>(row_offsets[rw1]) : rw1 * row_stride;
+  const bool staged   = b1 - b0 <= kUrStage;
+  uint8_t* wstage     = s_stage + static_cast<size_t>(warp_id()) * kUrStage;
+  if (r < n) {
+  const int64_t myoff = row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride;
+  uint8_t* row        = staged ? wstage + (myoff - b0) : rows + myoff;
+  uint64_t* slots     = reinterpret_cast<uint64_t*>(row + t.bitset_bytes);
   uint32_t cursor   = static_cast<uint32_t>(t.fixed_bytes);
   uint64_t nullbits = 0;
-  for (int c = 0; c < t.ncols; ++c) {
-    const UrCol col  = t.cols[c];
-    const bool valid = ur_valid(col.mask, r);
+  // the column loads of kUrBatch fields are issued together (a thread walking its fields one dependent load at a time is
+  // bound by DRAM latency): values are read whether or not the field is valid, the slot keeps 0 for a NULL
+  for (int c0 = 0; c0 < t.ncols; c0 += kUrBatch) {
+  uint64_t pv[kUrBatch];
+  bool pvalid[kUrBatch];
+#pragma unroll
+  for (int j = 0; j < kUrBatch; ++j) {
+    pv[j]     = 0;
+    pvalid[j] = false;
+    if (c0 + j < t.ncols) {
+      const UrCol pc = s_cols[c0 + j];
+      pvalid[j]      = ur_valid(pc.mask, r);
+      if (pc.kind == kUrFixed) pv[j] = ur_load_fixed(pc, r);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kUrBatch; ++j) {
+    const int c = c0 + j;
+    if (c >= t.ncols) break;
+    const UrCol col  = s_cols[c];
+    const bool valid = pvalid[j];
     uint64_t slot    = 0;
     if (col.kind == kUrFixed) {
-      if (valid) slot = ur_load_fixed(col, r);
+      if (valid) slot = pv[j];
     } else if (col.kind == kUrString) {
       if (valid) {
         const int32_t o0 = col.offsets[r], len = col.offsets[r + 1] - o0;
@@ -144,6 +182,15 @@ __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_
       nullbits                                = 0;
     }
   }
+  }
+  }
+  if (staged) {
+    __syncwarp();
+    uint64_t* g        = reinterpret_cast<uint64_t*>(rows + b0);
+    const uint64_t* sm = reinterpret_cast<const uint64_t*>(wstage);
+    for (int64_t i = lane; i < (b1 - b0) >> 3; i += 32) g[i] = sm[i];
+  }
+  }
 }
 
 // ---- rows -> columns (slots) ---------------------------------------------------------------------------------------------
@@ -162,14 +209,40 @@ __global__ void __launch_bounds__(256) ur_from_rows_kernel(const UrOutTable t, i
                                                           const int32_t* __restrict__ row_offsets, int64_t row_stride,
                                                           unsigned long long* __restrict__ null_counts)
 {
-  const int64_t r  = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  extern __shared__ __align__(16) uint8_t s_stage[];
+  // the column descriptors and the CTA's null counts live in shared memory behind the warps' stages
+  UrOut* s_cols = reinterpret_cast<UrOut*>(s_stage + 8 * kUrStage);
+  int* s_nulls  = reinterpret_cast<int*>(s_cols + t.ncols);
+  for (int i = threadIdx.x; i < t.ncols; i += 256) {
+    s_cols[i]  = t.cols[i];
+    s_nulls[i] = 0;
+  }
+  __syncthreads();
+  const int lane = lane_id();
+  for (int64_t blk = blockIdx.x; blk * 256 < n; blk += gridDim.x) {
+  const int64_t r  = blk * 256 + threadIdx.x;
   const bool live  = r < n;
-  const uint8_t* row = rows + (live ? (row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride) : 0);
+  const int64_t rw0 = r - lane;
+  if (rw0 >= n) continue;   // whole warp past the end
+  __syncwarp();             // the previous block's reads of this warp's stage are done
+  const int64_t rw1 = tmin<int64_t>(n, rw0 + 32);
+  const int64_t b0  = row_offsets ? static_cast<int64_t>(row_offsets[rw0]) : rw0 * row_stride;
+  const int64_t b1  = row_offsets ? static_cast<int64_t>(row_offsets[rw1]) : rw1 * row_stride;
+  const bool staged = b1 - b0 <= kUrStage;
+  uint8_t* wstage   = s_stage + static_cast<size_t>(warp_id()) * kUrStage;
+  if (staged) {   // the warp's 32 rows are one contiguous byte range: coalesced into shared memory, parsed from there
+    const uint64_t* g = reinterpret_cast<const uint64_t*>(rows + b0);
+    uint64_t* sm      = reinterpret_cast<uint64_t*>(wstage);
+    for (int64_t i = lane; i < (b1 - b0) >> 3; i += 32) sm[i] = g[i];
+    __syncwarp();
+  }
+  const int64_t myoff = live ? (row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride) : b0;
+  const uint8_t* row  = staged ? wstage + (myoff - b0) : rows + myoff;
   const uint64_t* slots = reinterpret_cast<const uint64_t*>(row + t.bitset_bytes);
   uint64_t nullbits = 0;
   for (int c = 0; c < t.ncols; ++c) {
     if ((c & 63) == 0) nullbits = live ? reinterpret_cast<const uint64_t*>(row)[c >> 6] : 0;
-    const UrOut col   = t.cols[c];
+    const UrOut col   = s_cols[c];
     const bool valid  = live && !((nullbits >> (c & 63)) & 1ull);
     const uint64_t sl = live ? slots[c] : 0;
     if (live) {
@@ -201,15 +274,18 @@ __global__ void __launch_bounds__(256) ur_from_rows_kernel(const UrOutTable t, i
       }
     }
     const unsigned word = __ballot_sync(0xffffffffu, valid);
-    if (lane_id() == 0 && r < n) {
+    if (lane == 0 && r < n) {
       if (col.mask) col.mask[r >> 5] = word;
-      if (null_counts) {
-        const int rows_here = static_cast<int>(tmin<int64_t>(32, n - r));
-        const int nulls     = rows_here - __popc(word);
-        if (nulls) atomicAdd(null_counts + c, static_cast<unsigned long long>(nulls));
-      }
+      const int rows_here = static_cast<int>(tmin<int64_t>(32, n - r));
+      const int nulls     = rows_here - __popc(word);
+      if (nulls) atomicAdd(&s_nulls[c], nulls);
     }
   }
+  }
+  __syncthreads();
+  if (null_counts)
+    for (int i = threadIdx.x; i < t.ncols; i += 256)
+      if (s_nulls[i]) atomicAdd(null_counts + i, static_cast<unsigned long long>(s_nulls[i]));
 }
 
 // chars of one STRING column: a warp per 32 rows, lane = destination byte (the rows' strings are contiguous in the
@@ -243,6 +319,8 @@ __global__ void __launch_bounds__(256) ur_chars_kernel(const uint8_t* __restrict
     }
   }
 }
+
+static unsigned ur_grid(int64_t n) { return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8))); }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
 static bool ur_classify(int32_t type_id, int32_t* kind, int32_t* width, int32_t* sext)
@@ -337,7 +415,9 @@ int launch_unsafe_to_rows(const srj_column* cols, int32_t ncols, int64_t n, cons
   const int rc = ur_upload(cols, ncols, workspace, &t, stream);
   if (rc != SRJ_OK) return rc;
   if (n == 0) return SRJ_OK;
-  ur_to_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(t, n, d_row_offsets, t.fixed_bytes + 16 * t.ndec, rows);
+  const size_t smem = 8 * kUrStage + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
+  SRJ_CUDA_TRY(cudaFuncSetAttribute(ur_to_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kUrStage + kUrMaxCols * (sizeof(UrCol) + 4) + 16));
+  ur_to_rows_kernel<<<ur_grid(n), 256, smem, stream>>>(t, n, d_row_offsets, t.fixed_bytes + 16 * t.ndec, rows);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }
@@ -353,7 +433,9 @@ int launch_unsafe_from_rows(const srj_column* out, int32_t ncols, int64_t n, con
   int32_t* sums = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + kUrMaxCols * sizeof(UrCol) + 64);
   if (n > 0) {
     UrOutTable ot{reinterpret_cast<UrOut*>(t.cols), t.ncols, t.bitset_bytes, t.fixed_bytes, t.ndec};
-    ur_from_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ot, n, rows, d_row_offsets, t.fixed_bytes + 16 * t.ndec,
+    const size_t smem = 8 * kUrStage + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
+    SRJ_CUDA_TRY(cudaFuncSetAttribute(ur_from_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kUrStage + kUrMaxCols * (sizeof(UrCol) + 4) + 16));
+    ur_from_rows_kernel<<<ur_grid(n), 256, smem, stream>>>(ot, n, rows, d_row_offsets, t.fixed_bytes + 16 * t.ndec,
                                                                                    reinterpret_cast<unsigned long long*>(d_null_counts));
     SRJ_CUDA_TRY(cudaGetLastError());
   }
