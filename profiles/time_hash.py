@@ -33,7 +33,7 @@ for name, fn, outb in (("xxhash64", lambda: S.Hash.xxhash64(42, cols), 8), ("mur
     ms = timeit(fn)
     byts = n * (12 + 0.25 + outb)
     print(f"{name:9s} keys(int32,int64) rows={n} ms={ms:.3f} GB/s={byts / ms / 1e6:.0f} frac={byts / ms / 1e6 / 6576.1:.3f} rows/s={n / ms * 1e3:.3g}")
-ns = n // 5
+ns = int(os.environ.get("SRJ_TH_STR_ROWS", n // 5))
 sc = bench.synth_strings_gpu(torch, S, ns, 0.2, g)
 chars = sc.data.numel()
 for name, fn, outb in (("xxhash64", lambda: S.Hash.xxhash64(42, [sc]), 8), ("murmur3", lambda: S.Hash.murmurHash32(42, [sc]), 4),
