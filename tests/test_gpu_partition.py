@@ -114,3 +114,40 @@ def test_partition_is_a_permutation_at_scale():
     assert bool((pid_sorted[1:] >= pid_sorted[:-1]).all())                                        # grouped by partition
     same = pid_sorted[1:] == pid_sorted[:-1]
     assert bool((gmap[1:][same] > gmap[:-1][same]).all())                                         # stable inside a partition
+
+
+def test_concurrent_callers_on_their_own_streams():
+    """Spark task threads: 8 threads partition and UnsafeRow-convert their own tables concurrently (no shared state in
+    the library: every scratch buffer is the caller's)."""
+    import threading
+    G = _gpu()
+    import srj_b200 as S
+    from srj_b200.partitioning import HashPartitioner
+    from srj_b200.unsaferow import UnsafeRowConversion as UR
+    from oracle import unsafe_row as U
+    types = [O.INT32, O.STRING, O.INT64, O.DECIMAL128]
+    errors = []
+
+    def work(i):
+        try:
+            cols = random_table(types, 3000 + 17 * i, seed=100 + i)
+            ids = O.partition_ids([cols[0], cols[1]], 11 + i)
+            want_cols, want_offs, _ = O.stable_partition(cols, ids, 11 + i)
+            uoffs, udata = U.to_unsafe_rows(cols)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for _ in range(5):
+                    dt = G.table_to_device(cols)
+                    pt = HashPartitioner.partition(dt, [0, 1], 11 + i)
+                    assert pt.getPartitions() == want_offs[:-1].tolist()
+                    for g, w in zip(pt.getTable().columns, want_cols):
+                        assert cols_equal(G.to_host(g), w)
+                    rows = UR.convertToRows(dt)
+                    goffs, gdata = G.rows_to_host(rows)
+                    assert np.array_equal(goffs.astype(np.int64), uoffs) and np.array_equal(gdata, udata)
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errors, errors
