@@ -99,13 +99,13 @@ __global__ void __launch_bounds__(256) ur_sizes_kernel(const UrTable t, int64_t 
 
 // ---- columns -> rows -----------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_t n, const int32_t* __restrict__ row_offsets, int64_t row_stride,
-                                                        uint8_t* __restrict__ rows)
+                                                        uint8_t* __restrict__ rows, int stage)
 {
   // The 32 rows of a warp are one contiguous byte range of the output: when it fits the warp's shared-memory stage the
   // rows are assembled there (a thread walking its row touches shared memory, not 32 scattered sectors per instruction)
   // and leave with coalesced 8-byte stores; larger ranges are written in place.
   extern __shared__ __align__(16) uint8_t s_stage[];
-  UrCol* s_cols = reinterpret_cast<UrCol*>(s_stage + 8 * kUrStage);       // the column descriptors, once per CTA
+  UrCol* s_cols = reinterpret_cast<UrCol*>(s_stage + 8 * stage);       // the column descriptors, once per CTA
   for (int i = threadIdx.x; i < t.ncols; i += 256) s_cols[i] = t.cols[i];
   __syncthreads();
   const int lane = lane_id();
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_
   const int64_t rw1   = tmin<int64_t>(n, rw0 + 32);
   const int64_t b0    = row_offsets ? static_cast<int64_t>(row_offsets[rw0]) : rw0 * row_stride;
   const int64_t b1    = row_offsets ? static_cast<int64_t>(row_offsets[rw1]) : rw1 * row_stride;
-  const bool staged   = b1 - b0 <= kUrStage;
-  uint8_t* wstage     = s_stage + static_cast<size_t>(warp_id()) * kUrStage;
+  const bool staged   = b1 - b0 <= stage;
+  uint8_t* wstage     = s_stage + static_cast<size_t>(warp_id()) * stage;
   if (r < n) {
   const int64_t myoff = row_offsets ? static_cast<int64_t>(row_offsets[r]) : r * row_stride;
   uint8_t* row        = staged ? wstage + (myoff - b0) : rows + myoff;
@@ -129,14 +129,14 @@ __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_
   // bound by DRAM latency): values are read whether or not the field is valid, the slot keeps 0 for a NULL
   for (int c0 = 0; c0 < t.ncols; c0 += kUrBatch) {
   uint64_t pv[kUrBatch];
-  bool pvalid[kUrBatch];
+  uint32_t pmask[kUrBatch];   // the mask WORDS: tested only after every load of the batch is in flight
 #pragma unroll
   for (int j = 0; j < kUrBatch; ++j) {
-    pv[j]     = 0;
-    pvalid[j] = false;
+    pv[j]    = 0;
+    pmask[j] = 0xffffffffu;
     if (c0 + j < t.ncols) {
       const UrCol pc = s_cols[c0 + j];
-      pvalid[j]      = ur_valid(pc.mask, r);
+      if (pc.mask) pmask[j] = __ldg(pc.mask + (r >> 5));
       if (pc.kind == kUrFixed) pv[j] = ur_load_fixed(pc, r);
     }
   }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) ur_to_rows_kernel(const UrTable t, int64_
     const int c = c0 + j;
     if (c >= t.ncols) break;
     const UrCol col  = s_cols[c];
-    const bool valid = pvalid[j];
+    const bool valid = (pmask[j] >> (r & 31)) & 1u;
     uint64_t slot    = 0;
     if (col.kind == kUrFixed) {
       if (valid) slot = pv[j];
@@ -207,11 +207,11 @@ struct UrOutTable {
 
 __global__ void __launch_bounds__(256) ur_from_rows_kernel(const UrOutTable t, int64_t n, const uint8_t* __restrict__ rows,
                                                           const int32_t* __restrict__ row_offsets, int64_t row_stride,
-                                                          unsigned long long* __restrict__ null_counts)
+                                                          unsigned long long* __restrict__ null_counts, int stage)
 {
   extern __shared__ __align__(16) uint8_t s_stage[];
   // the column descriptors and the CTA's null counts live in shared memory behind the warps' stages
-  UrOut* s_cols = reinterpret_cast<UrOut*>(s_stage + 8 * kUrStage);
+  UrOut* s_cols = reinterpret_cast<UrOut*>(s_stage + 8 * stage);
   int* s_nulls  = reinterpret_cast<int*>(s_cols + t.ncols);
   for (int i = threadIdx.x; i < t.ncols; i += 256) {
     s_cols[i]  = t.cols[i];
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(256) ur_from_rows_kernel(const UrOutTable t, i
   const int64_t rw1 = tmin<int64_t>(n, rw0 + 32);
   const int64_t b0  = row_offsets ? static_cast<int64_t>(row_offsets[rw0]) : rw0 * row_stride;
   const int64_t b1  = row_offsets ? static_cast<int64_t>(row_offsets[rw1]) : rw1 * row_stride;
-  const bool staged = b1 - b0 <= kUrStage;
-  uint8_t* wstage   = s_stage + static_cast<size_t>(warp_id()) * kUrStage;
+  const bool staged = b1 - b0 <= stage;
+  uint8_t* wstage   = s_stage + static_cast<size_t>(warp_id()) * stage;
   if (staged) {   // the warp's 32 rows are one contiguous byte range: coalesced into shared memory, parsed from there
     const uint64_t* g = reinterpret_cast<const uint64_t*>(rows + b0);
     uint64_t* sm      = reinterpret_cast<uint64_t*>(wstage);
@@ -318,6 +318,14 @@ __global__ void __launch_bounds__(256) ur_chars_kernel(const uint8_t* __restrict
       if (q < T) out_chars[ob + q] = *reinterpret_cast<const uint8_t*>(sj + (q - pj));
     }
   }
+}
+
+// shared-memory stage of a warp: its 32 rows.  Fixed-size rows: exactly that (more CTAs stay resident); rows with
+// strings: kUrStage (larger 32-row ranges are handled in place)
+static int ur_stage(const int32_t* d_row_offsets, int fixed_row_bytes)
+{
+  if (d_row_offsets) return kUrStage;
+  return std::min(kUrStage, (32 * fixed_row_bytes + 15) & ~15);
 }
 
 static unsigned ur_grid(int64_t n) { return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8))); }
@@ -415,9 +423,10 @@ int launch_unsafe_to_rows(const srj_column* cols, int32_t ncols, int64_t n, cons
   const int rc = ur_upload(cols, ncols, workspace, &t, stream);
   if (rc != SRJ_OK) return rc;
   if (n == 0) return SRJ_OK;
-  const size_t smem = 8 * kUrStage + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
+  const int stage   = ur_stage(d_row_offsets, t.fixed_bytes + 16 * t.ndec);
+  const size_t smem = 8 * static_cast<size_t>(stage) + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
   SRJ_CUDA_TRY(cudaFuncSetAttribute(ur_to_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kUrStage + kUrMaxCols * (sizeof(UrCol) + 4) + 16));
-  ur_to_rows_kernel<<<ur_grid(n), 256, smem, stream>>>(t, n, d_row_offsets, t.fixed_bytes + 16 * t.ndec, rows);
+  ur_to_rows_kernel<<<ur_grid(n), 256, smem, stream>>>(t, n, d_row_offsets, t.fixed_bytes + 16 * t.ndec, rows, stage);
   SRJ_CUDA_TRY(cudaGetLastError());
   return SRJ_OK;
 }
@@ -433,10 +442,11 @@ int launch_unsafe_from_rows(const srj_column* out, int32_t ncols, int64_t n, con
   int32_t* sums = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(workspace) + kUrMaxCols * sizeof(UrCol) + 64);
   if (n > 0) {
     UrOutTable ot{reinterpret_cast<UrOut*>(t.cols), t.ncols, t.bitset_bytes, t.fixed_bytes, t.ndec};
-    const size_t smem = 8 * kUrStage + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
+    const int stage   = ur_stage(d_row_offsets, t.fixed_bytes + 16 * t.ndec);
+    const size_t smem = 8 * static_cast<size_t>(stage) + static_cast<size_t>(ncols) * (sizeof(UrCol) + 4) + 16;
     SRJ_CUDA_TRY(cudaFuncSetAttribute(ur_from_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kUrStage + kUrMaxCols * (sizeof(UrCol) + 4) + 16));
     ur_from_rows_kernel<<<ur_grid(n), 256, smem, stream>>>(ot, n, rows, d_row_offsets, t.fixed_bytes + 16 * t.ndec,
-                                                                                   reinterpret_cast<unsigned long long*>(d_null_counts));
+                                                                                   reinterpret_cast<unsigned long long*>(d_null_counts), stage);
     SRJ_CUDA_TRY(cudaGetLastError());
   }
   for (int c = 0; c < ncols; ++c) {
