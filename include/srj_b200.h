@@ -254,6 +254,33 @@ SRJ_API int srj_partition_columns(const srj_column* in, const srj_column* out, i
 SRJ_API int srj_partition_strings(const srj_column* in, const srj_column* out, int32_t num_columns, int64_t num_rows,
                                   const int32_t* d_gather_map, void* stream);
 
+/* ---- Kudo shuffle wire format: split / assemble -------------------------------------------------
+ * shuffle_split / shuffle_assemble of the reference (src/main/cpp/src/shuffle_split.hpp:60-189) for FLAT tables
+ * (fixed-width, decimal, STRING columns): a table is cut at `splits` (P + 1 row indices, e.g. the partition offsets
+ * of srj_hash_partition) into P partitions written back to back, each in the Kudo format of
+ * kudo/KudoSerializer.java:49-171 (header "KUD0" + 6 big-endian ints + hasValidity bits | validity | offsets | data);
+ * assemble concatenates partitions (of one or several splits) back into one table.
+ *   srj_kudo_split_sizes    : d_partition_offsets[P + 1] (byte offset of every partition) and *total_bytes (host; one
+ *                             stream synchronisation).
+ *   srj_kudo_split          : writes the partitions into `out` (total_bytes, 4-byte aligned).
+ *   srj_kudo_assemble_sizes : parses the headers; *total_rows and, per STRING column, char_totals[c] (host arrays);
+ *                             SRJ_EINVAL on a malformed header.  The workspace keeps what srj_kudo_assemble needs.
+ *   srj_kudo_assemble       : fills `out` (total_rows rows per column; null masks, where given, are produced for every
+ *                             column -- partitions without validity contribute valid rows).
+ * <= 256 columns, <= 65535 partitions.  LIST / STRUCT columns are not supported (SRJ_EUNSUPPORTED).
+ */
+SRJ_API int64_t srj_kudo_workspace_bytes(int32_t num_columns, int32_t num_partitions);
+SRJ_API int srj_kudo_split_sizes(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_splits,
+                                 int32_t num_partitions, int64_t* d_partition_offsets, int64_t* total_bytes, void* workspace,
+                                 void* stream);
+SRJ_API int srj_kudo_split(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_splits,
+                           int32_t num_partitions, const int64_t* d_partition_offsets, uint8_t* out, void* workspace, void* stream);
+SRJ_API int srj_kudo_assemble_sizes(const uint8_t* partitions, const int64_t* d_partition_offsets, int32_t num_partitions,
+                                    const int32_t* type_ids, int32_t num_columns, int64_t* total_rows, int64_t* char_totals,
+                                    void* workspace, void* stream);
+SRJ_API int srj_kudo_assemble(const uint8_t* partitions, const int64_t* d_partition_offsets, int32_t num_partitions,
+                              const srj_column* out, int32_t num_columns, int64_t total_rows, void* workspace, void* stream);
+
 /* ---- Apache Spark UnsafeRow codec -----------------------------------------------------------
  * The row format Spark's own operators consume (org.apache.spark.sql.catalyst.expressions.UnsafeRow /
  * codegen.UnsafeRowWriter); the reference speaks only JCUDF (RowConversion.java:44-117) and leaves the adaptation to

@@ -816,4 +816,72 @@ int srj_convert_from_unsafe_rows_strings(const uint8_t* rows, const int32_t* d_r
   return launch_unsafe_from_rows_strings(out, num_columns, num_rows, rows, d_row_offsets, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Kudo shuffle wire format: split / assemble (kudo.cu)
+// ---------------------------------------------------------------------------------------------------
+int64_t srj_kudo_workspace_bytes(int32_t num_columns, int32_t num_partitions) { return kudo_workspace_bytes(std::max(num_columns, 0), std::max(num_partitions, 0)); }
+
+static int kudo_check(const char* what, int32_t ncols, int32_t P, const void* a, const void* b, const void* ws)
+{
+  if (ncols <= 0 || P < 0 || !a || !b || !ws) { set_error("%s: bad argument", what); return SRJ_EINVAL; }
+  if (ncols > 256 || P > 65535) { set_error("%s: at most 256 columns and 65535 partitions", what); return SRJ_EUNSUPPORTED; }
+  return SRJ_OK;
+}
+
+int srj_kudo_split_sizes(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_splits, int32_t num_partitions,
+                         int64_t* d_partition_offsets, int64_t* total_bytes, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = kudo_check("kudo_split_sizes", num_columns, num_partitions, cols, d_partition_offsets, workspace);
+  if (rc != SRJ_OK) return rc;
+  if (!d_splits || !total_bytes || num_rows < 0 || num_rows > INT32_MAX) { set_error("kudo_split_sizes: bad argument"); return SRJ_EINVAL; }
+  for (int32_t c = 0; c < num_columns; ++c)
+    if (cols[c].size != num_rows) { set_error("kudo_split_sizes: column %d: row count mismatch", c); return SRJ_EINVAL; }
+  rc = launch_kudo_split_sizes(cols, num_columns, d_splits, num_partitions, d_partition_offsets, total_bytes, workspace, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EUNSUPPORTED) set_error("kudo_split_sizes: only fixed-width, decimal and STRING columns");
+  return rc;
+}
+
+int srj_kudo_split(const srj_column* cols, int32_t num_columns, int64_t num_rows, const int32_t* d_splits, int32_t num_partitions,
+                   const int64_t* d_partition_offsets, uint8_t* out, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = kudo_check("kudo_split", num_columns, num_partitions, cols, d_partition_offsets, workspace);
+  if (rc != SRJ_OK) return rc;
+  if (!d_splits || (num_partitions > 0 && !out) || (reinterpret_cast<uintptr_t>(out) & 3)) { set_error("kudo_split: out must be a 4-byte aligned device buffer"); return SRJ_EINVAL; }
+  if (num_partitions == 0) return SRJ_OK;
+  (void)num_rows;
+  rc = launch_kudo_split(cols, num_columns, d_splits, num_partitions, d_partition_offsets, out, workspace, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EUNSUPPORTED) set_error("kudo_split: only fixed-width, decimal and STRING columns");
+  return rc;
+}
+
+int srj_kudo_assemble_sizes(const uint8_t* partitions, const int64_t* d_partition_offsets, int32_t num_partitions, const int32_t* type_ids,
+                            int32_t num_columns, int64_t* total_rows, int64_t* char_totals, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = kudo_check("kudo_assemble_sizes", num_columns, num_partitions, type_ids, d_partition_offsets, workspace);
+  if (rc != SRJ_OK) return rc;
+  if ((num_partitions > 0 && !partitions) || !total_rows || !char_totals) { set_error("kudo_assemble_sizes: bad argument"); return SRJ_EINVAL; }
+  rc = launch_kudo_assemble_sizes(partitions, d_partition_offsets, num_partitions, type_ids, num_columns, total_rows, char_totals, workspace,
+                                  static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EINVAL) set_error("kudo_assemble_sizes: a partition does not start with a Kudo header of %d columns", num_columns);
+  else if (rc == SRJ_EUNSUPPORTED) set_error("kudo_assemble_sizes: only fixed-width, decimal and STRING columns");
+  else if (rc == SRJ_OK && *total_rows > INT32_MAX) { set_error("kudo_assemble_sizes: %lld rows exceed a column", static_cast<long long>(*total_rows)); return SRJ_EOVERFLOW; }
+  return rc;
+}
+
+int srj_kudo_assemble(const uint8_t* partitions, const int64_t* d_partition_offsets, int32_t num_partitions, const srj_column* out,
+                      int32_t num_columns, int64_t total_rows, void* workspace, void* stream)
+{
+  SRJ_API_RANGE();
+  int rc = kudo_check("kudo_assemble", num_columns, num_partitions, out, d_partition_offsets, workspace);
+  if (rc != SRJ_OK) return rc;
+  for (int32_t c = 0; c < num_columns; ++c)
+    if (out[c].size != total_rows) { set_error("kudo_assemble: column %d: expected %lld rows", c, static_cast<long long>(total_rows)); return SRJ_EINVAL; }
+  rc = launch_kudo_assemble(partitions, d_partition_offsets, num_partitions, out, num_columns, total_rows, workspace, static_cast<cudaStream_t>(stream));
+  if (rc == SRJ_EUNSUPPORTED) set_error("kudo_assemble: only fixed-width, decimal and STRING columns");
+  return rc;
+}
+
 }  // extern "C"

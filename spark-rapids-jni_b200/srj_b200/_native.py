@@ -78,6 +78,14 @@ SYMBOLS = {
     "srj_convert_from_unsafe_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_int32, C.c_void_p, C.c_void_p,
                                                C.c_void_p]),
     "srj_convert_from_unsafe_rows_strings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SrjColumn), C.c_int32, C.c_void_p]),
+    "srj_kudo_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "srj_kudo_split_sizes": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int64),
+                                       C.c_void_p, C.c_void_p]),
+    "srj_kudo_split": (C.c_int, [C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "srj_kudo_assemble_sizes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "srj_kudo_assemble": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SrjColumn), C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     "srj_shard_rebase_offsets": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_void_p]),
     "srj_convert_from_rows_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(SrjColumn),
