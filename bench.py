@@ -71,6 +71,9 @@ WORKLOADS = {
                            "+ stable partition of every column",
                       types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, hash_keys=[1, 9], partitions=200,
                       partition=True),
+    # the Kudo shuffle wire format of the same store_sales batch, cut into 200 partitions
+    "kudo": dict(name="Kudo split / assemble: TPC-DS store_sales (23 cols, 96 data B/row, 4% nulls), 200 partitions",
+                 types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, partitions=200, kudo=True),
     # the same C2 table through Apache Spark's UnsafeRow format (264 B rows: 8 B bitset + 32 slots)
     "unsafe_c2": dict(name="UnsafeRow codec: 50M rows x 32 fixed-width cols ([INT8,INT16,INT32,INT64,FLOAT32,FLOAT64,BOOL8,TIMESTAMP_US]x4), "
                            "264 B UnsafeRows, 20% nulls", types=[INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US] * 4,
@@ -1013,6 +1016,72 @@ def run_partition(args, wl, rank, world):
                       "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
 
 
+def run_kudo(args, wl, rank, world):
+    """shuffle_split / shuffle_assemble of a device-resident table; --direction to_rows = split (default), from_rows = assemble."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "spark-rapids-jni_b200"))
+    import srj_b200 as S
+    from srj_b200 import _native as N
+    torch.cuda.set_device(0)
+    types, n, P = wl["types"], args.rows or wl["rows"], wl["partitions"]
+    cols = synth_columns_gpu(torch, S, types, n, wl["null_frac"], 42)
+    lib = N.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    splits = torch.linspace(0, n, P + 1, device="cuda").to(torch.int32)
+    splits[-1] = n
+    ws = torch.empty(lib.srj_kudo_workspace_bytes(len(cols), P), dtype=torch.uint8, device="cuda")
+    offs = torch.empty(P + 1, dtype=torch.int64, device="cuda")
+    total = ctypes.c_int64(0)
+    cin = (N.SrjColumn * len(cols))(*[c._c() for c in cols])
+    N.check(lib.srj_kudo_split_sizes(cin, len(cols), n, splits.data_ptr(), P, offs.data_ptr(), ctypes.byref(total), ws.data_ptr(), st))
+    buf = torch.empty(total.value, dtype=torch.uint8, device="cuda")
+    words = (n + 31) // 32
+    outs = [S.ColumnVector(c.dtype, n, torch.empty_like(c.data), torch.empty(words, dtype=torch.int32, device="cuda")) for c in cols]
+    cout = (N.SrjColumn * len(cols))(*[c._c() for c in outs])
+    ids = (C_int32 * len(types))(*types)
+    rows = ctypes.c_int64(0)
+    chars = (ctypes.c_int64 * len(types))()
+
+    def split():
+        N.check(lib.srj_kudo_split(cin, len(cols), n, splits.data_ptr(), P, offs.data_ptr(), buf.data_ptr(), ws.data_ptr(), st))
+
+    def assemble():
+        N.check(lib.srj_kudo_assemble(buf.data_ptr(), offs.data_ptr(), P, cout, len(cols), n, ws.data_ptr(), st))
+
+    split()
+    N.check(lib.srj_kudo_assemble_sizes(buf.data_ptr(), offs.data_ptr(), P, ids, len(types), ctypes.byref(rows), chars, ws.data_ptr(), st))
+    assert rows.value == n
+    assemble()
+    torch.cuda.synchronize()
+    for i in (0, 9, 22):                                     # assemble(split(x)) = x: data and masks of three columns
+        assert torch.equal(outs[i].data, cols[i].data) and torch.equal(outs[i].mask, cols[i].mask)
+    step = assemble if args.direction == "from_rows" else split
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(0)
+    sampler.start()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, peak_src = load_peaks()
+    bpr = 2 * (sum(SIZE[t] for t in types) + len(types) / 8.0)     # the table once, the partitions once
+    gbs = bpr * n / (ms * 1e-3) / 1e9
+    what = "assemble" if args.direction == "from_rows" else "split"
+    print(json.dumps({"metric": f"rows_per_sec_kudo_{what}", "value": n / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+                      "data": "synthetic", "config": {"workload": wl["name"], "rows": n, "partitions": P, "buffer_bytes": total.value,
+                                                      "l2": "table 9.6 GB + buffer 9.9 GB >> 126 MB L2"},
+                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": None,
+                                   "kernel": f"kudo_{what}_kernel", "algorithmic_bytes_per_row": bpr, "peak_source": peak_src},
+                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
+
+
 def run_unsafe(args, wl, rank, world):
     """columns <-> UnsafeRow on one GPU, inputs resident in HBM; --direction picks the timed side."""
     import torch
@@ -1159,7 +1228,7 @@ def main():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=16_000_000)
-    ap.add_argument("--direction", default="from_rows", choices=["from_rows", "to_rows"])
+    ap.add_argument("--direction", default="from_rows", choices=["from_rows", "to_rows"])  # kudo: to_rows = split, from_rows = assemble
     ap.add_argument("--no-gather", action="store_true", help="multi-GPU: skip the all-gather (conversion-only scaling)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU all-gather transport: copy engines over NVLink peer memory (default) or ncclAllGather")
@@ -1176,6 +1245,9 @@ def main():
     elif wl.get("partition"):
         if rank == 0:
             run_partition(args, wl, rank, world)
+    elif wl.get("kudo"):
+        if rank == 0:
+            run_kudo(args, wl, rank, world)
     elif wl.get("unsafe"):
         if rank == 0:
             run_unsafe(args, wl, rank, world)

@@ -52,30 +52,33 @@ __device__ __forceinline__ void kudo_col_sizes(const KCol& c, int32_t s, int32_t
   }
 }
 
-// cooperative byte copy by the CTA: 16-byte, 4-byte or single-byte accesses, whatever both addresses allow
+// cooperative byte copy by the CTA.  The destination is written with aligned 16-byte stores; the source is read with
+// aligned 16-byte loads when it is congruent to the destination mod 16, else as aligned 32-bit words funnel-shifted
+// into place (the buffers of a Kudo partition have no alignment guarantees: KudoSerializer.java:157-159).
 __device__ void cta_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t n)
 {
   const int tid = threadIdx.x, nt = blockDim.x;
   if (n <= 0) return;
-  const uintptr_t da = reinterpret_cast<uintptr_t>(dst), sa = reinterpret_cast<uintptr_t>(src);
-  const int g = ((da ^ sa) & 15) == 0 ? 16 : ((da ^ sa) & 3) == 0 ? 4 : 1;
-  if (g == 1) {
-    for (int64_t i = tid; i < n; i += nt) dst[i] = src[i];
-    return;
-  }
-  const int64_t head = tmin<int64_t>(n, (g - (da & (g - 1))) & (g - 1));
+  const uintptr_t da = reinterpret_cast<uintptr_t>(dst);
+  const int64_t head = tmin<int64_t>(n, (16 - (da & 15)) & 15);
   for (int64_t i = tid; i < head; i += nt) dst[i] = src[i];
-  const int64_t body = (n - head) / g;
-  if (g == 16) {
+  const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
+  int64_t body       = (n - head) >> 4;
+  uint4* d16         = reinterpret_cast<uint4*>(dst + head);
+  if ((sa & 15) == 0) {
     const uint4* s16 = reinterpret_cast<const uint4*>(src + head);
-    uint4* d16       = reinterpret_cast<uint4*>(dst + head);
     for (int64_t i = tid; i < body; i += nt) d16[i] = s16[i];
   } else {
-    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
-    uint32_t* d4       = reinterpret_cast<uint32_t*>(dst + head);
-    for (int64_t i = tid; i < body; i += nt) d4[i] = s4[i];
+    if (body > 0) --body;   // the last chunk's fifth word could lie past the source: it goes with the tail bytes
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t{3});
+    const uint32_t sh  = static_cast<uint32_t>(sa & 3) * 8u;
+    for (int64_t i = tid; i < body; i += nt) {
+      const uint32_t* w = sw + 4 * i;
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+      d16[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
   }
-  for (int64_t i = head + body * g + tid; i < n; i += nt) dst[i] = src[i];
+  for (int64_t i = head + body * 16 + tid; i < n; i += nt) dst[i] = src[i];
 }
 
 // ---- split ---------------------------------------------------------------------------------------------------------------
