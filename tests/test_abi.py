@@ -94,7 +94,7 @@ def test_library_holds_the_sm100a_kernels_and_tma_sass():
     funcs = [l for l in sass.splitlines() if "Function :" in l]
     for k in ("from_rows_kernel", "from_rows_wide_kernel", "wide_group_scan_kernel", "strings_wide_kernel", "strings_from_rows_kernel", "to_rows2_kernel", "to_rows3_kernel",
               "to_rows_w_kernel", "to_rows_kernel", "row_hash_kernel", "row_hash_plain_kernel", "row_hash_stream_kernel", "row_hash_nested_kernel",
-              "part_ids_kernel", "part_rank_kernel", "partition_move_tile_kernel", "ur_to_rows_kernel", "ur_from_rows_kernel", "ur_chars_kernel"):
+              "part_ids_kernel", "part_rank_kernel", "partition_move_tile_kernel", "ur_to_rows_kernel", "ur_from_rows_kernel", "ur_chars_kernel", "kudo_split_kernel", "kudo_assemble_kernel"):
         assert any(k in f for f in funcs), f"kernel {k} missing from the cubin"
     assert "UBLKCP" in sass, "no TMA bulk copy in the SASS"
     assert "LDGSTS" in sass, "no cp.async in the SASS"
