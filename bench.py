@@ -71,6 +71,12 @@ WORKLOADS = {
                            "+ stable partition of every column",
                       types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, hash_keys=[1, 9], partitions=200,
                       partition=True),
+    # the exchange step of the widened path: every GPU hash-partitions its store_sales batch, writes Kudo partitions, the
+    # partitions travel with ONE all_to_all_single over NVLink (NCCL), every GPU assembles what it received
+    "shuffle": dict(name="shuffle exchange: per GPU 50M store_sales rows (23 cols, 96 data B/row, 4% nulls) -> pmod(murmur3(ss_item_sk, "
+                         "ss_ticket_number)) -> Kudo split -> all_to_all_single -> assemble; 8 partitions per GPU",
+                    types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=50_000_000, null_frac=0.04, hash_keys=[1, 9], parts_per_rank=8,
+                    shuffle=True),
     # the Kudo shuffle wire format of the same store_sales batch, cut into 200 partitions
     "kudo": dict(name="Kudo split / assemble: TPC-DS store_sales (23 cols, 96 data B/row, 4% nulls), 200 partitions",
                  types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=100_000_000, null_frac=0.04, partitions=200, kudo=True),
@@ -1016,6 +1022,73 @@ def run_partition(args, wl, rank, world):
                       "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
 
 
+def run_shuffle(args, wl, rank, world):
+    """The multi-GPU exchange of the widened path through its public API (srj_b200.shuffle.ShuffleExchange), device-resident
+    input, weak scaling (rows per GPU fixed).  The collective (all_to_all_single) is inside the timed step."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "spark-rapids-jni_b200"))
+    import srj_b200 as S
+    from srj_b200.shuffle import ShuffleExchange
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29517")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    types, n, k = wl["types"], args.rows or wl["rows"], wl["parts_per_rank"]
+    cols = synth_columns_gpu(torch, S, types, n, wl["null_frac"], 42 + rank)
+    table = S.Table(cols)
+    ex = ShuffleExchange()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        return ex.shuffle(table, wl["hash_keys"], parts_per_rank=k)
+
+    out = step()
+    tot = torch.tensor([out.getRowCount()], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot)
+    assert int(tot[0]) == n * world, "rows were lost or duplicated in the exchange"
+    del out
+    for _ in range(args.warmup):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        data_b = sum(SIZE[t_] for t_ in types) + len(types) / 8.0
+        # table read + partitioned copy written and read + buffer written; buffer read + assembled table written on the other side
+        bpr = 6 * data_b
+        gbs = bpr * n / (ms * 1e-3) / 1e9
+        sent = data_b * n * (world - 1) / world                     # bytes a rank sends over NVLink per step
+        print(json.dumps({"metric": "rows_per_sec_shuffle_exchange", "value": n * world / (ms * 1e-3), "unit": "rows/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": wl["name"], "rows_per_gpu": n, "partitions": world * k,
+                                     "collective": "torch.distributed.all_to_all_single (NCCL) inside the timed step",
+                                     "l2": "every pass touches >= 4.8 GB per GPU >> 126 MB L2"},
+                          "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                                       "traffic": None, "kernel": "whole step per GPU: murmur3 + partition plan + column moves + kudo split + all-to-all + assemble",
+                                       "algorithmic_bytes_per_row": bpr, "peak_source": peak_src, "per_gpu": True,
+                                       "nvlink_send_gbs_per_gpu": round(sent / (ms * 1e-3) / 1e9, 1)},
+                          "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * 70, "clocks": clocks}))
+    dist.destroy_process_group()
+
+
 def run_kudo(args, wl, rank, world):
     """shuffle_split / shuffle_assemble of a device-resident table; --direction to_rows = split (default), from_rows = assemble."""
     import torch
@@ -1245,6 +1318,8 @@ def main():
     elif wl.get("partition"):
         if rank == 0:
             run_partition(args, wl, rank, world)
+    elif wl.get("shuffle"):
+        run_shuffle(args, wl, rank, world)
     elif wl.get("kudo"):
         if rank == 0:
             run_kudo(args, wl, rank, world)
