@@ -52,7 +52,7 @@ WORKLOADS = {
                     "convert_from_rows, 200 B rows, 20% nulls",
                types=[INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, BOOL8, TS_US] * 4, rows=100_000_000, null_frac=0.2),
     # BASELINE.json configs[3]: store_sales, from_rows fused with xxhash64(ss_item_sk, ss_ticket_number)
-    "c4": dict(name="C4: TPC-DS store_sales (23 cols, 104 B rows) convert_from_rows fused with xxhash64 partition key",
+    "c4": dict(name="C4: TPC-DS store_sales (23 cols, 104 B rows) convert_from_rows + xxhash64 partition key in one call",
                types=[INT32] * 9 + [INT64, INT32] + [DEC32] * 12, rows=400_000_000, null_frac=0.04, hash_keys=[1, 9]),
     # BASELINE.json configs[2]: 100M rows x 256 mixed cols (int32/int64/decimal128/utf8, 20% null), to+from rows.
     # ~390 GB of rows cannot be resident: a step streams 100M rows as `batches` x `batch_rows` conversions over a
@@ -353,7 +353,8 @@ def run_ours(args, wl, rank, world):
     peak, peak_src = load_peaks()
     achieved = bpr * n / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "srj::from_rows_kernel",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel": "srj::from_rows_kernel" + (" + row_hash_stream_kernel over the key columns just written (one C-ABI call)" if wl.get("hash_keys") else ""),
                 "kernel_ms": round(kern_ms, 4), "algorithmic_bytes_per_row": bpr, "rows_per_launch": n,
                 "peak_source": peak_src, "this_box_copy_gbs": box_copy_gbs(torch) if rank == 0 else None}
     tr = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
@@ -443,7 +444,7 @@ def run_ours(args, wl, rank, world):
                                      "rows were produced by srj_convert_to_rows in %d <=2GiB batches)" % nbatches,
                            "sharding": "contiguous row range per GPU, no data-path collective"},
                 "hbm_gbs": round(achieved, 1), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": args.steps, "clocks": clocks}
+                "gpu_launches": args.steps * (2 if wl.get("hash_keys") else 1), "clocks": clocks}
         if allgather:
             line["allgather"] = allgather
         print(json.dumps(line))

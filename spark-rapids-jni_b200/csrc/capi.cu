@@ -520,12 +520,26 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
     }
     if (!cols[c].null_mask && num_rows > 0) { set_error("convert_from_rows: column %d has no null mask buffer (always allocated, RC:2220)", c); return SRJ_EINVAL; }
   }
-  if (use_wide_from_rows(plan, row_offsets, hash)) {
+  // The hash of a "fused" call can run inside the conversion kernel (no extra traffic: the consumer warps hash the key
+  // fields they already hold) or as the streaming hash kernel over the key columns just written (12 more bytes per row
+  // for two integer keys, but the conversion kernel keeps its issue slots for the transpose and the hash its own kernel
+  // shape).  SRJ_FUSE_SPLIT picks the second; it also lets wide variable-width tables keep their fast path.
+  const bool want_hash  = hash && hash->kind != SRJ_HASH_NONE;
+  const bool split_hash = want_hash && SRJ_KNOB("SRJ_FUSE_SPLIT", 1) != 0;
+  const srj_fused_hash* fused = split_hash ? nullptr : hash;
+  auto hash_after = [&]() -> int {
+    if (!split_hash || num_rows == 0) return SRJ_OK;
+    srj_column keys[16];
+    for (int k = 0; k < hash->num_keys; ++k) keys[k] = cols[hash->key_columns[k]];
+    return launch_hash(hash->kind, keys, hash->num_keys, num_rows, hash->seed, hash->out, stream);
+  };
+  if (use_wide_from_rows(plan, row_offsets, fused)) {
     // wide variable-width table: per-row slabs; the pointer tables travel as kernel parameters and the kernels publish
     // null counts / totals / status themselves: no memset, no staging copy, no hidden allocation
     if (num_rows > 0 && !workspace) { set_error("convert_from_rows: this schema needs a workspace (srj_from_rows_workspace_bytes)"); return SRJ_EINVAL; }
-    return launch_from_rows_wide(plan, rows, row_offsets, rows_bytes, num_rows, cols, d_null_counts, d_char_totals, workspace,
-                                 SRJ_KNOB("SRJ_W_FINALIZE", 0) != 0, stream);
+    rc = launch_from_rows_wide(plan, rows, row_offsets, rows_bytes, num_rows, cols, d_null_counts, d_char_totals, workspace,
+                               SRJ_KNOB("SRJ_W_FINALIZE", 0) != 0, stream);
+    return rc != SRJ_OK ? rc : hash_after();
   }
   if (d_null_counts) SRJ_CUDA_TRY(cudaMemsetAsync(d_null_counts, 0, sizeof(int64_t) * nc, stream));
   if (d_char_totals) SRJ_CUDA_TRY(cudaMemsetAsync(d_char_totals, 0, sizeof(int64_t) * (nc + 1), stream));
@@ -549,7 +563,7 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
   if (rc != SRJ_OK) return rc;
   auto** d = static_cast<void**>(sc.dev());
   rc = launch_from_rows(plan, rows, row_offsets, rows_bytes, num_rows, d, reinterpret_cast<uint32_t* const*>(d + nent),
-                        d_null_counts, d_char_totals ? d_char_totals + nc : nullptr, hash, stream);
+                        d_null_counts, d_char_totals ? d_char_totals + nc : nullptr, fused, stream);
   if (rc != SRJ_OK) return rc;
   if (nstr > 0) {
     uint8_t* tail = static_cast<uint8_t*>(sc.dev()) + tab_bytes;
@@ -557,7 +571,7 @@ int srj_convert_from_rows_fixed(const srj_plan* plan, const uint8_t* rows, const
                                     d_char_totals, d_char_totals ? d_char_totals + nc : nullptr, tail, plan->wide.enabled, stream);
     if (rc != SRJ_OK) return rc;
   }
-  return SRJ_OK;
+  return hash_after();
 }
 
 int srj_convert_from_rows_strings(const srj_plan* plan, const uint8_t* rows, const int32_t* row_offsets,
