@@ -853,6 +853,7 @@ int srj_kudo_split_sizes(const srj_column* cols, int32_t num_columns, int64_t nu
     if (cols[c].size != num_rows) { set_error("kudo_split_sizes: column %d: row count mismatch", c); return SRJ_EINVAL; }
   rc = launch_kudo_split_sizes(cols, num_columns, d_splits, num_partitions, d_partition_offsets, total_bytes, workspace, static_cast<cudaStream_t>(stream));
   if (rc == SRJ_EUNSUPPORTED) set_error("kudo_split_sizes: only fixed-width, decimal and STRING columns");
+  else if (rc == SRJ_EOVERFLOW) set_error("kudo_split_sizes: a partition exceeds the 32-bit section lengths of the Kudo header, or the splits are not increasing");
   return rc;
 }
 

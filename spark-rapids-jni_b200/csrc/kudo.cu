@@ -83,7 +83,7 @@ __device__ void cta_copy_bytes(uint8_t* __restrict__ dst, const uint8_t* __restr
 
 // ---- split ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kudo_split_sizes_kernel(const KCol* __restrict__ cols, int ncols, const int32_t* __restrict__ splits, int P,
-                                                              int64_t* __restrict__ part_sizes)
+                                                              int64_t* __restrict__ part_sizes, int32_t* __restrict__ bad)
 {
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= P) return;
@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(256) kudo_split_sizes_kernel(const KCol* __res
   }
   const int hs  = kudo_header_bytes(ncols);
   part_sizes[p] = pad4(hs + V) + pad4(O) + pad4(D);
+  // the header holds the section lengths as 32-bit integers (KudoTableHeaderCalc.java:70-77: toIntExact)
+  if (n < 0 || pad4(hs + V) - hs + pad4(O) + pad4(D) > INT32_MAX) atomicExch(bad, 1);
 }
 
 // exclusive scan of P + 1 int64 in place by one CTA (P <= a few 10^4); element P receives the total
@@ -392,12 +394,15 @@ int launch_kudo_split_sizes(const srj_column* cols, int32_t ncols, const int32_t
   int nstr = 0;
   const int rc = kudo_upload(cols, ncols, ws, &nstr, stream);
   if (rc != SRJ_OK) return rc;
-  kudo_split_sizes_kernel<<<(P + 255) / 256, 256, 0, stream>>>(ws.cols, ncols, d_splits, P, d_part_offsets);
+  SRJ_CUDA_TRY(cudaMemsetAsync(ws.bad, 0, 4, stream));
+  kudo_split_sizes_kernel<<<(P + 255) / 256, 256, 0, stream>>>(ws.cols, ncols, d_splits, P, d_part_offsets, ws.bad);
   i64_scan_small_kernel<<<1, 1024, 0, stream>>>(d_part_offsets, P);
   SRJ_CUDA_TRY(cudaGetLastError());
+  int32_t bad = 0;
   SRJ_CUDA_TRY(cudaMemcpyAsync(h_total, d_part_offsets + P, 8, cudaMemcpyDeviceToHost, stream));
+  SRJ_CUDA_TRY(cudaMemcpyAsync(&bad, ws.bad, 4, cudaMemcpyDeviceToHost, stream));
   SRJ_CUDA_TRY(cudaStreamSynchronize(stream));
-  return SRJ_OK;
+  return bad ? SRJ_EOVERFLOW : SRJ_OK;
 }
 
 int launch_kudo_split(const srj_column* cols, int32_t ncols, const int32_t* d_splits, int32_t P, const int64_t* d_part_offsets, uint8_t* out,

@@ -117,3 +117,5 @@ def test_malformed_header_is_rejected():
         KS.assembleFromDeviceRaw([S.DType(O.INT32)], torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda())
     with pytest.raises(S.CudfException):
         KS.splitAndSerializeToDevice(S.Table([S.ColumnView.makeStructView(G.to_device(cols[0]))]), [0, 100])
+    with pytest.raises(S.CudfColumnSizeOverflowException):                      # splits must be increasing
+        KS.splitAndSerializeToDevice(G.table_to_device(cols), [0, 60, 40, 100])
