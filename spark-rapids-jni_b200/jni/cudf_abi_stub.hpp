@@ -29,6 +29,8 @@ struct data_type {
   int32_t scale() const;
 };
 struct column_view {
+  column_view(data_type type, size_type size, void const* data, bitmask_type const* null_mask, size_type null_count, size_type offset = 0,
+              std::vector<column_view> const& children = {});
   data_type type() const;
   size_type size() const;
   size_type offset() const;

@@ -26,5 +26,10 @@ struct JNIEnv {
   void ReleaseLongArrayElements(jlongArray, jlong*, jint);
   jlongArray NewLongArray(jsize);
   void SetLongArrayRegion(jlongArray, jsize, jsize, const jlong*);
+  jintArray NewIntArray(jsize);
+  void SetIntArrayRegion(jintArray, jsize, jsize, const jint*);
+  struct _jmethodID* GetMethodID(jclass, const char*, const char*);
+  jobject NewObject(jclass, struct _jmethodID*, ...);
 };
+typedef struct _jmethodID* jmethodID;
 #define JNI_ABORT 2

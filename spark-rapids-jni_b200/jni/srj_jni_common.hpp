@@ -85,6 +85,7 @@ inline int32_t size_of_type(int32_t t)
 
 // blocking device -> host copy on `stream` (cudaMemcpyAsync + synchronize in the real build)
 bool copy_to_host(void* dst, const void* src, size_t bytes, rmm::cuda_stream_view stream);
+bool copy_from_host(void* dst, const void* src, size_t bytes, rmm::cuda_stream_view stream);
 
 template <typename T>
 jlong release_as_jlong(std::unique_ptr<T>&& p) { return reinterpret_cast<jlong>(p.release()); }   // jni_utils.hpp:34-46

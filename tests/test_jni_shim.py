@@ -1,5 +1,6 @@
 """The JNI shim sources (spark-rapids-jni_b200/jni/) compile against the stub JNI / cudf headers and define exactly
-the eight symbols of the reference's RowConversionJni.cpp:23-124 and hash/HashJni.cpp:26-79."""
+the symbols of the reference's RowConversionJni.cpp:23-124, hash/HashJni.cpp:26-79 and KudoGpuSerializerJni.cpp:22-140, plus the
+bindings of the two new plugin-side classes (HashPartition, UnsafeRowConversion)."""
 import os
 import shutil
 import subprocess
@@ -17,6 +18,13 @@ EXPECTED = {
                              "Java_com_nvidia_spark_rapids_jni_RowConversion_convertFromRowsFixedWidthOptimized"],
     "HashJni.cpp": ["Java_com_nvidia_spark_rapids_jni_Hash_getMaxStackDepth", "Java_com_nvidia_spark_rapids_jni_Hash_murmurHash32",
                     "Java_com_nvidia_spark_rapids_jni_Hash_xxhash64", "Java_com_nvidia_spark_rapids_jni_Hash_hiveHash"],
+    # kudo/KudoGpuSerializer.java's two natives (KudoGpuSerializerJni.cpp:22-140), flat schemas
+    "KudoGpuSerializerJni.cpp": ["Java_com_nvidia_spark_rapids_jni_kudo_KudoGpuSerializer_splitAndSerializeToDevice",
+                                 "Java_com_nvidia_spark_rapids_jni_kudo_KudoGpuSerializer_assembleFromDeviceRawNative"],
+    # new classes for the plugin-side steps (no reference counterpart): INTEGRATION.md 2c
+    "HashPartitionJni.cpp": ["Java_com_nvidia_spark_rapids_jni_HashPartition_hashPartition"],
+    "UnsafeRowConversionJni.cpp": ["Java_com_nvidia_spark_rapids_jni_UnsafeRowConversion_convertToRows",
+                                   "Java_com_nvidia_spark_rapids_jni_UnsafeRowConversion_convertFromRows"],
 }
 
 
