@@ -21,7 +21,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, k, q):
+def _worker(rank, world, port, k, q, base_rows=500):
+    os.environ["SRJ_TEST_ROWS"] = str(base_rows)
     for p in (ROOT, os.path.join(ROOT, "spark-rapids-jni_b200"), os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -35,7 +36,8 @@ def _worker(rank, world, port, k, q):
         from util import cols_equal, random_table
         types = [O.INT32, O.STRING, O.INT64, O.DECIMAL128]
         P = world * k
-        tables = [random_table(types, 500 + 37 * r, seed=50 + r) for r in range(world)]       # every rank can rebuild all inputs
+        nrows = [int(os.environ.get("SRJ_TEST_ROWS", 500)) + 37 * r for r in range(world)]
+        tables = [random_table(types, nrows[r], seed=50 + r) for r in range(world)]            # every rank can rebuild all inputs
         mine = tables[rank]
         ids = O.partition_ids([mine[0], mine[2]], P)
         pcols, poffs, _ = O.stable_partition(mine, ids, P)
@@ -63,14 +65,14 @@ def _worker(rank, world, port, k, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,k", [(2, 1), (2, 3), (3, 2)])
-def test_shuffle_exchange_over_gloo(world, k):
+@pytest.mark.parametrize("world,k,base_rows", [(2, 1, 500), (2, 3, 500), (3, 2, 500), (2, 16, 3)])     # last: more partitions than rows (empty partitions)
+def test_shuffle_exchange_over_gloo(world, k, base_rows):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, k, q, base_rows)) for r in range(world)]
     [p.start() for p in procs]
     res = [q.get(timeout=180) for _ in range(world)]
     [p.join(timeout=60) for p in procs]
     assert all(ok for _, ok, _ in res), res
-    assert sum(n for _, _, n in res) == sum(500 + 37 * r for r in range(world))      # every row arrived exactly once
+    assert sum(n for _, _, n in res) == sum(base_rows + 37 * r for r in range(world))      # every row arrived exactly once
