@@ -955,6 +955,70 @@ def cpu_baseline(types, row_size, h_rows_np, sample_rows, bpr, steps=None, nthre
             "ms_per_pass": sec * 1e3}
 
 
+def synth_columns_host(types, n, null_frac, seed):
+    """The host twin of synth_columns_gpu for the CPU baselines of the 8(f) workloads (fixed-width columns)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(seed)
+    cols = []
+    for t in types:
+        data = rng.integers(0, 256, n * SIZE[t], dtype=np.uint8)
+        if t == BOOL8:
+            data &= 1
+        cols.append(O.HCol(t, data, O.pack_mask(rng.random(n) >= null_frac), None, 0, n))
+    return cols
+
+
+def cpu_baseline_f(kind, types, null_frac, n, hash_keys=None, P=200):
+    """Single-core numpy / C-oracle port of one 8(f) step on a bounded sample of the same workload (rank 0, N = 1):
+    kind = partition (murmur3 ids + stable argsort + take of every column), kudo_split, kudo_assemble,
+    unsafe_to / unsafe_from (fixed-width rows)."""
+    from oracle import kudo as K
+    from oracle import oracle as O
+    from oracle import unsafe_row as U
+    cols = synth_columns_host(types, n, null_frac, 42)
+    splits = np.linspace(0, n, P + 1).astype(np.int64)
+    if kind == "kudo_assemble":
+        buf, offs = K.split(cols, splits)
+    if kind == "unsafe_from":
+        rows = U.to_unsafe_rows_fixed(cols)
+        bs = U.bitset_bytes(len(types))
+
+    def once():
+        if kind == "partition":
+            ids = O.partition_ids([cols[i] for i in hash_keys], P, 42)
+            return O.stable_partition(cols, ids, P)
+        if kind == "kudo_split":
+            return K.split(cols, splits)
+        if kind == "kudo_assemble":
+            return K.assemble(buf, offs, types)
+        if kind == "unsafe_to":
+            return U.to_unsafe_rows_fixed(cols)
+        out = []                                        # unsafe_from: slots -> columns + masks
+        for f, t in enumerate(types):
+            out.append(np.ascontiguousarray(rows[:, bs + 8 * f: bs + 8 * f + SIZE[t]]))
+            out.append(np.packbits(((rows[:, f // 64 * 8 + (f % 64) // 8] >> (f % 8)) & 1) ^ 1, bitorder="little"))
+        return out
+
+    once()
+    times = []
+    while sum(times) < 8.0 and len(times) < 10:
+        t0 = time.perf_counter()
+        once()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": n / best, "unit": "rows/s", "cores": 1, "kind": "port",
+            "sample": f"{n} rows of the same workload, best of {len(times)} passes, one core: numpy restatement of the step "
+                      f"(oracle/oracle.py, oracle/kudo.py, oracle/unsafe_row.py; murmur3 in oracle/srj_oracle.c)",
+            "ms_per_pass": best * 1e3}
+
+
+def _cpu_f(kind, wl, n, **kw):
+    try:
+        return cpu_baseline_f(kind, wl["types"], wl["null_frac"], n, **kw)
+    except Exception as e:                               # the baseline must never take the bench line down
+        return {"value": None, "unit": "rows/s", "cores": 1, "kind": "port", "sample": f"failed: {e!r}"}
+
+
 def run_partition(args, wl, rank, world):
     """Spark HashPartitioning step on one GPU: ids + stable partition maps + moving every column, inputs resident in HBM."""
     import ctypes as C
@@ -1020,7 +1084,7 @@ def run_partition(args, wl, rank, world):
                       "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
                                    "traffic": None, "kernel": "whole step: murmur3 + ids/histogram + scan + ranks + 23 column scatters + 23 mask gathers",
                                    "algorithmic_bytes_per_row": bpr, "peak_source": peak_src, "plan_only_ms": plan_ms},
-                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
+                      "cpu_baseline": _cpu_f("partition", wl, 4_000_000, hash_keys=wl["hash_keys"], P=P), "e2e": None, "gpu_launches": args.steps * (6 + 2 * len(types)), "clocks": clocks}))
 
 
 def run_shuffle(args, wl, rank, world):
@@ -1153,7 +1217,7 @@ def run_kudo(args, wl, rank, world):
                                                       "l2": "table 9.6 GB + buffer 9.9 GB >> 126 MB L2"},
                       "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": None,
                                    "kernel": f"kudo_{what}_kernel", "algorithmic_bytes_per_row": bpr, "peak_source": peak_src},
-                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
+                      "cpu_baseline": _cpu_f("kudo_" + what, wl, 4_000_000, P=P), "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
 
 
 def run_unsafe(args, wl, rank, world):
@@ -1219,7 +1283,7 @@ def run_unsafe(args, wl, rank, world):
                       "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
                                    "traffic": None, "kernel": "ur_to_rows_kernel" if args.direction == "to_rows" else "ur_from_rows_kernel",
                                    "algorithmic_bytes_per_row": bpr, "peak_source": peak_src},
-                      "cpu_baseline": None, "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
+                      "cpu_baseline": _cpu_f("unsafe_to" if args.direction == "to_rows" else "unsafe_from", wl, 2_000_000), "e2e": None, "gpu_launches": args.steps, "clocks": clocks}))
 
 
 def run_reference(args, wl, rank, world):

@@ -66,3 +66,10 @@ def test_round_trip():
     back = U.from_unsafe_rows(data, offs, types)
     for a, b in zip(cols, back):
         assert cols_equal(a, b)
+
+
+def test_vectorised_fixed_width_form_equals_the_loop():
+    types = [O.INT8, O.INT16, O.INT32, O.INT64, O.FLOAT32, O.FLOAT64, O.BOOL8, O.DECIMAL32, O.DECIMAL64] * 8     # 72 fields: two bitset words
+    cols = random_table(types, 257, seed=13)
+    _, data = U.to_unsafe_rows(cols)
+    assert np.array_equal(U.to_unsafe_rows_fixed(cols).reshape(-1), data)
