@@ -827,6 +827,7 @@ int srj_convert_from_unsafe_rows_strings(const uint8_t* rows, const int32_t* d_r
 {
   SRJ_API_RANGE();
   if (num_columns <= 0 || num_rows < 0 || !out || (num_rows > 0 && (!rows || !d_row_offsets))) { set_error("convert_from_unsafe_rows_strings: bad argument"); return SRJ_EINVAL; }
+  if (reinterpret_cast<uintptr_t>(rows) & 7) { set_error("convert_from_unsafe_rows_strings: rows must be 8-byte aligned"); return SRJ_EINVAL; }
   return launch_unsafe_from_rows_strings(out, num_columns, num_rows, rows, d_row_offsets, static_cast<cudaStream_t>(stream));
 }
 
